@@ -1,0 +1,141 @@
+/* mauv_b200 — C-ABI of the B200-native Monte-Carlo Bayesian hot path of Multimodal-AUV.
+ *
+ * The reference (sams-tom/Multimodal-AUV) is pure Python and has no FFI of its own; the
+ * hot path lives behind two Python surfaces: the bayesian-torch layer
+ * library (dnn_to_bnn / get_kl_loss / *Reparameterization.forward) and the five driver
+ * functions in train/multimodal.py, train/unimodal.py, inference/predictors.py. Each entry
+ * point below cites the reference code whose arithmetic it replaces. The Python package
+ * `mauv` binds these symbols with ctypes (multimodal-auv_b200/mauv/_lib.py) and mirrors
+ * the reference's Python API on top.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero (MAUV_ERR_*) on failure; the message is
+ *    in mauv_last_error() (thread local). No C++ exception crosses this boundary.
+ *  - all tensor pointers are caller-owned DEVICE pointers on the current CUDA device; the
+ *    library never allocates or frees device memory and keeps no pointer past return.
+ *  - `stream` is a cudaStream_t (CUstream). Work is only enqueued, never synchronised.
+ *  - activations are NHWC fp16, parameters fp32 in the PyTorch layout ([Cout][Cin][kh][kw],
+ *    [out][in]), accumulation and statistics fp32 (fp64 where noted).
+ *  - requires an sm_100a device (mauv_device_check); there is no fallback of any kind.
+ */
+#ifndef MAUV_B200_H
+#define MAUV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  MAUV_OK = 0,
+  MAUV_ERR_BAD_ARG = 1,
+  MAUV_ERR_CUDA = 2,
+  MAUV_ERR_UNSUPPORTED_ARCH = 3,
+  MAUV_ERR_DRIVER = 4
+};
+
+/* ---- runtime ---------------------------------------------------------------------- */
+int mauv_version(void);
+const char* mauv_last_error(void);
+int mauv_device_check(void);
+int mauv_num_sms_c(void);
+
+/* ---- K1 operand staging: w = mu + log1p(exp(rho)) * eps ---------------------------------
+ * Replaces bayesian-torch 0.5.0 Conv2dReparameterization.forward / LinearReparameterization
+ * .forward lines "sigma_weight = log1p(exp(rho)); eps = eps.normal_(); weight = mu + sigma*eps"
+ * (layers installed by reference models/model_utils.py:26-35).
+ * Writes G sampled copies of ONE layer, fp16, [G][cout][k_pad] with K ordered (kh, kw, cin)
+ * and zero padded to k_pad (multiple of 8). eps: injected [G][cout*cin*kh*kw] (PyTorch
+ * element order) or NULL -> Philox4x32-10, counter (elem/4, sample0+g, layer_id), key seed. */
+int mauv_sample_weights_f16(const float* mu, const float* rho, const float* eps, uint64_t seed,
+                            uint32_t layer_id, uint32_t sample0, int G, int cout, int cin, int kh,
+                            int kw, int k_pad, void* w_out, void* stream);
+/* fp32 sampled vector (biases): out[g][i] = mu[i] + log1p(exp(rho[i])) * eps[g][i]. */
+int mauv_sample_vector_f32(const float* mu, const float* rho, const float* eps, uint64_t seed,
+                           uint32_t layer_id, uint32_t sample0, int G, int n, float* out, void* stream);
+/* The N(0,1) stream itself (Philox + Box-Muller), for cross-checking oracle/philox.py. */
+int mauv_philox_normal_f32(uint64_t seed, uint32_t layer_id, uint32_t sample_id, long long n,
+                           float* out, void* stream);
+
+/* ---- K1 contraction: tcgen05 implicit-GEMM conv / GEMM, grouped over MC samples ---------
+ * Replaces F.conv2d(input, weight, None, stride, padding) / F.linear in the same forward
+ * functions, called per MC pass from models/base_models.py:74-90 (torchvision resnet.py
+ * Bottleneck.forward :143-165). y[g] = A[g] * W[g]^T, fp16 in, fp32 accumulate, fp16 out.
+ * stats_partial (nullable): [G][mauv_gemm_m_tiles(M)][N][2] fp32 per-tile (sum, sum of squares)
+ * of the fp32 accumulators = the BatchNorm batch statistics, reduced by mauv_bn_finalize. */
+int mauv_gemm_m_tiles(long long M);
+/* A: [G][M][K] row-major fp16 (a_sample_stride elements between samples; 0 = one A shared by
+ * all samples, e.g. the stem's im2col matrix). W: [G][N][K]. bias (nullable): [G][N] fp32. */
+int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const void* bias,
+                  void* y, float* stats_partial, int G, long long M, int N, int K, void* stream);
+/* x: [G*imgs_per_sample][H][W][Cin] NHWC fp16, fetched with im2col-mode TMA (Cin % 64 == 0);
+ * W: [G][Cout][kh*kw*Cin]; y: [G*imgs_per_sample][Ho][Wo][Cout]. */
+int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,
+                           int imgs_per_sample, int H, int W, int Cin, int Cout, int kh, int kw,
+                           int stride, int pad, void* stream);
+
+/* ---- K3: BatchNorm(train) / ReLU / residual / pooling ------------------------------------
+ * Replaces nn.BatchNorm2d in training mode (the reference keeps .train() on for every MC
+ * pass: inference/predictors.py:27, train/multimodal.py:60,232), ReLU, the residual add,
+ * MaxPool2d(3,2,1) and AdaptiveAvgPool2d(1) of torchvision resnet.py:266-282. */
+/* x: NCHW fp32 [B][C][H][W] -> explicit im2col matrix [B*Ho*Wo][k_pad] fp16 for the 7x7/2 stem. */
+int mauv_stem_im2col_f16(const float* x_nchw, int B, int C, int H, int W, int kh, int kw, int stride,
+                         int pad, int k_pad, void* out, void* stream);
+long long mauv_bn_finalize_ws_bytes(int G, int m_tiles, int C);
+/* scale_shift: [G][C][2] fp32 (y*scale+shift == gamma*(y-mean)/sqrt(var+eps)+beta, biased var);
+ * running_mean/var (nullable) receive the G sequential momentum updates (unbiased var) the
+ * reference's G passes would apply; batch_stats (nullable): [G][C][2] = (mean, biased var). */
+int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long long count,
+                     const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, float* scale_shift, float* batch_stats,
+                     void* ws, void* stream);
+/* out = relu?( y*ss + [residual] + [y2*ss2] ), all [G][M][C] fp16. */
+int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residual, const void* y2,
+                    const float* scale_shift2, int relu, int G, long long M, int C, void* out, void* stream);
+int mauv_bn_relu_maxpool_f16(const void* y, const float* scale_shift, int G, int imgs_per_sample, int H,
+                             int W, int C, void* out, void* stream);
+int mauv_avgpool_f16(const void* x, long long N, int HW, int C, float* out, void* stream);
+int mauv_nchw_f32_to_nhwc_f16(const float* x, long long N, int C, int HW, int c_pad, void* out, void* stream);
+int mauv_nhwc_f16_to_nchw_f32(const void* x, long long N, int C, int HW, float* out, void* stream);
+
+/* ---- K2: fusion head (sampling fused into operand staging, fp32) --------------------------
+ * Replaces LinearReparameterization.forward for AdditiveAttention (models/base_models.py:35-52)
+ * and fc/fc1/fc2 (:60-65,86-89): y[g] = x[g] * (mu_w + sp(rho_w)*eps_w[g])^T + (mu_b + sp(rho_b)*eps_b[g]).
+ * Bias Philox stream uses layer_id | 0x80000000. */
+int mauv_sampled_linear_f32(const float* x, long long x_sample_stride, int ldx, const float* mu_w,
+                            const float* rho_w, const float* eps_w, const float* mu_b, const float* rho_b,
+                            const float* eps_b, uint64_t seed, uint32_t layer_id, uint32_t sample0, int G,
+                            int B, int in_features, int out_features, float* y, long long y_sample_stride,
+                            int ldy, void* stream);
+/* tanh(queries + keys)                              models/base_models.py:47 */
+int mauv_tanh_add_f32(const float* a, const float* b, long long n, float* out, void* stream);
+/* values * softmax(score, dim=1), row stride ld_out    models/base_models.py:48-51 */
+int mauv_softmax_gate_f32(const float* score, const float* v, long long rows, int n, float* out,
+                          int ld_out, void* stream);
+
+/* ---- K5: MC predictive statistics over logits[S][B][C] -------------------------------------
+ * Replaces inference/predictors.py:65-84, train/multimodal.py:287-310, train/unimodal.py:282-308.
+ * Any output pointer may be NULL. var_mean = torch.var(p, dim=0).mean(dim=1) (unbiased; S=1 -> NaN),
+ * entropies use log(p + eps_entropy) (1e-7 predictor/unimodal, 1e-8 multimodal eval),
+ * mutual_info = pred_entropy - aleatoric, argmax = first maximum. dtype: 0 = fp32. */
+int mauv_mc_reduce(const void* logits, int S, long long B, int C, int dtype, float eps_entropy,
+                   float* mean_prob, float* mean_logit, long long* argmax_prob, long long* argmax_logit,
+                   float* pred_entropy, float* aleatoric, float* mutual_info, float* var_mean, void* stream);
+
+/* ---- K4: KL(q||p) forward + gradient --------------------------------------------------------
+ * Replaces bayesian-torch BaseVariationalLayer_.kl_div (per-tensor .mean()) summed over layers by
+ * get_kl_loss (train/multimodal.py:114,284; train/unimodal.py:130,262) and its autograd backward.
+ * table_dev: device array of n_tensors records {mu*, rho*, grad_mu* (nullable), grad_rho*, n} as
+ * five int64; chunk_prefix_dev[t] = sum_{u<t} ceil(n_u / mauv_kl_chunk_elems()).
+ * kl_out = sum_t mean_i kl(mu_i, softplus(rho_i)); grads += grad_scale * dKL/d(mu, rho). */
+int mauv_kl_chunk_elems(void);
+long long mauv_kl_ws_bytes(void);
+int mauv_kl_fwd_bwd(const void* table_dev, const long long* chunk_prefix_dev, int n_tensors,
+                    long long total_chunks, float prior_mu, float prior_sigma, float grad_scale,
+                    float* kl_out, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUV_B200_H */

@@ -1,0 +1,471 @@
+// K1: grouped (per-MC-sample) implicit-GEMM convolution / plain GEMM on the
+// Blackwell tensor cores.
+//
+//   Y[g][m][n] = sum_k A[g][m][k] * W[g][n][k]       fp16 in, fp32 accumulate in TMEM
+//
+// A is either a plain row-major [M,K] matrix (1x1/stride-1 convs, linear layers,
+// the explicit im2col matrix of the 7x7 stem) fetched with tiled TMA, or an
+// NHWC activation tensor fetched with *im2col-mode* TMA (3x3 and strided convs):
+// the K loop then walks (filter tap r, s) x (64-channel block). W[g] is the g-th
+// Monte-Carlo sample of the layer's weights (sample_weights.cu writes it in the
+// same (r, s, c) K order). The reference does the same contraction with
+// F.conv2d / F.linear per MC pass (bayesian-torch conv_variational.py forward;
+// called from models/base_models.py:74-90 through torchvision resnet.py:143-165).
+//
+// Structure (one persistent CTA per SM, 8 warps):
+//   warp 0      TMA producer   (one elected lane), kStages-deep smem ring
+//   warp 1      MMA issuer     (one elected lane), tcgen05.mma 128 x BN x 16
+//   warp 2      TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4..7  epilogue: tcgen05.ld -> fp16 store + per-channel sum / sum-of-squares
+//               (the BatchNorm batch statistics of the reference's BN-train pass)
+// Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x) with the
+// n-tile fastest so that CTAs running concurrently share their A tile in L2.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;      // rows per tile  (UMMA M)
+constexpr int BK = 64;       // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // fixed for 16-bit inputs
+
+struct GemmParams {
+  int M;            // rows per sample
+  int N;            // output channels
+  int k_blocks;     // ceil(K / 64)
+  int G;            // samples in this launch
+  int m_tiles, n_tiles;
+  long long total_tiles;
+  int a_mode;       // 0 = tiled [K, M, G] ; 1 = im2col (C, W, H, N)
+  int a_batch_mul;  // 0 when A is shared by all samples (stem), else 1
+  // im2col geometry
+  int Wo, Ho, imgs_per_sample, stride, pad, kw, c_blocks;
+  // outputs
+  __half* y;             // [G][M][N]
+  float* stats;          // [G][m_tiles][N][2] or nullptr
+  const float* bias;     // [G][N] or nullptr (sampled bias, linear layers)
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kStatBytes + kBarBytes;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t tiles_base = smem_base;
+  float* stat_smem = reinterpret_cast<float*>(smem_gen + kStages * L::kStageBytes);
+  const uint32_t bar_base = smem_base + kStages * L::kStageBytes + L::kStatBytes;
+  // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + kStages * L::kStageBytes + L::kStatBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kTmemCols>(tmem_ptr_addr);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const long long tiles_per_sample = static_cast<long long>(p.m_tiles) * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int g = static_cast<int>(tile / tiles_per_sample);
+        const long long rem = tile - g * tiles_per_sample;
+        const int m_tile = static_cast<int>(rem / p.n_tiles);
+        const int n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+        const int m0 = m_tile * BM;
+        // im2col start pixel of this tile
+        int iq = 0, ip = 0, in_ = 0;
+        if (p.a_mode == 1) {
+          const int hw = p.Ho * p.Wo;
+          const int b = m0 / hw;
+          const int r2 = m0 - b * hw;
+          ip = r2 / p.Wo;
+          iq = r2 - ip * p.Wo;
+          in_ = g * p.imgs_per_sample + b;
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = tiles_base + stage * L::kStageBytes;
+          const uint32_t b_dst = a_dst + L::kABytes;
+          mbar_expect_tx(full_bar(stage), L::kStageBytes);
+          if (p.a_mode == 0) {
+            tma_load_3d(a_dst, &tmA, full_bar(stage), kb * BK, m0, g * p.a_batch_mul);
+          } else {
+            const int tap = kb / p.c_blocks;
+            const int cb = kb - tap * p.c_blocks;
+            const int r = tap / p.kw;
+            const int s = tap - r * p.kw;
+            tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), cb * BK, iq * p.stride - p.pad,
+                               ip * p.stride - p.pad, in_, static_cast<uint16_t>(s),
+                               static_cast<uint16_t>(r));
+          }
+          tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, g);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = tiles_base + stage * L::kStageBytes;
+          const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+            umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // TMEM lane quarter accessible to this warp (warp_id % 4)
+    const uint32_t lane = lane_id();
+    const int et = threadIdx.x - 128;  // 0..127
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int g = static_cast<int>(tile / tiles_per_sample);
+      const long long rem = tile - g * tiles_per_sample;
+      const int m_tile = static_cast<int>(rem / p.n_tiles);
+      const int n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int row = m_tile * BM + ew * 32 + static_cast<int>(lane);
+      const bool row_ok = row < p.M;
+      const int n0 = n_tile * BN;
+      __half* yrow = p.y + (static_cast<long long>(g) * p.M + row) * p.N + n0;
+      const float* bias = p.bias ? p.bias + static_cast<long long>(g) * p.N + n0 : nullptr;
+      float* stat_buf = stat_smem + (it & 1u) * (4 * BN * 2);
+
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(ew * 32) << 16), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c * 32 + j < p.N) v[j] += bias[c * 32 + j];
+        }
+        // fp16 store: 32 consecutive channels of one output pixel = 64 bytes
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n0 + c * 32 + q * 8 < p.N) {
+              uint4 pk;
+              __half2 h0 = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]);
+              __half2 h1 = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
+              __half2 h2 = __floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]);
+              __half2 h3 = __floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(yrow + c * 32 + q * 8) = pk;
+            }
+          }
+        }
+        if (p.stats) {
+          // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends
+          // with the sum of column c*32+j. Rows past M (next sample's pixels in im2col
+          // mode / zero fill in tiled mode) are excluded.
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = row_ok ? v[j] : 0.f;
+            s1[j] = x;
+            s2[j] = x * x;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send1 = upper ? s1[i] : s1[i + off];
+              const float send2 = upper ? s2[i] : s2[i + off];
+              const float recv1 = __shfl_xor_sync(0xffffffffu, send1, off);
+              const float recv2 = __shfl_xor_sync(0xffffffffu, send2, off);
+              s1[i] = (upper ? s1[i + off] : s1[i]) + recv1;
+              s2[i] = (upper ? s2[i + off] : s2[i]) + recv2;
+            }
+          }
+          stat_buf[(ew * BN + c * 32 + lane) * 2 + 0] = s1[0];
+          stat_buf[(ew * BN + c * 32 + lane) * 2 + 1] = s2[0];
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+
+      if (p.stats) {
+        // combine the 4 epilogue warps and emit one deterministic partial per (tile, channel)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = et; j < BN; j += 128) {
+          if (n0 + j < p.N) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              a += stat_buf[(w * BN + j) * 2 + 0];
+              b += stat_buf[(w * BN + j) * 2 + 1];
+            }
+            float2* dst = reinterpret_cast<float2*>(p.stats) +
+                          (static_cast<long long>(g) * p.m_tiles + m_tile) * p.N + n0 + j;
+            *dst = make_float2(a, b);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side: tensor-map encoding through the driver entry points (no -lcuda).
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled g_encode_tiled = nullptr;
+PFN_encodeIm2col g_encode_im2col = nullptr;
+
+int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return MAUV_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return mauv_set_error(MAUV_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return mauv_set_error(MAUV_ERR_DRIVER, "cuTensorMapEncodeIm2col not available from the driver");
+  g_encode_im2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+  return MAUV_OK;
+}
+
+// [G][rows][K] fp16 row-major, box = 64 x box_rows x 1, 128B swizzle.
+int make_tiled_map(CUtensorMap* tm, const void* base, int64_t K, int64_t rows, int64_t G,
+                   int64_t sample_stride_elems, int box_rows) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(G)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2,
+                           static_cast<cuuint64_t>(sample_stride_elems) * 2};
+  if (G == 1) strides[1] = static_cast<cuuint64_t>(K) * 2 * static_cast<cuuint64_t>(rows);
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return mauv_set_error(MAUV_ERR_DRIVER,
+                          "cuTensorMapEncodeTiled failed (%d) K=%lld rows=%lld G=%lld stride=%lld",
+                          (int)r, (long long)K, (long long)rows, (long long)G,
+                          (long long)sample_stride_elems);
+  return MAUV_OK;
+}
+
+// NHWC fp16 activations seen as (C, W, H, N) in im2col mode: 64 channels x 128 output pixels.
+int make_im2col_map(CUtensorMap* tm, const void* base, int64_t C, int64_t W, int64_t H, int64_t N,
+                    int kh, int kw, int stride, int pad) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
+                        static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(C) * 2 * W,
+                           static_cast<cuuint64_t>(C) * 2 * W * H};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
+                               strides, lower, upper, BK, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return mauv_set_error(MAUV_ERR_DRIVER,
+                          "cuTensorMapEncodeIm2col failed (%d) C=%lld W=%lld H=%lld N=%lld k=%dx%d s=%d p=%d",
+                          (int)r, (long long)C, (long long)W, (long long)H, (long long)N, kh, kw,
+                          stride, pad);
+  return MAUV_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
+  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 256, L::kTotal, stream>>>(tmA, tmB, p);
+  MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
+  return MAUV_OK;
+}
+
+int pick_bn(int N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  const int bn = pick_bn(p.N);
+  p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
+  p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
+  p.total_tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.G;
+  if (p.total_tiles == 0) return MAUV_OK;
+  switch (bn) {
+    case 64: return launch_gemm<64>(tmA, tmB, p, stream);
+    case 128: return launch_gemm<128>(tmA, tmB, p, stream);
+    default: return launch_gemm<256>(tmA, tmB, p, stream);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Number of 128-row tiles per sample: the leading dimension of the BN partial-statistics buffer.
+int mauv_gemm_m_tiles(long long M) { return static_cast<int>(ceil_div_i64(M, BM)); }
+
+int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const void* bias,
+                  void* y, float* stats_partial, int G, long long M, int N, int K, void* stream) {
+  MAUV_CHECK_ARG(a && w && y, "mauv_gemm_f16: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 8 && K >= 8, "mauv_gemm_f16: bad shape G=%d M=%lld N=%d K=%d", G, M, N, K);
+  MAUV_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "mauv_gemm_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  MAUV_CHECK_ARG(a_sample_stride % 8 == 0, "mauv_gemm_f16: sample stride must be a multiple of 8 elements");
+  MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0, "mauv_gemm_f16: pointers must be 16-byte aligned");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  const bool shared_a = (a_sample_stride == 0);
+  if (int rc = make_tiled_map(&tmA, a, K, M, shared_a ? 1 : G, shared_a ? M * K : a_sample_stride, BM)) return rc;
+  if (int rc = make_tiled_map(&tmB, w, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.k_blocks = static_cast<int>(ceil_div_i64(K, BK));
+  p.G = G;
+  p.a_mode = 0;
+  p.a_batch_mul = shared_a ? 0 : 1;
+  p.y = static_cast<__half*>(y);
+  p.stats = stats_partial;
+  p.bias = static_cast<const float*>(bias);
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,
+                           int imgs_per_sample, int H, int W, int Cin, int Cout, int kh, int kw,
+                           int stride, int pad, void* stream) {
+  MAUV_CHECK_ARG(x && w && y, "mauv_conv2d_im2col_f16: null pointer");
+  MAUV_CHECK_ARG(Cin % 64 == 0, "mauv_conv2d_im2col_f16: Cin must be a multiple of 64 (got %d)", Cin);
+  MAUV_CHECK_ARG(Cout % 8 == 0, "mauv_conv2d_im2col_f16: Cout must be a multiple of 8 (got %d)", Cout);
+  MAUV_CHECK_ARG(stride >= 1 && stride <= 8 && pad >= 0 && kh >= 1 && kw >= 1, "mauv_conv2d_im2col_f16: bad geometry");
+  const int Ho = (H + 2 * pad - kh) / stride + 1;
+  const int Wo = (W + 2 * pad - kw) / stride + 1;
+  MAUV_CHECK_ARG(Ho >= 1 && Wo >= 1, "mauv_conv2d_im2col_f16: empty output");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_im2col_map(&tmA, x, Cin, W, H, static_cast<int64_t>(G) * imgs_per_sample, kh, kw, stride, pad)) return rc;
+  const int K = kh * kw * Cin;
+  if (int rc = make_tiled_map(&tmB, w, K, Cout, G, static_cast<int64_t>(Cout) * K, pick_bn(Cout))) return rc;
+  GemmParams p{};
+  p.M = imgs_per_sample * Ho * Wo;
+  p.N = Cout;
+  p.k_blocks = K / BK;
+  p.G = G;
+  p.a_mode = 1;
+  p.a_batch_mul = 1;
+  p.Wo = Wo; p.Ho = Ho; p.imgs_per_sample = imgs_per_sample;
+  p.stride = stride; p.pad = pad; p.kw = kw; p.c_blocks = Cin / BK;
+  p.y = static_cast<__half*>(y);
+  p.stats = stats_partial;
+  p.bias = nullptr;
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

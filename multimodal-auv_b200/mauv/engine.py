@@ -1,0 +1,241 @@
+"""S-batched Monte-Carlo forward engine: the B200 execution plan behind the reference's S-pass loops
+
+    for s in range(S): model(img, bathy, sss)      (inference/predictors.py:54-66,
+                                                    train/multimodal.py:107-118, 280-285,
+                                                    train/unimodal.py:127-131, 259-264)
+
+Instead of S sequential full-network passes of ~1000 small ATen launches each, the engine walks the
+network ONCE per group of G samples: for every Bayesian layer it samples G weight copies
+(w = mu + softplus(rho)*eps, Philox in-kernel or injected eps) into a small fp16 operand buffer and runs
+one grouped tcgen05 implicit-GEMM over all G samples; BatchNorm uses per-(sample, channel) batch
+statistics accumulated in the GEMM epilogue (the reference keeps BN in train mode for every MC pass).
+Activations are NHWC fp16, statistics and the fusion head fp32. All compute is libmauv_b200.so.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .bayesian import bayesian_layers, current_seed
+
+F16, F32 = torch.float16, torch.float32
+
+
+def _one(v):
+    return v[0] if isinstance(v, (tuple, list)) else v
+
+
+@dataclass
+class _Conv:
+    name: str
+    layer: nn.Module
+    layer_id: int
+    cin: int
+    cout: int
+    k: int
+    stride: int
+    pad: int
+
+
+@dataclass
+class _Block:
+    conv1: _Conv
+    bn1: nn.BatchNorm2d
+    conv2: _Conv
+    bn2: nn.BatchNorm2d
+    conv3: _Conv
+    bn3: nn.BatchNorm2d
+    down: Optional[_Conv] = None
+    down_bn: Optional[nn.BatchNorm2d] = None
+
+
+@dataclass
+class _Trunk:
+    stem: _Conv
+    stem_bn: nn.BatchNorm2d
+    blocks: List[_Block] = field(default_factory=list)
+    fc: Optional[tuple] = None   # (name, layer, layer_id) Bayesian Linear head of a unimodal ResNet50Custom
+
+
+class MCEngine:
+    """Execution plan for a (Bayesian) MultiModalModel or ResNet50Custom living on a CUDA device."""
+
+    def __init__(self, model: nn.Module, max_group: int = 8):
+        _lib.require_device()
+        if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
+            model = model.module
+        self.model = model
+        self.max_group = max_group
+        self.layer_ids: Dict[str, int] = {n: i for i, (n, _) in enumerate(bayesian_layers(model))}
+        self._by_module = {id(l): n for n, l in bayesian_layers(model)}
+        if hasattr(model, "image_model_feat"):
+            self.kind = "multimodal"
+            self.trunks = [self._plan_trunk(model.image_model_feat, "image_model_feat"),
+                           self._plan_trunk(model.bathy_model_feat, "bathy_model_feat"),
+                           self._plan_trunk(model.sss_model_feat, "sss_model_feat")]
+            self.attn = [model.attention_image, model.attention_bathy, model.attention_sss]
+        elif hasattr(model, "model") and hasattr(model.model, "layer1"):
+            self.kind = "unimodal"
+            self.trunks = [self._plan_trunk(model.model, "model")]
+        else:
+            raise _lib.MauvError("MCEngine supports the reference's MultiModalModel and ResNet50Custom topologies")
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise _lib.MauvError("MCEngine: move the model to a CUDA device first (there is no CPU path)")
+        self.device = p.device
+        self.launches = 0
+
+    # ------------------------------------------------------------------ planning
+    def _conv(self, layer: nn.Module, name: str) -> _Conv:
+        if not hasattr(layer, "mu_kernel"):
+            raise _lib.MauvError(f"{name}: expected a Bayesian conv (run dnn_to_bnn first)")
+        kh, kw = layer.kernel_size
+        assert kh == kw
+        if _one(layer.dilation) != 1 or layer.groups != 1 or layer.mu_bias is not None:
+            raise _lib.MauvError(f"{name}: unsupported conv configuration")
+        return _Conv(name, layer, self.layer_ids[name], layer.in_channels, layer.out_channels, kh,
+                     _one(layer.stride), _one(layer.padding))
+
+    def _plan_trunk(self, net: nn.Module, prefix: str) -> _Trunk:
+        t = _Trunk(self._conv(net.conv1, f"{prefix}.conv1"), net.bn1)
+        for li in range(1, 5):
+            stage = getattr(net, f"layer{li}")
+            for bi, b in enumerate(stage):
+                pre = f"{prefix}.layer{li}.{bi}"
+                blk = _Block(self._conv(b.conv1, pre + ".conv1"), b.bn1, self._conv(b.conv2, pre + ".conv2"), b.bn2,
+                             self._conv(b.conv3, pre + ".conv3"), b.bn3)
+                if b.downsample is not None:
+                    blk.down = self._conv(b.downsample[0], pre + ".downsample.0")
+                    blk.down_bn = b.downsample[1]
+                t.blocks.append(blk)
+        fc = getattr(net, "fc", None)
+        if fc is not None and hasattr(fc, "mu_weight"):
+            t.fc = (f"{prefix}.fc", fc, self.layer_ids[f"{prefix}.fc"])
+        return t
+
+    # ------------------------------------------------------------------ helpers
+    def _eps_w(self, eps, name, s0, G):
+        if eps is None:
+            return None
+        return eps[name]["w"][s0:s0 + G].to(self.device, F32, non_blocking=True).contiguous()
+
+    def _eps_b(self, eps, name, s0, G):
+        if eps is None or eps[name]["b"] is None:
+            return None
+        return eps[name]["b"][s0:s0 + G].to(self.device, F32, non_blocking=True).contiguous()
+
+    def _sample(self, c: _Conv, G, s0, eps, seed):
+        self.launches += 1
+        return ops.sample_weights_f16(c.layer.mu_kernel.detach(), c.layer.rho_kernel.detach(), G,
+                                      eps=self._eps_w(eps, c.name, s0, G), seed=seed, layer_id=c.layer_id, sample0=s0)
+
+    def _bn(self, stats, count, bn: nn.BatchNorm2d, G):
+        self.launches += 2 if stats.shape[1] > 64 else 1
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        track = bn.track_running_stats and bn.running_mean is not None
+        ss = ops.bn_finalize(stats, count, bn.weight.detach() if bn.weight is not None else None,
+                             bn.bias.detach() if bn.bias is not None else None, bn.eps, mom,
+                             bn.running_mean if track else None, bn.running_var if track else None)
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += G
+        return ss
+
+    def _conv_bn(self, c: _Conv, bn, x, G, B, s0, eps, seed):
+        """x: [G*B, H, W, Cin] fp16 -> raw conv output [G*B, Ho, Wo, Cout] fp16 + BN scale/shift [G, Cout, 2]."""
+        w = self._sample(c, G, s0, eps, seed)
+        NB, H, W, Cin = x.shape
+        self.launches += 1
+        if c.k == 1 and c.stride == 1 and c.pad == 0:
+            y, st = ops.gemm_f16(x.view(G, B * H * W, Cin), w, stats=True)
+            y = y.view(NB, H, W, c.cout)
+        else:
+            y, st = ops.conv2d_im2col_f16(x, w, G, c.k, c.k, c.stride, c.pad, stats=True)
+        count = y.numel() // (G * c.cout)
+        return y, self._bn(st, count, bn, G)
+
+    # ------------------------------------------------------------------ trunk
+    def _run_trunk(self, t: _Trunk, x_nchw: torch.Tensor, G: int, s0: int, eps, seed) -> torch.Tensor:
+        B = x_nchw.shape[0]
+        st = t.stem
+        a0 = ops.stem_im2col_f16(x_nchw, st.k, st.k, st.stride, st.pad)          # shared by all samples
+        w = self._sample(st, G, s0, eps, seed)
+        y, stats = ops.gemm_f16(a0, w, stats=True, shared_a=True)                # [G, B*Ho*Wo, 64]
+        self.launches += 2
+        Ho = (x_nchw.shape[2] + 2 * st.pad - st.k) // st.stride + 1
+        Wo = (x_nchw.shape[3] + 2 * st.pad - st.k) // st.stride + 1
+        ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
+        x = ops.bn_relu_maxpool_f16(y.view(G * B, Ho, Wo, st.cout), ss, G)
+        self.launches += 1
+        del y, a0
+        for blk in t.blocks:
+            y1, ss1 = self._conv_bn(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
+            a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
+            y2, ss2 = self._conv_bn(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
+            a2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True)
+            y3, ss3 = self._conv_bn(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
+            if blk.down is not None:
+                yd, ssd = self._conv_bn(blk.down, blk.down_bn, x, G, B, s0, eps, seed)
+                x = ops.bn_act_f16(y3, ss3, G, blk.conv3.cout, y2=yd, ss2=ssd, relu=True)
+            else:
+                x = ops.bn_act_f16(y3, ss3, G, blk.conv3.cout, residual=x, relu=True)
+            self.launches += 3
+        feat = ops.avgpool_f16(x)                                                 # [G*B, 2048] fp32
+        self.launches += 1
+        return feat.view(G, B, -1)
+
+    # ------------------------------------------------------------------ head
+    def _linear(self, layer, name, x, G, s0, eps, seed, out=None, out_col=0):
+        self.launches += 1
+        return ops.sampled_linear_f32(
+            x, layer.mu_weight.detach(), layer.rho_weight.detach(),
+            layer.mu_bias.detach() if layer.mu_bias is not None else None,
+            layer.rho_bias.detach() if layer.rho_bias is not None else None,
+            eps_w=self._eps_w(eps, name, s0, G), eps_b=self._eps_b(eps, name, s0, G), seed=seed,
+            layer_id=self.layer_ids[name], sample0=s0, out=out, out_col=out_col)
+
+    def _attention(self, attn, prefix, feat, G, s0, eps, seed, concat, col):
+        k = self._linear(attn.key_projection, prefix + ".key_projection", feat, G, s0, eps, seed)
+        v = self._linear(attn.value_projection, prefix + ".value_projection", feat, G, s0, eps, seed)
+        q = self._linear(attn.query_projection, prefix + ".query_projection", feat, G, s0, eps, seed)
+        t = ops.tanh_add_f32(q, k)
+        sc = self._linear(attn.attention_mechanism, prefix + ".attention_mechanism", t, G, s0, eps, seed)
+        ops.softmax_gate_f32(sc, v, concat, col)
+        self.launches += 2
+
+    # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def forward_group(self, inputs: Sequence[torch.Tensor], G: int, sample0: int = 0, eps: Optional[dict] = None,
+                      seed: Optional[int] = None) -> torch.Tensor:
+        """One walk of the network for MC samples [sample0, sample0+G) -> logits [G, B, C] fp32."""
+        seed = current_seed() if seed is None else seed
+        xs = [x.to(self.device, F32).contiguous() for x in inputs]
+        B = xs[0].shape[0]
+        if self.kind == "unimodal":
+            t = self.trunks[0]
+            feat = self._run_trunk(t, xs[0], G, sample0, eps, seed)
+            name, fc, _ = t.fc
+            return self._linear(fc, name, feat, G, sample0, eps, seed)
+        m = self.model
+        concat = torch.empty((G, B, 384), dtype=F32, device=self.device)
+        for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn,
+                                                  ("attention_image", "attention_bathy", "attention_sss"))):
+            feat = self._run_trunk(t, x, G, sample0, eps, seed)
+            self._attention(attn, pre, feat, G, sample0, eps, seed, concat, 128 * i)
+        h = self._linear(m.fc, "fc", concat, G, sample0, eps, seed)
+        h = self._linear(m.fc1, "fc1", h, G, sample0, eps, seed)
+        return self._linear(m.fc2, "fc2", h, G, sample0, eps, seed)
+
+    @torch.no_grad()
+    def forward_mc(self, inputs: Sequence[torch.Tensor], S: int, sample0: int = 0, eps: Optional[dict] = None,
+                   seed: Optional[int] = None, group: Optional[int] = None) -> torch.Tensor:
+        """logits [S, B, C] for MC samples sample0 .. sample0+S-1 (eps indexed from 0 when injected)."""
+        G = min(group or self.max_group, S)
+        outs = []
+        for s in range(0, S, G):
+            g = min(G, S - s)
+            outs.append(self.forward_group(inputs, g, sample0 + s, eps, seed))
+        return torch.cat(outs, dim=0)

@@ -1,0 +1,311 @@
+"""Tensor-level wrappers over the C-ABI: torch supplies device memory and the stream,
+every computation happens in libmauv_b200.so. No wrapper has a PyTorch fallback."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+F16, F32, I64 = torch.float16, torch.float32, torch.int64
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MauvError("mauv ops take CUDA tensors only (no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.MauvError("mauv ops take contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.MauvError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------ sampling
+def sample_weights_f16(mu: torch.Tensor, rho: torch.Tensor, G: int, *, eps: Optional[torch.Tensor] = None,
+                       seed: int = 0, layer_id: int = 0, sample0: int = 0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mu/rho: [cout, cin, kh, kw] or [out, in] fp32 -> [G, cout, k_pad] fp16, K order (kh, kw, cin)."""
+    lib = _lib.require_device()
+    if mu.dim() == 2:
+        cout, cin = mu.shape
+        kh = kw = 1
+    else:
+        cout, cin, kh, kw = mu.shape
+    K = cin * kh * kw
+    k_pad = round_up(K, 8)
+    if out is None:
+        out = torch.empty((G, cout, k_pad), dtype=F16, device=mu.device)
+    if eps is not None:
+        assert eps.numel() == G * mu.numel(), "eps must be [G, *mu.shape]"
+    _lib.check(lib.mauv_sample_weights_f16(_ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
+                                           G, cout, cin, kh, kw, k_pad, _ptr(out, F16), _stream()))
+    return out
+
+
+def sample_vector_f32(mu: torch.Tensor, rho: torch.Tensor, G: int, *, eps: Optional[torch.Tensor] = None,
+                      seed: int = 0, layer_id: int = 0, sample0: int = 0) -> torch.Tensor:
+    lib = _lib.require_device()
+    out = torch.empty((G, mu.numel()), dtype=F32, device=mu.device)
+    _lib.check(lib.mauv_sample_vector_f32(_ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
+                                          G, mu.numel(), _ptr(out), _stream()))
+    return out
+
+
+def philox_normal(n: int, *, seed: int, layer_id: int, sample_id: int, device="cuda") -> torch.Tensor:
+    lib = _lib.require_device()
+    out = torch.empty(n, dtype=F32, device=device)
+    _lib.check(lib.mauv_philox_normal_f32(seed, layer_id, sample_id, n, _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ contraction
+def gemm_m_tiles(M: int) -> int:
+    return (M + 127) // 128
+
+
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, stats: bool = False,
+             shared_a: bool = False, out: Optional[torch.Tensor] = None,
+             stats_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """a: [G, M, K] (or [M, K] with shared_a) fp16, w: [G, N, K] fp16 -> y [G, M, N] fp16,
+    stats partial [G, m_tiles, N, 2] fp32."""
+    lib = _lib.require_device()
+    G, N, K = w.shape
+    if shared_a:
+        M = a.shape[-2]
+        stride = 0
+    else:
+        assert a.shape[0] == G
+        M = a.shape[1]
+        stride = M * K
+    assert a.shape[-1] == K
+    if out is None:
+        out = torch.empty((G, M, N), dtype=F16, device=a.device)
+    if stats and stats_out is None:
+        stats_out = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a.device)
+    _lib.check(lib.mauv_gemm_f16(_ptr(a, F16), stride, _ptr(w, F16), _ptr(bias, F32), _ptr(out, F16),
+                                 _ptr(stats_out, F32) if stats else None, G, M, N, K, _stream()))
+    return out, (stats_out if stats else None)
+
+
+def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int, stride: int, pad: int, *,
+                      stats: bool = False, out: Optional[torch.Tensor] = None,
+                      stats_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """x: [G*B, H, W, Cin] NHWC fp16, w: [G, Cout, kh*kw*Cin] fp16 -> y [G*B, Ho, Wo, Cout] fp16."""
+    lib = _lib.require_device()
+    NB, H, W, Cin = x.shape
+    assert NB % G == 0
+    B = NB // G
+    Cout = w.shape[1]
+    assert w.shape[0] == G and w.shape[2] == kh * kw * Cin
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((NB, Ho, Wo, Cout), dtype=F16, device=x.device)
+    if stats and stats_out is None:
+        stats_out = torch.empty((G, gemm_m_tiles(B * Ho * Wo), Cout, 2), dtype=F32, device=x.device)
+    _lib.check(lib.mauv_conv2d_im2col_f16(_ptr(x, F16), _ptr(w, F16), _ptr(out, F16),
+                                          _ptr(stats_out, F32) if stats else None, G, B, H, W, Cin, Cout,
+                                          kh, kw, stride, pad, _stream()))
+    return out, (stats_out if stats else None)
+
+
+# ------------------------------------------------------------------ BN / pooling
+def stem_im2col_f16(x_nchw: torch.Tensor, kh: int, kw: int, stride: int, pad: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.require_device()
+    B, C, H, W = x_nchw.shape
+    k_pad = round_up(kh * kw * C, 8)
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((B * Ho * Wo, k_pad), dtype=F16, device=x_nchw.device)
+    _lib.check(lib.mauv_stem_im2col_f16(_ptr(x_nchw, F32), B, C, H, W, kh, kw, stride, pad, k_pad,
+                                        _ptr(out, F16), _stream()))
+    return out
+
+
+def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.Tensor],
+                beta: Optional[torch.Tensor], eps: float = 1e-5, momentum: float = 0.1,
+                running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
+                want_batch_stats: bool = False, out: Optional[torch.Tensor] = None):
+    lib = _lib.require_device()
+    G, m_tiles, Cc, _ = stats_partial.shape
+    if out is None:
+        out = torch.empty((G, Cc, 2), dtype=F32, device=stats_partial.device)
+    bs = torch.empty((G, Cc, 2), dtype=F32, device=stats_partial.device) if want_batch_stats else None
+    ws_bytes = lib.mauv_bn_finalize_ws_bytes(G, m_tiles, Cc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=stats_partial.device) if ws_bytes else None
+    _lib.check(lib.mauv_bn_finalize(_ptr(stats_partial, F32), G, m_tiles, Cc, count, _ptr(gamma, F32),
+                                    _ptr(beta, F32), eps, momentum, _ptr(running_mean, F32),
+                                    _ptr(running_var, F32), _ptr(out), _ptr(bs), _ptr(ws), _stream()))
+    return (out, bs) if want_batch_stats else out
+
+
+def bn_act_f16(y: torch.Tensor, ss: torch.Tensor, G: int, C: int, *, residual: Optional[torch.Tensor] = None,
+               y2: Optional[torch.Tensor] = None, ss2: Optional[torch.Tensor] = None, relu: bool = True,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.require_device()
+    M = y.numel() // (G * C)
+    if out is None:
+        out = torch.empty_like(y)
+    _lib.check(lib.mauv_bn_act_f16(_ptr(y, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2, F16), _ptr(ss2, F32),
+                                   int(relu), G, M, C, _ptr(out, F16), _stream()))
+    return out
+
+
+def bn_relu_maxpool_f16(y: torch.Tensor, ss: torch.Tensor, G: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.require_device()
+    NB, H, W, Cc = y.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    if out is None:
+        out = torch.empty((NB, Ho, Wo, Cc), dtype=F16, device=y.device)
+    _lib.check(lib.mauv_bn_relu_maxpool_f16(_ptr(y, F16), _ptr(ss, F32), G, NB // G, H, W, Cc, _ptr(out, F16), _stream()))
+    return out
+
+
+def avgpool_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [N, H, W, C] fp16 -> [N, C] fp32"""
+    lib = _lib.require_device()
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((N, Cc), dtype=F32, device=x.device)
+    _lib.check(lib.mauv_avgpool_f16(_ptr(x, F16), N, H * W, Cc, _ptr(out, F32), _stream()))
+    return out
+
+
+def nchw_f32_to_nhwc_f16(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    lib = _lib.require_device()
+    N, Cc, H, W = x.shape
+    c_pad = c_pad or Cc
+    out = torch.empty((N, H, W, c_pad), dtype=F16, device=x.device)
+    _lib.check(lib.mauv_nchw_f32_to_nhwc_f16(_ptr(x, F32), N, Cc, H * W, c_pad, _ptr(out), _stream()))
+    return out
+
+
+def nhwc_f16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, Cc, H, W), dtype=F32, device=x.device)
+    _lib.check(lib.mauv_nhwc_f16_to_nchw_f32(_ptr(x, F16), N, Cc, H * W, _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ head
+def sampled_linear_f32(x: torch.Tensor, mu_w, rho_w, mu_b, rho_b, *, eps_w=None, eps_b=None, seed: int = 0,
+                       layer_id: int = 0, sample0: int = 0, out: Optional[torch.Tensor] = None,
+                       out_col: int = 0) -> torch.Tensor:
+    """x: [G, B, in] fp32 (last-dim stride 1; may be a column slice of a wider buffer) -> y [G, B, out]."""
+    lib = _lib.require_device()
+    G, B, fin = x.shape
+    fout = mu_w.shape[0]
+    assert x.stride(2) == 1
+    if out is None:
+        out = torch.empty((G, B, fout), dtype=F32, device=x.device)
+        out_col = 0
+    y_view = out[:, :, out_col:out_col + fout]
+    _lib.check(lib.mauv_sampled_linear_f32(
+        x.data_ptr(), x.stride(0), x.stride(1), _ptr(mu_w, F32), _ptr(rho_w, F32), _ptr(eps_w, F32),
+        _ptr(mu_b, F32), _ptr(rho_b, F32), _ptr(eps_b, F32), seed, layer_id, sample0, G, B, fin, fout,
+        y_view.data_ptr(), out.stride(0), out.stride(1), _stream()))
+    return out
+
+
+def tanh_add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    out = torch.empty_like(a)
+    _lib.check(lib.mauv_tanh_add_f32(_ptr(a, F32), _ptr(b, F32), a.numel(), _ptr(out), _stream()))
+    return out
+
+
+def softmax_gate_f32(score: torch.Tensor, v: torch.Tensor, out: torch.Tensor, out_col: int = 0) -> torch.Tensor:
+    """out[..., out_col:out_col+n] = v * softmax(score, -1); out is [rows..., ld]."""
+    lib = _lib.require_device()
+    n = score.shape[-1]
+    rows = score.numel() // n
+    assert out.is_contiguous() and out.dtype == F32
+    ld = out.shape[-1]
+    _lib.check(lib.mauv_softmax_gate_f32(_ptr(score, F32), _ptr(v, F32), rows, n,
+                                         out.data_ptr() + 4 * out_col, ld, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ statistics
+def mc_reduce(logits: torch.Tensor, eps_entropy: float = 1e-7) -> dict:
+    """logits [S, B, C] fp32 -> dict of all MC statistics (see include/mauv_b200.h)."""
+    lib = _lib.require_device()
+    S, B, Cc = logits.shape
+    dev = logits.device
+    o = {
+        "mean_prob": torch.empty((B, Cc), dtype=F32, device=dev),
+        "mean_logit": torch.empty((B, Cc), dtype=F32, device=dev),
+        "argmax_prob": torch.empty((B,), dtype=I64, device=dev),
+        "argmax_logit": torch.empty((B,), dtype=I64, device=dev),
+        "pred_entropy": torch.empty((B,), dtype=F32, device=dev),
+        "aleatoric": torch.empty((B,), dtype=F32, device=dev),
+        "mutual_info": torch.empty((B,), dtype=F32, device=dev),
+        "var_mean": torch.empty((B,), dtype=F32, device=dev),
+    }
+    _lib.check(lib.mauv_mc_reduce(_ptr(logits, F32), S, B, Cc, 0, eps_entropy, _ptr(o["mean_prob"]),
+                                  _ptr(o["mean_logit"]), _ptr(o["argmax_prob"]), _ptr(o["argmax_logit"]),
+                                  _ptr(o["pred_entropy"]), _ptr(o["aleatoric"]), _ptr(o["mutual_info"]),
+                                  _ptr(o["var_mean"]), _stream()))
+    return o
+
+
+class KlPlan:
+    """Device-side table of (mu, rho, grad_mu, grad_rho, n) records for one model."""
+
+    def __init__(self, pairs, device, grads=None):
+        lib = _lib.require_device()
+        self.pairs = list(pairs)  # [(mu, rho)]
+        self.grads = grads        # optional [(grad_mu, grad_rho)] accumulation buffers (else .grad)
+        chunk = lib.mauv_kl_chunk_elems()
+        prefix, tot = [], 0
+        for mu, _ in self.pairs:
+            prefix.append(tot)
+            tot += (mu.numel() + chunk - 1) // chunk
+        self.total_chunks = tot
+        self.prefix = torch.tensor(prefix, dtype=I64, device=device)
+        self.ws = torch.empty(lib.mauv_kl_ws_bytes(), dtype=torch.uint8, device=device)
+        self.device = device
+        self._table = None
+        self._table_key = None
+
+    def _build_table(self, with_grad: bool):
+        rows, key = [], []
+        for i, (mu, rho) in enumerate(self.pairs):
+            if self.grads is not None:
+                g_mu, g_rho = self.grads[i]
+            else:
+                g_mu, g_rho = mu.grad, rho.grad
+            gm = _ptr(g_mu, F32) if (with_grad and g_mu is not None) else 0
+            gr = _ptr(g_rho, F32) if (with_grad and g_rho is not None) else 0
+            if with_grad and (gm == 0 or gr == 0):
+                raise _lib.MauvError("KlPlan: grad buffers must be allocated before the fused KL backward")
+            rows.append([mu.data_ptr(), rho.data_ptr(), gm, gr, mu.numel()])
+            key.append((mu.data_ptr(), rho.data_ptr(), gm, gr))
+        key = tuple(key)
+        if key != self._table_key:
+            self._table = torch.tensor(rows, dtype=I64, device=self.device)
+            self._table_key = key
+        return self._table
+
+    def run(self, prior_mu: float, prior_sigma: float, grad_scale: Optional[float] = None) -> torch.Tensor:
+        lib = _lib.require_device()
+        table = self._build_table(grad_scale is not None)
+        out = torch.empty((), dtype=F32, device=self.device)
+        _lib.check(lib.mauv_kl_fwd_bwd(table.data_ptr(), self.prefix.data_ptr(), len(self.pairs), self.total_chunks,
+                                       prior_mu, prior_sigma, grad_scale if grad_scale is not None else 0.0,
+                                       out.data_ptr(), self.ws.data_ptr(), _stream()))
+        return out

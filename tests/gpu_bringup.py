@@ -1,0 +1,339 @@
+"""GPU bring-up diagnostics (run on the B200 box): prints error metrics per kernel / shape.
+Usage: python tests/gpu_bringup.py <group>   group in {simple, gemm, conv, engine, all}
+Each group should be run in its own process so that a CUDA fault in one does not poison the others.
+"""
+import sys
+import time
+import traceback
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT / "multimodal-auv_b200", ROOT / "oracle"):
+    sys.path.insert(0, str(p))
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from mauv import ops
+
+dev = "cuda"
+
+
+def report(name, got, ref, tol=None):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-30
+    msg = (f"{name}: max_abs_err={err.max().item():.3e} rel_to_max={err.max().item() / denom:.3e} "
+           f"mean_abs_err={err.mean().item():.3e} ref_absmax={denom:.3e} nan={int(torch.isnan(got).sum())}")
+    ok = True
+    if tol is not None:
+        ok = bool(err.max().item() <= tol * max(denom, 1e-6)) and not torch.isnan(got).any()
+        msg += "  [OK]" if ok else "  [FAIL]"
+    print(msg, flush=True)
+    return ok
+
+
+def run_case(fn, *a, **k):
+    try:
+        fn(*a, **k)
+        torch.cuda.synchronize()
+    except Exception:
+        print(f"EXCEPTION in {fn.__name__}{a}:", flush=True)
+        traceback.print_exc()
+        sys.stdout.flush()
+
+
+# ------------------------------------------------------------------ simple kernels
+def t_philox():
+    import philox
+    z = ops.philox_normal(100003, seed=0x1234567890ABCDEF, layer_id=17, sample_id=5)
+    ref = torch.from_numpy(philox.philox_normal(100003, 0x1234567890ABCDEF, 17, 5))
+    report("philox_normal vs numpy oracle", z, ref, 1e-5)
+    print(f"   mean={z.mean().item():.4f} std={z.std().item():.4f}")
+
+
+def t_sample():
+    torch.manual_seed(0)
+    for shape in [(64, 3, 7, 7), (64, 1, 7, 7), (128, 64, 3, 3), (256, 64, 1, 1), (1284, 384)]:
+        mu = (torch.randn(shape) * 0.05).to(dev)
+        rho = (torch.randn(shape) - 4).to(dev)
+        G = 3
+        eps = torch.randn((G, *shape), device=dev)
+        w = ops.sample_weights_f16(mu, rho, G, eps=eps)
+        ref = mu + torch.log1p(torch.exp(rho)) * eps
+        if len(shape) == 4:
+            ref = ref.permute(0, 1, 3, 4, 2).reshape(G, shape[0], -1)   # (kh, kw, cin) K order
+        K = ref.shape[-1]
+        report(f"sample_weights{shape} injected", w[..., :K], ref, 2e-3)
+        if w.shape[-1] != K:
+            print("   pad zero:", bool((w[..., K:] == 0).all()))
+        # philox path == injected philox eps
+        import philox
+        n = mu.numel()
+        e2 = torch.stack([torch.from_numpy(philox.philox_normal(n, 99, 7, 10 + g)) for g in range(G)]).to(dev)
+        w2 = ops.sample_weights_f16(mu, rho, G, seed=99, layer_id=7, sample0=10)
+        w3 = ops.sample_weights_f16(mu, rho, G, eps=e2.view(G, *shape))
+        report(f"sample_weights{shape} philox vs injected-philox", w2, w3, 2e-3)
+
+
+def t_stem():
+    torch.manual_seed(1)
+    for C in (1, 3):
+        x = torch.randn(2, C, 32, 32, device=dev)
+        a = ops.stem_im2col_f16(x, 7, 7, 2, 3)
+        cols = F.unfold(x, 7, padding=3, stride=2)           # [B, C*49, L] with (c, r, s) order
+        B, _, L = cols.shape
+        ref = cols.view(B, C, 49, L).permute(0, 3, 2, 1).reshape(B * L, 49 * C)
+        report(f"stem_im2col C={C}", a[:, :49 * C], ref, 1e-3)
+
+
+def t_bn():
+    torch.manual_seed(2)
+    G, M, Cc = 2, 1000, 64
+    y = (torch.randn(G, M, Cc, device=dev) * 2 + 0.5).half()
+    a = torch.randn(G, M, 8, device=dev).half()
+    # use the GEMM with identity-like weights to produce stats? here: build partials directly
+    mt = (M + 127) // 128
+    part = torch.zeros(G, mt, Cc, 2, device=dev)
+    yf = y.float()
+    for t in range(mt):
+        blk = yf[:, t * 128:(t + 1) * 128]
+        part[:, t, :, 0] = blk.sum(1)
+        part[:, t, :, 1] = (blk * blk).sum(1)
+    gamma = torch.rand(Cc, device=dev) + 0.5
+    beta = torch.randn(Cc, device=dev)
+    rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    ss, bs = ops.bn_finalize(part, M, gamma, beta, 1e-5, 0.1, rm, rv, want_batch_stats=True)
+    out = ops.bn_act_f16(y, ss, G, Cc, relu=True)
+    rm_ref, rv_ref = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    refs = []
+    for g in range(G):
+        refs.append(F.relu(F.batch_norm(yf[g], rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)))
+    ref = torch.stack(refs)
+    report("bn_finalize+bn_act(relu)", out, ref, 2e-3)
+    report("bn running_mean", rm, rm_ref, 1e-5)
+    report("bn running_var", rv, rv_ref, 1e-5)
+    res = torch.randn(G, M, Cc, device=dev).half()
+    out2 = ops.bn_act_f16(y, ss, G, Cc, residual=res, relu=True)
+    report("bn_act residual", out2, F.relu(torch.stack([F.batch_norm(yf[g], None, None, gamma, beta, True) for g in range(G)]) + res.float()), 2e-3)
+    out3 = ops.bn_act_f16(y, ss, G, Cc, y2=res, ss2=ss, relu=False)
+    sc, sh = ss[..., 0].unsqueeze(1), ss[..., 1].unsqueeze(1)
+    report("bn_act dual", out3, yf * sc + sh + res.float() * sc + sh, 2e-3)
+    # many-tile path (m_tiles > 64)
+    M2 = 128 * 100
+    part2 = torch.rand(G, 100, Cc, 2, device=dev) * 128
+    part2[..., 1] += part2[..., 0] ** 2 / 128
+    ss2 = ops.bn_finalize(part2, M2, gamma, beta)
+    mean = part2[..., 0].double().sum(1) / M2
+    var = part2[..., 1].double().sum(1) / M2 - mean * mean
+    sc_ref = gamma.double() / torch.sqrt(var + 1e-5)
+    report("bn_finalize split path scale", ss2[..., 0], sc_ref.float(), 1e-4)
+    report("bn_finalize split path shift", ss2[..., 1], (beta.double() - mean * sc_ref).float(), 1e-4)
+
+
+def t_pool():
+    torch.manual_seed(3)
+    G, B, H, W, Cc = 2, 2, 16, 16, 64
+    y = torch.randn(G * B, H, W, Cc, device=dev).half()
+    ss = torch.stack([torch.rand(G, Cc, device=dev) + 0.5, torch.randn(G, Cc, device=dev)], -1).contiguous()
+    out = ops.bn_relu_maxpool_f16(y, ss, G)
+    z = y.float().view(G, B, H, W, Cc) * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]
+    z = F.relu(z).view(G * B, H, W, Cc).permute(0, 3, 1, 2)
+    ref = F.max_pool2d(z, 3, 2, 1).permute(0, 2, 3, 1)
+    report("bn_relu_maxpool", out, ref, 2e-3)
+    x = torch.randn(6, 4, 4, 2048, device=dev).half()
+    report("avgpool", ops.avgpool_f16(x), x.float().mean((1, 2)), 1e-5)
+    xn = torch.randn(3, 64, 5, 7, device=dev)
+    xh = ops.nchw_f32_to_nhwc_f16(xn)
+    report("nchw->nhwc", xh, xn.permute(0, 2, 3, 1), 1e-3)
+    report("nhwc->nchw", ops.nhwc_f16_to_nchw_f32(xh), xn, 1e-3)
+
+
+def t_linear():
+    torch.manual_seed(4)
+    for (G, B, fin, fout) in [(2, 8, 2048, 128), (3, 70, 384, 1284), (1, 5, 32, 7), (2, 256, 1284, 32)]:
+        x = torch.randn(G, B, fin, device=dev)
+        mu = torch.randn(fout, fin, device=dev) * 0.05
+        rho = torch.randn(fout, fin, device=dev) - 4
+        mub = torch.randn(fout, device=dev) * 0.05
+        rhob = torch.randn(fout, device=dev) - 4
+        ew = torch.randn(G, fout, fin, device=dev)
+        eb = torch.randn(G, fout, device=dev)
+        y = ops.sampled_linear_f32(x, mu, rho, mub, rhob, eps_w=ew, eps_b=eb)
+        w = mu + torch.log1p(torch.exp(rho)) * ew
+        b = mub + torch.log1p(torch.exp(rhob)) * eb
+        ref = torch.einsum("gbi,goi->gbo", x.double(), w.double()) + b.double().unsqueeze(1)
+        report(f"sampled_linear G={G} B={B} {fin}->{fout}", y, ref.float(), 1e-5)
+    a, b = torch.randn(1000, device=dev), torch.randn(1000, device=dev)
+    report("tanh_add", ops.tanh_add_f32(a, b), torch.tanh(a + b), 1e-6)
+    sc, v = torch.randn(2, 9, 128, device=dev), torch.randn(2, 9, 128, device=dev)
+    out = torch.zeros(2, 9, 384, device=dev)
+    ops.softmax_gate_f32(sc, v, out, 128)
+    report("softmax_gate", out[..., 128:256], v * F.softmax(sc, -1), 1e-6)
+    print("   untouched cols zero:", bool((out[..., :128] == 0).all() and (out[..., 256:] == 0).all()))
+
+
+def t_mc():
+    import bnn_oracle as O
+    torch.manual_seed(5)
+    for (S, B, Cc) in [(30, 256, 7), (10, 8, 7), (1, 4, 7), (5, 1000, 12)]:
+        lg = torch.randn(S, B, Cc) * 3
+        o7 = ops.mc_reduce(lg.to(dev), 1e-7)
+        o8 = ops.mc_reduce(lg.to(dev), 1e-8)
+        p = O.predictor_stats(lg)
+        m = O.multimodal_eval_stats(lg)
+        u = O.unimodal_eval_stats(lg)
+        tag = f"mc_reduce S={S} B={B} C={Cc}"
+        if S > 1:
+            report(tag + " var_mean", o7["var_mean"], p["predictive_uncertainty"], 1e-4)
+        else:
+            print(tag + " var_mean all-NaN (torch.var S=1):", bool(torch.isnan(o7["var_mean"]).all()),
+                  bool(torch.isnan(p["predictive_uncertainty"]).all()))
+        report(tag + " aleatoric(1e-7)", o7["aleatoric"], p["aleatoric_uncertainty"], 1e-5)
+        report(tag + " mean_prob", o7["mean_prob"], p["mean_prob"], 1e-5)
+        print("   argmax_prob exact:", bool((o7["argmax_prob"].cpu() == p["predicted_class"]).all()),
+              " argmax_logit exact:", bool((o8["argmax_logit"].cpu() == m["predicted"]).all()),
+              " unimodal argmax exact:", bool((o7["argmax_logit"].cpu() == u["predicted"]).all()))
+        report(tag + " pred_entropy(1e-8)", o8["pred_entropy"], m["predictive_uncertainty"], 1e-5)
+        report(tag + " MI(1e-8)", o8["mutual_info"], m["model_uncertainty"], 1e-4)
+        report(tag + " mean_logit", o8["mean_logit"], m["output_mean"], 1e-5)
+
+
+def t_kl():
+    import bnn_oracle as O
+    torch.manual_seed(6)
+    shapes = [(64, 3, 7, 7), (256, 64, 1, 1), (128, 128, 3, 3), (1284, 384), (1284,), (7, 32), (7,)]
+    mus = [(torch.randn(s) * 0.05).to(dev).requires_grad_() for s in shapes]
+    rhos = [O.get_rho(m.detach().cpu(), 0.1).to(dev).requires_grad_() for m in mus]
+    rhos[1].data[:10] = -46.0
+    pairs = list(zip(mus, rhos))
+    plan = ops.KlPlan([(m.detach(), r.detach()) for m, r in pairs], dev)
+    kl = plan.run(0.0, 1.0)
+    ref = sum(O.kl_div(m.double(), torch.log1p(torch.exp(r.double())), torch.tensor(0.0, dtype=torch.float64, device=dev),
+                       torch.tensor(1.0, dtype=torch.float64, device=dev)) for m, r in pairs)
+    print(f"kl fwd: got={kl.item():.8f} ref64={ref.item():.8f} rel={(abs(kl.item() - ref.item()) / abs(ref.item())):.3e}")
+    ref.backward()
+    gbufs = [(torch.zeros_like(m), torch.zeros_like(r)) for m, r in pairs]
+    plan2 = ops.KlPlan([(m.detach(), r.detach()) for m, r in pairs], dev, grads=gbufs)
+    plan2.run(0.0, 1.0, grad_scale=0.25)
+    for i, ((m, r), (gm, gr)) in enumerate(zip(pairs, gbufs)):
+        report(f"kl grad_mu[{i}]", gm, 0.25 * m.grad.float(), 1e-4)
+        report(f"kl grad_rho[{i}]", gr, 0.25 * r.grad.float(), 1e-4)
+
+
+# ------------------------------------------------------------------ tensor-core GEMM
+def t_gemm(G, M, N, K, shared=False, bias=False):
+    torch.manual_seed(7)
+    a = (torch.randn((M, K) if shared else (G, M, K), device=dev) * 0.5).half()
+    w = (torch.randn(G, N, K, device=dev) * 0.1).half()
+    b = torch.randn(G, N, device=dev) if bias else None
+    y, st = ops.gemm_f16(a, w, bias=b, stats=True, shared_a=shared)
+    torch.cuda.synchronize()
+    af = a.float().expand(G, M, K) if shared else a.float()
+    ref = torch.einsum("gmk,gnk->gmn", af, w.float())
+    if bias:
+        ref = ref + b.unsqueeze(1)
+    ok = report(f"gemm G={G} M={M} N={N} K={K} shared={shared} bias={bias}", y, ref, 3e-3)
+    s1 = st[..., 0].sum(1)
+    s2 = st[..., 1].sum(1)
+    report("   stats sum", s1, ref.sum(1), 2e-3)
+    report("   stats sumsq", s2, (ref * ref).sum(1), 2e-3)
+    if not ok:
+        err = (y.float() - ref).abs()
+        bad = (err > 3e-3 * ref.abs().max()).nonzero()
+        print("   first bad idx:", bad[:8].tolist(), " n_bad:", bad.shape[0], "of", err.numel())
+        rows = torch.unique(bad[:, 1])
+        cols = torch.unique(bad[:, 2])
+        print("   bad rows (first 16):", rows[:16].tolist(), " bad cols (first 16):", cols[:16].tolist())
+
+
+def t_conv(G, B, H, W, Cin, Cout, k, stride, pad):
+    torch.manual_seed(8)
+    x = (torch.randn(G * B, H, W, Cin, device=dev) * 0.5).half()
+    w = (torch.randn(G, Cout, k, k, Cin, device=dev) * 0.1).half()      # (kh, kw, cin) K order
+    y, st = ops.conv2d_im2col_f16(x, w.view(G, Cout, -1), G, k, k, stride, pad, stats=True)
+    torch.cuda.synchronize()
+    refs = []
+    for g in range(G):
+        xg = x[g * B:(g + 1) * B].float().permute(0, 3, 1, 2)
+        wg = w[g].float().permute(0, 3, 1, 2)
+        refs.append(F.conv2d(xg, wg, None, stride, pad).permute(0, 2, 3, 1))
+    ref = torch.cat(refs)
+    ok = report(f"conv G={G} B={B} {H}x{W} {Cin}->{Cout} k={k} s={stride} p={pad}", y, ref, 3e-3)
+    Cn = Cout
+    report("   stats sum", st[..., 0].sum(1), ref.view(G, -1, Cn).sum(1), 2e-3)
+    if not ok:
+        err = (y.float() - ref).abs().view(G, B, *ref.shape[1:])
+        bad = (err > 3e-3 * ref.abs().max()).nonzero()
+        print("   n_bad:", bad.shape[0], "of", err.numel(), " first:", bad[:6].tolist())
+
+
+# ------------------------------------------------------------------ engine vs oracle
+def t_engine(B=2, S=2, size=64, kind="multimodal"):
+    import bnn_oracle as O
+    from mauv.bayesian import dnn_to_bnn
+    from mauv.engine import MCEngine
+    import mauv.models.base_models as MB
+    torch.manual_seed(1234)
+    if kind == "multimodal":
+        o_model = O.define_models(7, unimodal=False)["multimodal_model"]
+    else:
+        torch.manual_seed(1234)
+        o_model = O.ResNet50Custom(3, 7)
+        O.dnn_to_bnn(o_model, O.DEFAULT_PRIOR)
+    img, bathy, sss, _ = O.synthetic_batch(B, size=size)
+    inputs = (img, bathy, sss) if kind == "multimodal" else (img,)
+    eps = O.draw_eps(o_model, S, seed=77)
+    t0 = time.time()
+    ref = O.mc_logits(o_model, inputs, S, eps)
+    print(f"oracle {kind} B={B} S={S} size={size}: {time.time() - t0:.1f}s; logits absmax {ref.abs().max():.4f}")
+    # build the product model with identical parameters (same state_dict keys)
+    torch.manual_seed(1234)
+    if kind == "multimodal":
+        feats = [O.feature_extractor(), O.feature_extractor(), O.feature_extractor(1)]
+        model = MB.MultiModalModel(*feats, 7)
+    else:
+        model = O.ResNet50Custom(3, 7)
+    dnn_to_bnn(model, O.DEFAULT_PRIOR)
+    sd = {k: v for k, v in o_model.state_dict().items()}
+    missing = model.load_state_dict(sd, strict=False)
+    print("   load_state_dict:", missing)
+    model.to(dev).train()
+    eng = MCEngine(model)
+    t0 = time.time()
+    got = eng.forward_mc([t.to(dev) for t in inputs], S, eps=eps)
+    torch.cuda.synchronize()
+    print(f"   engine time {time.time() - t0:.2f}s, launches {eng.launches}")
+    report(f"engine {kind} logits vs oracle fp32", got, ref, 2e-2)
+    print("   argmax equal:", bool((got.mean(0).argmax(1).cpu() == ref.mean(0).argmax(1)).all()),
+          " got:", got[0, 0].tolist(), " ref:", ref[0, 0].tolist())
+    # BN running stats of the first BN
+    bn_g = model.image_model_feat.bn1 if kind == "multimodal" else model.model.bn1
+    bn_r = o_model.image_model_feat.bn1 if kind == "multimodal" else o_model.model.bn1
+    report("   bn1.running_mean", bn_g.running_mean, bn_r.running_mean, 1e-3)
+    report("   bn1.running_var", bn_g.running_var, bn_r.running_var, 1e-3)
+
+
+GROUPS = {
+    "simple": lambda: [run_case(f) for f in (t_philox, t_sample, t_stem, t_bn, t_pool, t_linear, t_mc, t_kl)],
+    "gemm": lambda: [run_case(t_gemm, *a) for a in [
+        (1, 128, 64, 64), (1, 128, 128, 64), (1, 128, 256, 64), (1, 256, 128, 128), (2, 300, 256, 192),
+        (3, 1000, 512, 576), (1, 128, 2048, 512), (2, 4096, 64, 152, True), (1, 20000, 64, 64),
+        (2, 256, 128, 2048, False, True), (1, 77, 72, 136)]],
+    "conv": lambda: [run_case(t_conv, *a) for a in [
+        (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
+        (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),
+        (1, 2, 4, 4, 512, 512, 3, 1, 1), (3, 1, 6, 6, 128, 64, 3, 2, 1)]],
+    "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal")],
+}
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print(f"=== bringup group {which} on {torch.cuda.get_device_name(0)} ===", flush=True)
+    for name, fn in GROUPS.items():
+        if which in (name, "all"):
+            print(f"--- {name} ---", flush=True)
+            fn()
+    print("=== done ===", flush=True)
