@@ -27,6 +27,45 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+
+# ------------------------------------------------------------------ launch accounting / profiling
+# kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
+KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2}
+launch_count = 0
+_prof = None   # list of (name, start_event, end_event) while profiling
+
+
+def start_profile():
+    global _prof
+    _prof = []
+
+
+def stop_profile():
+    """-> {name: (calls, total_ms)} measured with CUDA events on the launching stream."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in rec or []:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    return out
+
+
+def _run(name, fn, *args):
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _prof.append((name, e0, e1))
+    else:
+        rc = fn(*args)
+    _lib.check(rc)
+
+
 def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -48,8 +87,8 @@ def sample_weights_f16(mu: torch.Tensor, rho: torch.Tensor, G: int, *, eps: Opti
         out = torch.empty((G, cout, k_pad), dtype=F16, device=mu.device)
     if eps is not None:
         assert eps.numel() == G * mu.numel(), "eps must be [G, *mu.shape]"
-    _lib.check(lib.mauv_sample_weights_f16(_ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
-                                           G, cout, cin, kh, kw, k_pad, _ptr(out, F16), _stream()))
+    _run("mauv_sample_weights_f16", lib.mauv_sample_weights_f16, _ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
+                                           G, cout, cin, kh, kw, k_pad, _ptr(out, F16), _stream())
     return out
 
 
@@ -57,15 +96,15 @@ def sample_vector_f32(mu: torch.Tensor, rho: torch.Tensor, G: int, *, eps: Optio
                       seed: int = 0, layer_id: int = 0, sample0: int = 0) -> torch.Tensor:
     lib = _lib.require_device()
     out = torch.empty((G, mu.numel()), dtype=F32, device=mu.device)
-    _lib.check(lib.mauv_sample_vector_f32(_ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
-                                          G, mu.numel(), _ptr(out), _stream()))
+    _run("mauv_sample_vector_f32", lib.mauv_sample_vector_f32, _ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0,
+                                          G, mu.numel(), _ptr(out), _stream())
     return out
 
 
 def philox_normal(n: int, *, seed: int, layer_id: int, sample_id: int, device="cuda") -> torch.Tensor:
     lib = _lib.require_device()
     out = torch.empty(n, dtype=F32, device=device)
-    _lib.check(lib.mauv_philox_normal_f32(seed, layer_id, sample_id, n, _ptr(out), _stream()))
+    _run("mauv_philox_normal_f32", lib.mauv_philox_normal_f32, seed, layer_id, sample_id, n, _ptr(out), _stream())
     return out
 
 
@@ -93,8 +132,8 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] =
         out = torch.empty((G, M, N), dtype=F16, device=a.device)
     if stats and stats_out is None:
         stats_out = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a.device)
-    _lib.check(lib.mauv_gemm_f16(_ptr(a, F16), stride, _ptr(w, F16), _ptr(bias, F32), _ptr(out, F16),
-                                 _ptr(stats_out, F32) if stats else None, G, M, N, K, _stream()))
+    _run("mauv_gemm_f16", lib.mauv_gemm_f16, _ptr(a, F16), stride, _ptr(w, F16), _ptr(bias, F32), _ptr(out, F16),
+                                 _ptr(stats_out, F32) if stats else None, G, M, N, K, _stream())
     return out, (stats_out if stats else None)
 
 
@@ -114,9 +153,9 @@ def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int
         out = torch.empty((NB, Ho, Wo, Cout), dtype=F16, device=x.device)
     if stats and stats_out is None:
         stats_out = torch.empty((G, gemm_m_tiles(B * Ho * Wo), Cout, 2), dtype=F32, device=x.device)
-    _lib.check(lib.mauv_conv2d_im2col_f16(_ptr(x, F16), _ptr(w, F16), _ptr(out, F16),
+    _run("mauv_conv2d_im2col_f16", lib.mauv_conv2d_im2col_f16, _ptr(x, F16), _ptr(w, F16), _ptr(out, F16),
                                           _ptr(stats_out, F32) if stats else None, G, B, H, W, Cin, Cout,
-                                          kh, kw, stride, pad, _stream()))
+                                          kh, kw, stride, pad, _stream())
     return out, (stats_out if stats else None)
 
 
@@ -130,8 +169,8 @@ def stem_im2col_f16(x_nchw: torch.Tensor, kh: int, kw: int, stride: int, pad: in
     Wo = (W + 2 * pad - kw) // stride + 1
     if out is None:
         out = torch.empty((B * Ho * Wo, k_pad), dtype=F16, device=x_nchw.device)
-    _lib.check(lib.mauv_stem_im2col_f16(_ptr(x_nchw, F32), B, C, H, W, kh, kw, stride, pad, k_pad,
-                                        _ptr(out, F16), _stream()))
+    _run("mauv_stem_im2col_f16", lib.mauv_stem_im2col_f16, _ptr(x_nchw, F32), B, C, H, W, kh, kw, stride, pad, k_pad,
+                                        _ptr(out, F16), _stream())
     return out
 
 
@@ -146,9 +185,9 @@ def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.T
     bs = torch.empty((G, Cc, 2), dtype=F32, device=stats_partial.device) if want_batch_stats else None
     ws_bytes = lib.mauv_bn_finalize_ws_bytes(G, m_tiles, Cc)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=stats_partial.device) if ws_bytes else None
-    _lib.check(lib.mauv_bn_finalize(_ptr(stats_partial, F32), G, m_tiles, Cc, count, _ptr(gamma, F32),
+    _run("mauv_bn_finalize", lib.mauv_bn_finalize, _ptr(stats_partial, F32), G, m_tiles, Cc, count, _ptr(gamma, F32),
                                     _ptr(beta, F32), eps, momentum, _ptr(running_mean, F32),
-                                    _ptr(running_var, F32), _ptr(out), _ptr(bs), _ptr(ws), _stream()))
+                                    _ptr(running_var, F32), _ptr(out), _ptr(bs), _ptr(ws), _stream())
     return (out, bs) if want_batch_stats else out
 
 
@@ -159,8 +198,8 @@ def bn_act_f16(y: torch.Tensor, ss: torch.Tensor, G: int, C: int, *, residual: O
     M = y.numel() // (G * C)
     if out is None:
         out = torch.empty_like(y)
-    _lib.check(lib.mauv_bn_act_f16(_ptr(y, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2, F16), _ptr(ss2, F32),
-                                   int(relu), G, M, C, _ptr(out, F16), _stream()))
+    _run("mauv_bn_act_f16", lib.mauv_bn_act_f16, _ptr(y, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2, F16), _ptr(ss2, F32),
+                                   int(relu), G, M, C, _ptr(out, F16), _stream())
     return out
 
 
@@ -170,7 +209,7 @@ def bn_relu_maxpool_f16(y: torch.Tensor, ss: torch.Tensor, G: int, out: Optional
     Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
     if out is None:
         out = torch.empty((NB, Ho, Wo, Cc), dtype=F16, device=y.device)
-    _lib.check(lib.mauv_bn_relu_maxpool_f16(_ptr(y, F16), _ptr(ss, F32), G, NB // G, H, W, Cc, _ptr(out, F16), _stream()))
+    _run("mauv_bn_relu_maxpool_f16", lib.mauv_bn_relu_maxpool_f16, _ptr(y, F16), _ptr(ss, F32), G, NB // G, H, W, Cc, _ptr(out, F16), _stream())
     return out
 
 
@@ -180,7 +219,7 @@ def avgpool_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     N, H, W, Cc = x.shape
     if out is None:
         out = torch.empty((N, Cc), dtype=F32, device=x.device)
-    _lib.check(lib.mauv_avgpool_f16(_ptr(x, F16), N, H * W, Cc, _ptr(out, F32), _stream()))
+    _run("mauv_avgpool_f16", lib.mauv_avgpool_f16, _ptr(x, F16), N, H * W, Cc, _ptr(out, F32), _stream())
     return out
 
 
@@ -189,7 +228,7 @@ def nchw_f32_to_nhwc_f16(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.
     N, Cc, H, W = x.shape
     c_pad = c_pad or Cc
     out = torch.empty((N, H, W, c_pad), dtype=F16, device=x.device)
-    _lib.check(lib.mauv_nchw_f32_to_nhwc_f16(_ptr(x, F32), N, Cc, H * W, c_pad, _ptr(out), _stream()))
+    _run("mauv_nchw_f32_to_nhwc_f16", lib.mauv_nchw_f32_to_nhwc_f16, _ptr(x, F32), N, Cc, H * W, c_pad, _ptr(out), _stream())
     return out
 
 
@@ -197,7 +236,7 @@ def nhwc_f16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.require_device()
     N, H, W, Cc = x.shape
     out = torch.empty((N, Cc, H, W), dtype=F32, device=x.device)
-    _lib.check(lib.mauv_nhwc_f16_to_nchw_f32(_ptr(x, F16), N, Cc, H * W, _ptr(out), _stream()))
+    _run("mauv_nhwc_f16_to_nchw_f32", lib.mauv_nhwc_f16_to_nchw_f32, _ptr(x, F16), N, Cc, H * W, _ptr(out), _stream())
     return out
 
 
@@ -214,17 +253,17 @@ def sampled_linear_f32(x: torch.Tensor, mu_w, rho_w, mu_b, rho_b, *, eps_w=None,
         out = torch.empty((G, B, fout), dtype=F32, device=x.device)
         out_col = 0
     y_view = out[:, :, out_col:out_col + fout]
-    _lib.check(lib.mauv_sampled_linear_f32(
+    _run("mauv_sampled_linear_f32", lib.mauv_sampled_linear_f32, 
         x.data_ptr(), x.stride(0), x.stride(1), _ptr(mu_w, F32), _ptr(rho_w, F32), _ptr(eps_w, F32),
         _ptr(mu_b, F32), _ptr(rho_b, F32), _ptr(eps_b, F32), seed, layer_id, sample0, G, B, fin, fout,
-        y_view.data_ptr(), out.stride(0), out.stride(1), _stream()))
+        y_view.data_ptr(), out.stride(0), out.stride(1), _stream())
     return out
 
 
 def tanh_add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = _lib.require_device()
     out = torch.empty_like(a)
-    _lib.check(lib.mauv_tanh_add_f32(_ptr(a, F32), _ptr(b, F32), a.numel(), _ptr(out), _stream()))
+    _run("mauv_tanh_add_f32", lib.mauv_tanh_add_f32, _ptr(a, F32), _ptr(b, F32), a.numel(), _ptr(out), _stream())
     return out
 
 
@@ -235,8 +274,8 @@ def softmax_gate_f32(score: torch.Tensor, v: torch.Tensor, out: torch.Tensor, ou
     rows = score.numel() // n
     assert out.is_contiguous() and out.dtype == F32
     ld = out.shape[-1]
-    _lib.check(lib.mauv_softmax_gate_f32(_ptr(score, F32), _ptr(v, F32), rows, n,
-                                         out.data_ptr() + 4 * out_col, ld, _stream()))
+    _run("mauv_softmax_gate_f32", lib.mauv_softmax_gate_f32, _ptr(score, F32), _ptr(v, F32), rows, n,
+                                         out.data_ptr() + 4 * out_col, ld, _stream())
     return out
 
 
@@ -256,10 +295,10 @@ def mc_reduce(logits: torch.Tensor, eps_entropy: float = 1e-7) -> dict:
         "mutual_info": torch.empty((B,), dtype=F32, device=dev),
         "var_mean": torch.empty((B,), dtype=F32, device=dev),
     }
-    _lib.check(lib.mauv_mc_reduce(_ptr(logits, F32), S, B, Cc, 0, eps_entropy, _ptr(o["mean_prob"]),
+    _run("mauv_mc_reduce", lib.mauv_mc_reduce, _ptr(logits, F32), S, B, Cc, 0, eps_entropy, _ptr(o["mean_prob"]),
                                   _ptr(o["mean_logit"]), _ptr(o["argmax_prob"]), _ptr(o["argmax_logit"]),
                                   _ptr(o["pred_entropy"]), _ptr(o["aleatoric"]), _ptr(o["mutual_info"]),
-                                  _ptr(o["var_mean"]), _stream()))
+                                  _ptr(o["var_mean"]), _stream())
     return o
 
 
@@ -305,7 +344,7 @@ class KlPlan:
         lib = _lib.require_device()
         table = self._build_table(grad_scale is not None)
         out = torch.empty((), dtype=F32, device=self.device)
-        _lib.check(lib.mauv_kl_fwd_bwd(table.data_ptr(), self.prefix.data_ptr(), len(self.pairs), self.total_chunks,
+        _run("mauv_kl_fwd_bwd", lib.mauv_kl_fwd_bwd, table.data_ptr(), self.prefix.data_ptr(), len(self.pairs), self.total_chunks,
                                        prior_mu, prior_sigma, grad_scale if grad_scale is not None else 0.0,
-                                       out.data_ptr(), self.ws.data_ptr(), _stream()))
+                                       out.data_ptr(), self.ws.data_ptr(), _stream())
         return out

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from mauv import ops
 
 dev = "cuda"
+FAILS = []   # (name, message) of every toleranced check that failed; tests/test_gpu_parity.py asserts it stays empty
 
 
 def report(name, got, ref, tol=None):
@@ -31,6 +32,8 @@ def report(name, got, ref, tol=None):
     if tol is not None:
         ok = bool(err.max().item() <= tol * max(denom, 1e-6)) and not torch.isnan(got).any()
         msg += "  [OK]" if ok else "  [FAIL]"
+        if not ok:
+            FAILS.append((name, msg))
     print(msg, flush=True)
     return ok
 
@@ -271,49 +274,73 @@ def t_conv(G, B, H, W, Cin, Cout, k, stride, pad):
 
 
 # ------------------------------------------------------------------ engine vs oracle
-def t_engine(B=2, S=2, size=64, kind="multimodal"):
+def _emulate_fp16_operands(model):
+    """Oracle with every Bayesian conv's input rounded to fp16 (= 10-bit mantissa, TF32-class operands):
+    calibrates how much of an end-to-end difference is explained by operand precision alone."""
+    hs = []
+
+    def rnd_in(mod, inp):
+        return tuple(i.half().float() for i in inp)
+    for _, l in model.named_modules():
+        if hasattr(l, "mu_kernel"):
+            hs.append(l.register_forward_pre_hook(rnd_in))
+    return hs
+
+
+def build_pair(kind, seed=1234):
+    """(oracle model, product model on GPU) with identical parameters and BN buffers."""
     import bnn_oracle as O
     from mauv.bayesian import dnn_to_bnn
-    from mauv.engine import MCEngine
     import mauv.models.base_models as MB
-    torch.manual_seed(1234)
+    torch.manual_seed(seed)
     if kind == "multimodal":
-        o_model = O.define_models(7, unimodal=False)["multimodal_model"]
+        o_model = O.define_models(7, seed=None, unimodal=False)["multimodal_model"]
+        model = MB.MultiModalModel(O.feature_extractor(), O.feature_extractor(), O.feature_extractor(1), 7)
     else:
-        torch.manual_seed(1234)
         o_model = O.ResNet50Custom(3, 7)
         O.dnn_to_bnn(o_model, O.DEFAULT_PRIOR)
+        model = O.ResNet50Custom(3, 7)
+    dnn_to_bnn(model, O.DEFAULT_PRIOR)
+    model.load_state_dict({k: v.clone() for k, v in o_model.state_dict().items()}, strict=True)
+    return o_model, model.to(dev).train()
+
+
+def t_engine(B=2, S=2, size=64, kind="multimodal"):
+    import bnn_oracle as O
+    from mauv.engine import MCEngine
+    o_model, model = build_pair(kind)
+    sd0 = {k: v.clone() for k, v in o_model.state_dict().items()}
     img, bathy, sss, _ = O.synthetic_batch(B, size=size)
     inputs = (img, bathy, sss) if kind == "multimodal" else (img,)
     eps = O.draw_eps(o_model, S, seed=77)
     t0 = time.time()
     ref = O.mc_logits(o_model, inputs, S, eps)
+    bn_r = (o_model.image_model_feat.bn1 if kind == "multimodal" else o_model.model.bn1)
+    rm_ref, rv_ref = bn_r.running_mean.clone(), bn_r.running_var.clone()
     print(f"oracle {kind} B={B} S={S} size={size}: {time.time() - t0:.1f}s; logits absmax {ref.abs().max():.4f}")
-    # build the product model with identical parameters (same state_dict keys)
-    torch.manual_seed(1234)
-    if kind == "multimodal":
-        feats = [O.feature_extractor(), O.feature_extractor(), O.feature_extractor(1)]
-        model = MB.MultiModalModel(*feats, 7)
-    else:
-        model = O.ResNet50Custom(3, 7)
-    dnn_to_bnn(model, O.DEFAULT_PRIOR)
-    sd = {k: v for k, v in o_model.state_dict().items()}
-    missing = model.load_state_dict(sd, strict=False)
-    print("   load_state_dict:", missing)
-    model.to(dev).train()
+    o_model.load_state_dict(sd0)
+    hs = _emulate_fp16_operands(o_model)
+    emu = O.mc_logits(o_model, inputs, S, eps)
+    for h in hs:
+        h.remove()
+    calib = (emu - ref).abs().max().item()
+    print(f"   calibration: oracle with fp16-rounded conv operands differs from fp32 oracle by {calib:.3e}")
     eng = MCEngine(model)
     t0 = time.time()
     got = eng.forward_mc([t.to(dev) for t in inputs], S, eps=eps)
     torch.cuda.synchronize()
-    print(f"   engine time {time.time() - t0:.2f}s, launches {eng.launches}")
-    report(f"engine {kind} logits vs oracle fp32", got, ref, 2e-2)
-    print("   argmax equal:", bool((got.mean(0).argmax(1).cpu() == ref.mean(0).argmax(1)).all()),
-          " got:", got[0, 0].tolist(), " ref:", ref[0, 0].tolist())
-    # BN running stats of the first BN
+    print(f"   engine time {time.time() - t0:.2f}s")
+    err = (got.cpu() - ref).abs().max().item()
+    ok = err <= 3.0 * calib + 1e-4
+    print(f"engine {kind} B={B} size={size} logits vs oracle fp32: max_abs_err={err:.3e} (bound 3x calib = {3 * calib:.3e})"
+          f"  {'[OK]' if ok else '[FAIL]'}", flush=True)
+    if not ok:
+        FAILS.append((f"engine {kind}", f"err {err} > 3*{calib}"))
+    print("   argmax(mean logits) equal:", bool((got.mean(0).argmax(1).cpu() == ref.mean(0).argmax(1)).all()))
     bn_g = model.image_model_feat.bn1 if kind == "multimodal" else model.model.bn1
-    bn_r = o_model.image_model_feat.bn1 if kind == "multimodal" else o_model.model.bn1
-    report("   bn1.running_mean", bn_g.running_mean, bn_r.running_mean, 1e-3)
-    report("   bn1.running_var", bn_g.running_var, bn_r.running_var, 1e-3)
+    report("   bn1.running_mean after S passes", bn_g.running_mean, rm_ref, 2e-3)
+    report("   bn1.running_var after S passes", bn_g.running_var, rv_ref, 2e-3)
+    return got, ref
 
 
 GROUPS = {
@@ -326,7 +353,8 @@ GROUPS = {
         (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
         (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),
         (1, 2, 4, 4, 512, 512, 3, 1, 1), (3, 1, 6, 6, 128, 64, 3, 2, 1)]],
-    "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal")],
+    "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal"),
+                       run_case(t_engine, 2, 2, 256, "unimodal")],
 }
 
 if __name__ == "__main__":
