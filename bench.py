@@ -225,12 +225,39 @@ def run_ours(args):
         ms_step = ms / args.steps
         value = B / (ms_step / 1e3)
         e2e_value = B / (ms_e2e / args.steps / 1e3)
-        conv = [prof.get("mauv_gemm_f16", (0, 0.0)), prof.get("mauv_conv2d_im2col_f16", (0, 0.0))]
-        conv_calls, conv_ms = conv[0][0] + conv[1][0], conv[0][1] + conv[1][1]
+        fam = {}
+        for k, (c, t) in prof.items():
+            b = k.split("|")[0]
+            fc, ft = fam.get(b, (0, 0.0))
+            fam[b] = (fc + c, ft + t)
+        conv_calls = fam.get("mauv_gemm_f16", (0, 0.0))[0] + fam.get("mauv_conv2d_im2col_f16", (0, 0.0))[0]
+        conv_ms = fam.get("mauv_gemm_f16", (0, 0.0))[1] + fam.get("mauv_conv2d_im2col_f16", (0, 0.0))[1]
+        if args.detail:
+            rows = []
+            for k, (c, t) in prof.items():
+                if "|" not in k:
+                    continue
+                base, tag = k.split("|")
+                toks = {x[0]: x[1:] for x in tag.split() if x[0] in "GMNKC" and x[1:].isdigit()}
+                gf = gb = 0.0
+                if "K" in toks:
+                    g_, m_, n_, k_ = (int(toks[q]) for q in "GMNK")
+                    gf = 2.0 * g_ * m_ * n_ * k_ * c / 1e9
+                    kin = k_ if "x" not in tag or tag.split()[-1].startswith("1x1") else k_ // 9
+                    gb = g_ * m_ * (kin + n_) * 2 * c / 1e9
+                elif "C" in toks:
+                    g_, m_, c_ = (int(toks[q]) for q in "GMC")
+                    nbuf = 2 + int("res1" in tag) + int("dual1" in tag)
+                    gb = g_ * m_ * c_ * 2 * nbuf * c / 1e9
+                rows.append((t, base.replace("mauv_", ""), tag, c, gf / t if t else 0, gb / t if t else 0))
+            rows.sort(reverse=True)
+            sys.stderr.write("ms      kernel                 shape                                   calls TFLOP/s  TB/s(min traffic)\n")
+            for t, b, tag, c, tf, tb in rows[:60]:
+                sys.stderr.write(f"{t:7.2f} {b:22s} {tag:40s} {c:4d} {tf:7.1f} {tb:7.2f}\n")
         s_local = hi - lo
         conv_tflop = CONV_GFLOP_PER_TRIPLET_SAMPLE * B * s_local / 1e3
         achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
-        total_prof = sum(v[1] for v in prof.values()) or 1.0
+        total_prof = sum(v[1] for v in fam.values()) or 1.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -249,7 +276,7 @@ def run_ours(args):
                          "peak_source": peak_src, "traffic": None,
                          "launches_per_step": conv_calls, "avg_launch_ms": conv_ms / max(conv_calls, 1),
                          "share_of_step": conv_ms / total_prof},
-            "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+            "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
@@ -268,6 +295,7 @@ def main():
     ap.add_argument("--samples", type=int, default=S_FULL)
     ap.add_argument("--group", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="per-shape kernel table on stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

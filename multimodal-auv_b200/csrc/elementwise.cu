@@ -51,8 +51,47 @@ stem_im2col_kernel(const float* __restrict__ x, int B, int C, int H, int W, int 
 // produce per-(sample, channel) scale/shift, and replay the running-stat updates of
 // the S sequential reference passes (momentum 0.1, unbiased variance).
 // ---------------------------------------------------------------------------
+// Stage 1: [G][m_tiles][C] float2 partials -> [G][splits][C] double2. Block = 32 channels x 8 tile lanes, so a
+// warp reads 256 contiguous bytes per tile row; enough blocks (C/32 x splits x G) to pull the partials at HBM speed.
+__global__ void __launch_bounds__(256)
+bn_partial_reduce_kernel(const float2* __restrict__ partial, int m_tiles, int C, int splits,
+                         double2* __restrict__ out /*[G][splits][C]*/) {
+  __shared__ double2 red[8][32];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int sp = blockIdx.y, g = blockIdx.z;
+  const int per = (m_tiles + splits - 1) / splits;
+  const int t0 = sp * per;
+  const int t1 = min(m_tiles, t0 + per);
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    const float2* pp = partial + static_cast<long long>(g) * m_tiles * C + c;
+    int t = t0 + ty;
+    for (; t + 24 < t1; t += 32) {   // 4 independent loads in flight
+      const float2 a = __ldcs(pp + static_cast<long long>(t) * C);
+      const float2 b = __ldcs(pp + static_cast<long long>(t + 8) * C);
+      const float2 d = __ldcs(pp + static_cast<long long>(t + 16) * C);
+      const float2 e = __ldcs(pp + static_cast<long long>(t + 24) * C);
+      s1 += (static_cast<double>(a.x) + b.x) + (static_cast<double>(d.x) + e.x);
+      s2 += (static_cast<double>(a.y) + b.y) + (static_cast<double>(d.y) + e.y);
+    }
+    for (; t < t1; t += 8) {
+      const float2 a = __ldcs(pp + static_cast<long long>(t) * C);
+      s1 += a.x; s2 += a.y;
+    }
+  }
+  red[ty][cx] = make_double2(s1, s2);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { s1 += red[j][cx].x; s2 += red[j][cx].y; }
+    out[(static_cast<long long>(g) * splits + sp) * C + c] = make_double2(s1, s2);
+  }
+}
+
+// Stage 2: per-(sample, channel) scale/shift + the G sequential running-stat updates (momentum, unbiased var).
 __global__ void __launch_bounds__(128)
-bn_finalize_kernel(const float2* __restrict__ partial, int G, int m_tiles, int C, long long count,
+bn_finalize_kernel(const double2* __restrict__ partial, int G, int splits, int C, long long count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                    float2* __restrict__ scale_shift, float2* __restrict__ batch_stats) {
@@ -64,9 +103,9 @@ bn_finalize_kernel(const float2* __restrict__ partial, int G, int m_tiles, int C
   const float be = beta ? beta[c] : 0.f;
   for (int g = 0; g < G; ++g) {
     double s1 = 0.0, s2 = 0.0;
-    const float2* pp = partial + static_cast<long long>(g) * m_tiles * C + c;
-    for (int t = 0; t < m_tiles; ++t) {
-      const float2 v = pp[static_cast<long long>(t) * C];
+    const double2* pp = partial + static_cast<long long>(g) * splits * C + c;
+    for (int t = 0; t < splits; ++t) {
+      const double2 v = pp[static_cast<long long>(t) * C];
       s1 += v.x;
       s2 += v.y;
     }
@@ -83,30 +122,6 @@ bn_finalize_kernel(const float2* __restrict__ partial, int G, int m_tiles, int C
   }
   if (running_mean) running_mean[c] = rm;
   if (running_var) running_var[c] = rv;
-}
-
-// The partial buffer is [G][m_tiles][C]; one thread per channel reads with stride C ->
-// coalesced across the warp. For the big early layers (m_tiles up to 32768) split the
-// tile range over blockIdx.y and combine in a second tiny pass.
-__global__ void __launch_bounds__(128)
-bn_partial_reduce_kernel(const float2* __restrict__ partial, int G, int m_tiles, int C, int splits,
-                         float2* __restrict__ out /*[G][splits][C]*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int sp = blockIdx.y;
-  const int g = blockIdx.z;
-  if (c >= C) return;
-  const int per = (m_tiles + splits - 1) / splits;
-  const int t0 = sp * per;
-  const int t1 = min(m_tiles, t0 + per);
-  float s1 = 0.f, s2 = 0.f;
-  float c1 = 0.f, c2 = 0.f;  // Kahan compensation
-  const float2* pp = partial + static_cast<long long>(g) * m_tiles * C + c;
-  for (int t = t0; t < t1; ++t) {
-    const float2 v = pp[static_cast<long long>(t) * C];
-    float y = v.x - c1; float tt = s1 + y; c1 = (tt - s1) - y; s1 = tt;
-    y = v.y - c2; tt = s2 + y; c2 = (tt - s2) - y; s2 = tt;
-  }
-  out[(static_cast<long long>(g) * splits + sp) * C + c] = make_float2(s1, s2);
 }
 
 // ---------------------------------------------------------------------------
@@ -131,44 +146,78 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+// One thread owns one 8-channel group (c0 is loop invariant because the thread stride is a multiple of C/8),
+// keeps its 8 (scale, shift) pairs in registers and streams rows with 4 independent 16-byte loads in flight.
+template <bool HAS_Y2, bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const uint4* __restrict__ res,
               const uint4* __restrict__ y2, const float2* __restrict__ ss2, int relu,
-              long long per_sample_vec /* M*C/8 */, int C, long long total_vec, uint4* __restrict__ out) {
-  const int cvec = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i / per_sample_vec);
-    const int c0 = static_cast<int>(i % cvec) * 8;
-    float f[8];
-    unpack8(__ldg(y + i), f);
-    const float2* s = ss + static_cast<long long>(g) * C + c0;
+              long long per_sample_vec /* M*C/8 */, int C, uint4* __restrict__ out) {
+  const int g = blockIdx.y;
+  const unsigned cvec = C >> 3;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;   // multiple of 256 >= cvec (power of 2)
+  const int c0 = static_cast<int>(static_cast<unsigned>(tid) % cvec) * 8;
+  float sc[8], sh[8], sc2[8], sh2[8];
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(ss + static_cast<long long>(g) * C + c0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 t = __ldg(s + j);
-      f[j] = fmaf(f[j], t.x, t.y);
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(s4 + j);
+      sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
     }
-    if (y2) {
-      float f2[8];
-      unpack8(__ldg(y2 + i), f2);
-      const float2* s2 = ss2 + static_cast<long long>(g) * C + c0;
+    if (HAS_Y2) {
+      const float4* t4 = reinterpret_cast<const float4*>(ss2 + static_cast<long long>(g) * C + c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 t = __ldg(s2 + j);
-        f[j] += fmaf(f2[j], t.x, t.y);
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(t4 + j);
+        sc2[2 * j] = t.x; sh2[2 * j] = t.y; sc2[2 * j + 1] = t.z; sh2[2 * j + 1] = t.w;
       }
     }
-    if (res) {
-      float fr[8];
-      unpack8(__ldg(res + i), fr);
+  }
+  const long long base = static_cast<long long>(g) * per_sample_vec;
+  y += base; out += base;
+  if (HAS_Y2) y2 += base;
+  if (HAS_RES) res += base;
+  constexpr int U = 4;
+  for (long long i0 = tid; i0 < per_sample_vec; i0 += stride * U) {
+    uint4 vy[U], v2[U], vr[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fr[j];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < per_sample_vec) {
+        vy[u] = __ldcs(y + i);
+        if (HAS_Y2) v2[u] = __ldcs(y2 + i);
+        if (HAS_RES) vr[u] = __ldcs(res + i);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < per_sample_vec) {
+        float f[8];
+        unpack8(vy[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (HAS_Y2) {
+          float f2[8];
+          unpack8(v2[u], f2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += fmaf(f2[j], sc2[j], sh2[j]);
+        }
+        if (HAS_RES) {
+          float fr[8];
+          unpack8(vr[u], fr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += fr[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        out[i] = pack8(f);
+      }
     }
-    out[i] = pack8(f);
   }
 }
 
@@ -275,32 +324,29 @@ int mauv_stem_im2col_f16(const float* x_nchw, int B, int C, int H, int W, int kh
   return MAUV_OK;
 }
 
-// workspace: float2[G * splits * C] when m_tiles > 64 (see mauv_bn_finalize_ws_bytes)
+static int bn_splits(int m_tiles) {
+  int sp = (m_tiles + 31) / 32;
+  return sp < 1 ? 1 : (sp > 64 ? 64 : sp);
+}
+// workspace: double2[G][splits][C]
 long long mauv_bn_finalize_ws_bytes(int G, int m_tiles, int C) {
-  if (m_tiles <= 64) return 0;
-  return static_cast<long long>(G) * 64 * C * sizeof(float2);
+  return static_cast<long long>(G) * bn_splits(m_tiles) * C * sizeof(double2);
 }
 
 int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long long count,
                      const float* gamma, const float* beta, float eps, float momentum,
                      float* running_mean, float* running_var, float* scale_shift, float* batch_stats,
                      void* ws, void* stream) {
-  MAUV_CHECK_ARG(stats_partial && scale_shift && G >= 1 && m_tiles >= 1 && C >= 1 && count >= 1,
+  MAUV_CHECK_ARG(stats_partial && scale_shift && ws && G >= 1 && m_tiles >= 1 && C >= 1 && count >= 1,
                  "mauv_bn_finalize: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float2* part = reinterpret_cast<const float2*>(stats_partial);
-  int tiles = m_tiles;
-  if (m_tiles > 64) {
-    MAUV_CHECK_ARG(ws != nullptr, "mauv_bn_finalize: workspace required for m_tiles=%d", m_tiles);
-    const int splits = 64;
-    dim3 grid((C + 127) / 128, splits, G);
-    bn_partial_reduce_kernel<<<grid, 128, 0, st>>>(part, G, m_tiles, C, splits, static_cast<float2*>(ws));
-    MAUV_LAUNCH_CHECK("bn_partial_reduce_kernel");
-    part = static_cast<const float2*>(ws);
-    tiles = splits;
-  }
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, G, tiles, C, count, gamma, beta, eps, momentum,
-                                                      running_mean, running_var,
+  const int splits = bn_splits(m_tiles);
+  dim3 grid((C + 31) / 32, splits, G);
+  bn_partial_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(stats_partial), m_tiles, C, splits,
+                                                 static_cast<double2*>(ws));
+  MAUV_LAUNCH_CHECK("bn_partial_reduce_kernel");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(static_cast<const double2*>(ws), G, splits, C, count, gamma, beta,
+                                                      eps, momentum, running_mean, running_var,
                                                       reinterpret_cast<float2*>(scale_shift),
                                                       reinterpret_cast<float2*>(batch_stats));
   MAUV_LAUNCH_CHECK("bn_finalize_kernel");
@@ -312,11 +358,24 @@ int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residua
   MAUV_CHECK_ARG(y && scale_shift && out, "mauv_bn_act_f16: null pointer");
   MAUV_CHECK_ARG(C % 8 == 0, "mauv_bn_act_f16: C must be a multiple of 8");
   MAUV_CHECK_ARG((y2 == nullptr) == (scale_shift2 == nullptr), "mauv_bn_act_f16: y2 and scale_shift2 go together");
-  const long long per = M * C / 8, total = per * G;
-  bn_act_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift),
-      static_cast<const uint4*>(residual), static_cast<const uint4*>(y2),
-      reinterpret_cast<const float2*>(scale_shift2), relu, per, C, total, static_cast<uint4*>(out));
+  MAUV_CHECK_ARG((C & (C - 1)) == 0 && C <= 2048, "mauv_bn_act_f16: C must be a power of two <= 2048 (got %d)", C);
+  const long long per = M * C / 8;
+  long long bx = ceil_div_i64(per, 256 * 4);
+  const long long cap = static_cast<long long>(mauv_num_sms()) * 16 / (G < 16 ? G : 16) + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(static_cast<unsigned>(bx), G);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint4* py = static_cast<const uint4*>(y);
+  const float2* pss = reinterpret_cast<const float2*>(scale_shift);
+  const uint4* pres = static_cast<const uint4*>(residual);
+  const uint4* py2 = static_cast<const uint4*>(y2);
+  const float2* pss2 = reinterpret_cast<const float2*>(scale_shift2);
+  uint4* po = static_cast<uint4*>(out);
+  if (y2 && residual) bn_act_kernel<true, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
+  else if (y2) bn_act_kernel<true, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
+  else if (residual) bn_act_kernel<false, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
+  else bn_act_kernel<false, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
   MAUV_LAUNCH_CHECK("bn_act_kernel");
   return MAUV_OK;
 }

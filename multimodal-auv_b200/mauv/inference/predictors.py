@@ -26,6 +26,23 @@ def shard_samples(S: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def gather_sample_blocks(local: Optional[torch.Tensor], S: int, B: int, C: int, world: int, device) -> torch.Tensor:
+    """All ranks contribute logits of their sample block ([hi-lo, B, C], possibly empty) and receive the full
+    [S, B, C] stack in sample order. The only collective on the inference path: S*B*C*4 bytes."""
+    per = (S + world - 1) // world
+    pad = torch.zeros((per, B, C), dtype=torch.float32, device=device)
+    if local is not None and local.shape[0] > 0:
+        pad[: local.shape[0]] = local
+    gathered = torch.empty((world * per, B, C), dtype=torch.float32, device=device)   # concatenated along dim 0
+    torch.distributed.all_gather_into_tensor(gathered, pad)
+    gathered = gathered.view(world, per, B, C)
+    parts = []
+    for r in range(world):
+        rlo, rhi = shard_samples(S, world, r)
+        parts.append(gathered[r, : rhi - rlo])
+    return torch.cat(parts, dim=0).contiguous()
+
+
 class MCPredictor:
     """H2D -> S-batched MC forward -> MC statistics -> one D2H, for one batch."""
 
@@ -46,19 +63,8 @@ class MCPredictor:
         local = self.engine.forward_mc(inputs, hi - lo, sample0=lo, eps=eps, seed=seed) if hi > lo else None
         if self.world == 1:
             return local
-        B = inputs[0].shape[0]
-        per = (self.S + self.world - 1) // self.world
         C = local.shape[-1] if local is not None else self._num_classes()
-        pad = torch.zeros((per, B, C), dtype=torch.float32, device=self.device)
-        if local is not None:
-            pad[: hi - lo] = local
-        gathered = torch.empty((self.world, per, B, C), dtype=torch.float32, device=self.device)
-        torch.distributed.all_gather_into_tensor(gathered, pad)
-        parts = []
-        for r in range(self.world):
-            rlo, rhi = shard_samples(self.S, self.world, r)
-            parts.append(gathered[r, : rhi - rlo])
-        return torch.cat(parts, dim=0).contiguous()
+        return gather_sample_blocks(local, self.S, inputs[0].shape[0], C, self.world, self.device)
 
     def _num_classes(self) -> int:
         m = self.engine.model

@@ -11,11 +11,14 @@ from torchvision.models import ResNet50_Weights, resnet50
 
 
 def _resnet50_backbone() -> nn.Module:
-    try:
+    """torchvision ResNet-50 with the ImageNet checkpoint when it is already in the local torch hub cache
+    (the reference downloads it: models/base_models.py:15); random init otherwise - never touches the network."""
+    import os
+    ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(ResNet50_Weights.IMAGENET1K_V1.url))
+    if os.path.exists(ckpt):
         return resnet50(weights=ResNet50_Weights.IMAGENET1K_V1)
-    except Exception as e:  # offline: no cached checkpoint
-        logging.warning(f"ImageNet ResNet-50 weights unavailable ({type(e).__name__}); using random init")
-        return resnet50(weights=None)
+    logging.warning("ImageNet ResNet-50 checkpoint not in the local cache; using random init")
+    return resnet50(weights=None)
 
 
 class ResNet50Custom(nn.Module):

@@ -30,7 +30,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------ launch accounting / profiling
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
-KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2}
+KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2, "mauv_bn_finalize": 2}
 launch_count = 0
 _prof = None   # list of (name, start_event, end_event) while profiling
 
@@ -52,7 +52,7 @@ def stop_profile():
     return out
 
 
-def _run(name, fn, *args):
+def _run(name, fn, *args, tag=None):
     global launch_count
     launch_count += KERNELS_PER_CALL.get(name, 1)
     if _prof is not None:
@@ -60,7 +60,7 @@ def _run(name, fn, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _prof.append((name, e0, e1))
+        _prof.append((name if tag is None else f"{name}|{tag}", e0, e1))
     else:
         rc = fn(*args)
     _lib.check(rc)
@@ -133,7 +133,8 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] =
     if stats and stats_out is None:
         stats_out = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a.device)
     _run("mauv_gemm_f16", lib.mauv_gemm_f16, _ptr(a, F16), stride, _ptr(w, F16), _ptr(bias, F32), _ptr(out, F16),
-                                 _ptr(stats_out, F32) if stats else None, G, M, N, K, _stream())
+                                 _ptr(stats_out, F32) if stats else None, G, M, N, K, _stream(),
+         tag=f"G{G} M{M} N{N} K{K}" if _prof is not None else None)
     return out, (stats_out if stats else None)
 
 
@@ -155,7 +156,8 @@ def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int
         stats_out = torch.empty((G, gemm_m_tiles(B * Ho * Wo), Cout, 2), dtype=F32, device=x.device)
     _run("mauv_conv2d_im2col_f16", lib.mauv_conv2d_im2col_f16, _ptr(x, F16), _ptr(w, F16), _ptr(out, F16),
                                           _ptr(stats_out, F32) if stats else None, G, B, H, W, Cin, Cout,
-                                          kh, kw, stride, pad, _stream())
+                                          kh, kw, stride, pad, _stream(),
+         tag=f"G{G} M{B * Ho * Wo} N{Cout} K{kh * kw * Cin} {kh}x{kw}/{stride}" if _prof is not None else None)
     return out, (stats_out if stats else None)
 
 
@@ -184,7 +186,7 @@ def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.T
         out = torch.empty((G, Cc, 2), dtype=F32, device=stats_partial.device)
     bs = torch.empty((G, Cc, 2), dtype=F32, device=stats_partial.device) if want_batch_stats else None
     ws_bytes = lib.mauv_bn_finalize_ws_bytes(G, m_tiles, Cc)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=stats_partial.device) if ws_bytes else None
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=stats_partial.device)
     _run("mauv_bn_finalize", lib.mauv_bn_finalize, _ptr(stats_partial, F32), G, m_tiles, Cc, count, _ptr(gamma, F32),
                                     _ptr(beta, F32), eps, momentum, _ptr(running_mean, F32),
                                     _ptr(running_var, F32), _ptr(out), _ptr(bs), _ptr(ws), _stream())
@@ -199,7 +201,8 @@ def bn_act_f16(y: torch.Tensor, ss: torch.Tensor, G: int, C: int, *, residual: O
     if out is None:
         out = torch.empty_like(y)
     _run("mauv_bn_act_f16", lib.mauv_bn_act_f16, _ptr(y, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2, F16), _ptr(ss2, F32),
-                                   int(relu), G, M, C, _ptr(out, F16), _stream())
+                                   int(relu), G, M, C, _ptr(out, F16), _stream(),
+         tag=f"G{G} M{M} C{C} res{int(residual is not None)} dual{int(y2 is not None)}" if _prof is not None else None)
     return out
 
 
