@@ -47,19 +47,22 @@ struct GemmParams {
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // epilogue staging for the TMA store: per epilogue warp 2 buffers of 32 rows x 64 fp16 (128B-swizzled rows)
+  static constexpr int kOutBufBytes = 32 * 64 * 2;
+  static constexpr int kOutBytes = 4 /*warps*/ * 2 /*buffers*/ * kOutBufBytes;
   static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kStatBytes + kBarBytes;
+  static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
@@ -70,8 +73,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const uint32_t tiles_base = smem_base;
-  float* stat_smem = reinterpret_cast<float*>(smem_gen + kStages * L::kStageBytes);
-  const uint32_t bar_base = smem_base + kStages * L::kStageBytes + L::kStatBytes;
+  const uint32_t out_base = smem_base + kStages * L::kStageBytes;   // 1024-aligned (stage bytes are multiples of 1024)
+  float* stat_smem = reinterpret_cast<float*>(smem_gen + kStages * L::kStageBytes + L::kOutBytes);
+  const uint32_t bar_base = smem_base + kStages * L::kStageBytes + L::kOutBytes + L::kStatBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -79,13 +83,14 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + kStages * L::kStageBytes + L::kStatBytes + 8 * (2 * kStages + 4));
+      smem_gen + kStages * L::kStageBytes + L::kOutBytes + L::kStatBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) {
@@ -107,6 +112,21 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   const long long tiles_per_sample = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  // tile -> (g, m_tile, n_tile). n-tile fastest so concurrent CTAs share their A tile through L2; when A is shared
+  // by all samples (stem) the sample index is the fastest instead, so the G samples of one m-tile run together.
+  auto decode = [&](long long tile, int& g, int& m_tile, int& n_tile) {
+    if (p.a_batch_mul == 0) {
+      g = static_cast<int>(tile % p.G);
+      const long long rem = tile / p.G;
+      n_tile = static_cast<int>(rem % p.n_tiles);
+      m_tile = static_cast<int>(rem / p.n_tiles);
+    } else {
+      g = static_cast<int>(tile / tiles_per_sample);
+      const long long rem = tile - g * tiles_per_sample;
+      m_tile = static_cast<int>(rem / p.n_tiles);
+      n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+    }
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -114,10 +134,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int g = static_cast<int>(tile / tiles_per_sample);
-        const long long rem = tile - g * tiles_per_sample;
-        const int m_tile = static_cast<int>(rem / p.n_tiles);
-        const int n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+        int g, m_tile, n_tile;
+        decode(tile, g, m_tile, n_tile);
         const int m0 = m_tile * BM;
         // im2col start pixel of this tile
         int iq = 0, ip = 0, in_ = 0;
@@ -182,89 +200,99 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers -> fp16 -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous, clipped at
+    // the tensor bounds), 64 output channels at a time per warp. The BatchNorm (sum, sum of squares) come from the
+    // staged fp16 values - exactly the values the BN pass will normalise.
     const int ew = warp - 4;  // TMEM lane quarter accessible to this warp (warp_id % 4)
     const uint32_t lane = lane_id();
     const int et = threadIdx.x - 128;  // 0..127
-    uint32_t it = 0;
+    const uint32_t my_out = out_base + ew * (2 * L::kOutBufBytes);
+    uint32_t it = 0, blk = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int g = static_cast<int>(tile / tiles_per_sample);
-      const long long rem = tile - g * tiles_per_sample;
-      const int m_tile = static_cast<int>(rem / p.n_tiles);
-      const int n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+      int g, m_tile, n_tile;
+      decode(tile, g, m_tile, n_tile);
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row = m_tile * BM + ew * 32 + static_cast<int>(lane);
-      const bool row_ok = row < p.M;
+      const int row0 = m_tile * BM + ew * 32;
+      int rmax = p.M - row0;            // valid rows of this warp's 32-row slab
+      rmax = rmax < 0 ? 0 : (rmax > 32 ? 32 : rmax);
       const int n0 = n_tile * BN;
-      __half* yrow = p.y + (static_cast<long long>(g) * p.M + row) * p.N + n0;
       const float* bias = p.bias ? p.bias + static_cast<long long>(g) * p.N + n0 : nullptr;
       float* stat_buf = stat_smem + (it & 1u) * (4 * BN * 2);
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
 
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(ew * 32) << 16), r);
+      for (int cb = 0; cb < BN / 64; ++cb) {
+        const int col0 = cb * 64;
+        const bool cols_ok = (n0 + col0) < p.N;     // warp uniform
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(taddr + col0, ra);
+        tmem_ld_32x32b_x32(taddr + col0 + 32, rb);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (cb == BN / 64 - 1) {
+          // every TMEM read of this accumulator stage is complete -> hand it back to the MMA warp early
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        if (!cols_ok) {
+          if (p.stats) {
+            *reinterpret_cast<float4*>(stat_buf + (ew * BN + col0 + 2 * lane) * 2) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          continue;
+        }
         if (bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c * 32 + j < p.N) v[j] += bias[c * 32 + j];
-        }
-        // fp16 store: 32 consecutive channels of one output pixel = 64 bytes
-        if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n0 + c * 32 + q * 8 < p.N) {
-              uint4 pk;
-              __half2 h0 = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]);
-              __half2 h1 = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
-              __half2 h2 = __floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]);
-              __half2 h3 = __floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(yrow + c * 32 + q * 8) = pk;
-            }
-          }
-        }
-        if (p.stats) {
-          // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends
-          // with the sum of column c*32+j. Rows past M (next sample's pixels in im2col
-          // mode / zero fill in tiled mode) are excluded.
-          float s1[32], s2[32];
-#pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = row_ok ? v[j] : 0.f;
-            s1[j] = x;
-            s2[j] = x * x;
+            if (n0 + col0 + j < p.N) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + bias[col0 + j]);
+            if (n0 + col0 + 32 + j < p.N) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + bias[col0 + 32 + j]);
           }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send1 = upper ? s1[i] : s1[i + off];
-              const float send2 = upper ? s2[i] : s2[i + off];
-              const float recv1 = __shfl_xor_sync(0xffffffffu, send1, off);
-              const float recv2 = __shfl_xor_sync(0xffffffffu, send2, off);
-              s1[i] = (upper ? s1[i + off] : s1[i]) + recv1;
-              s2[i] = (upper ? s2[i + off] : s2[i]) + recv2;
-            }
-          }
-          stat_buf[(ew * BN + c * 32 + lane) * 2 + 0] = s1[0];
-          stat_buf[(ew * BN + c * 32 + lane) * 2 + 1] = s2[0];
         }
+        const uint32_t buf = my_out + (blk & 1u) * L::kOutBufBytes;
+        // the TMA store issued from this buffer two blocks ago must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t* src = (q < 4) ? &ra[q * 8] : &rb[(q - 4) * 8];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]), __uint_as_float(src[1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]), __uint_as_float(src[3]));
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]), __uint_as_float(src[5]));
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]), __uint_as_float(src[7]));
+          const uint32_t dst = buf + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h3))
+                       : "memory");
+        }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0 && rmax > 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmY)),
+                       "r"(buf), "r"(n0 + col0), "r"(row0), "r"(g)
+                       : "memory");
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (p.stats) {
+          // lane j owns output channels col0 + 2j, 2j+1: column sums over the warp's valid rows
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+          const uint32_t cbase = buf + ((lane & 3u) << 2);
+          const uint32_t chunk = lane >> 2;
+#pragma unroll 8
+          for (int r = 0; r < rmax; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + r * 128u + ((chunk ^ (r & 7u)) << 4)));
+            const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+            s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+            s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+          }
+          *reinterpret_cast<float4*>(stat_buf + (ew * BN + col0 + 2 * lane) * 2) = make_float4(s0, q0, s1, q1);
+        }
+        ++blk;
       }
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
 
       if (p.stats) {
         // combine the 4 epilogue warps and emit one deterministic partial per (tile, channel)
@@ -284,6 +312,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
+    // smem must stay valid until the last bulk stores have read it; global visibility at kernel end
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
 
   tcgen05_fence_before();
@@ -371,7 +402,7 @@ int make_im2col_map(CUtensorMap* tm, const void* base, int64_t C, int64_t W, int
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const GemmParams& p,
                 cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
@@ -381,7 +412,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 256, L::kTotal, stream>>>(tmA, tmB, p);
+  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 256, L::kTotal, stream>>>(tmA, tmB, tmY, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
@@ -394,14 +425,17 @@ int pick_bn(int N) {
 
 int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   const int bn = pick_bn(p.N);
+  // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
+  CUtensorMap tmY;
+  if (int rc = make_tiled_map(&tmY, p.y, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
   p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
   p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
   p.total_tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.G;
   if (p.total_tiles == 0) return MAUV_OK;
   switch (bn) {
-    case 64: return launch_gemm<64>(tmA, tmB, p, stream);
-    case 128: return launch_gemm<128>(tmA, tmB, p, stream);
-    default: return launch_gemm<256>(tmA, tmB, p, stream);
+    case 64: return launch_gemm<64>(tmA, tmB, tmY, p, stream);
+    case 128: return launch_gemm<128>(tmA, tmB, tmY, p, stream);
+    default: return launch_gemm<256>(tmA, tmB, tmY, p, stream);
   }
 }
 
