@@ -1,0 +1,117 @@
+"""Kernel micro-benchmarks on the B200 box (CUDA events, L2 flushed by the working-set size).
+  python tests/gpu_microbench.py gemm  G M N K [iters]
+  python tests/gpu_microbench.py conv  G B H W Cin Cout k stride pad [iters]
+  python tests/gpu_microbench.py bnact G M C [iters]
+  python tests/gpu_microbench.py mcreduce S B C [iters]
+  python tests/gpu_microbench.py kl | sample
+  python tests/gpu_microbench.py layers        (the ResNet-50 trunk shapes at B=256)
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "multimodal-auv_b200"))
+import torch
+
+from mauv import ops
+
+dev = "cuda"
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm(G, M, N, K, iters=5, shared=False, quiet=False):
+    a = torch.randn((M, K) if shared else (G, M, K), device=dev, dtype=torch.float16)
+    w = torch.randn(G, N, K, device=dev, dtype=torch.float16)
+    y = torch.empty(G, M, N, device=dev, dtype=torch.float16)
+    st = torch.empty(G, ops.gemm_m_tiles(M), N, 2, device=dev)
+    ms = timeit(lambda: ops.gemm_f16(a, w, stats=True, shared_a=shared, out=y, stats_out=st), iters)
+    fl = 2.0 * G * M * N * K
+    by = (a.numel() + y.numel() + w.numel()) * 2 + st.numel() * 4
+    if not quiet:
+        print(f"gemm G={G} M={M} N={N} K={K} shared={shared}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e9:.2f} TB/s", flush=True)
+    return ms
+
+
+def conv(G, B, H, W, Cin, Cout, k, stride, pad, iters=5):
+    x = torch.randn(G * B, H, W, Cin, device=dev, dtype=torch.float16)
+    w = torch.randn(G, Cout, k * k * Cin, device=dev, dtype=torch.float16)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty(G * B, Ho, Wo, Cout, device=dev, dtype=torch.float16)
+    st = torch.empty(G, ops.gemm_m_tiles(B * Ho * Wo), Cout, 2, device=dev)
+    ms = timeit(lambda: ops.conv2d_im2col_f16(x, w, G, k, k, stride, pad, stats=True, out=y, stats_out=st), iters)
+    fl = 2.0 * G * B * Ho * Wo * Cout * k * k * Cin
+    by = (x.numel() + y.numel() + w.numel()) * 2 + st.numel() * 4
+    print(f"conv G={G} B={B} {H}x{W} {Cin}->{Cout} k{k}/{stride}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e9:.2f} TB/s", flush=True)
+    return ms
+
+
+def bnact(G, M, C, iters=5):
+    y = torch.randn(G, M, C, device=dev, dtype=torch.float16)
+    r = torch.randn(G, M, C, device=dev, dtype=torch.float16)
+    ss = torch.rand(G, C, 2, device=dev)
+    out = torch.empty_like(y)
+    for name, kw, nbuf in (("plain", {}, 2), ("residual", {"residual": r}, 3), ("dual", {"y2": r, "ss2": ss}, 3)):
+        ms = timeit(lambda: ops.bn_act_f16(y, ss, G, C, out=out, **kw), iters)
+        print(f"bn_act {name} G={G} M={M} C={C}: {ms:.3f} ms  {y.numel() * 2 * nbuf / ms / 1e9:.2f} TB/s", flush=True)
+
+
+def mcreduce(S, B, C, iters=5):
+    lg = torch.randn(S, B, C, device=dev)
+    ms = timeit(lambda: ops.mc_reduce(lg, 1e-8), iters)
+    by = S * B * C * 4 + B * (2 * C + 4) * 4 + B * 16
+    print(f"mc_reduce S={S} B={B} C={C}: {ms:.4f} ms  {by / ms / 1e6:.1f} GB/s (algorithmic bytes {by / 1e6:.1f} MB)", flush=True)
+
+
+def kl():
+    shapes = [(2048, 512, 1, 1)] * 40 + [(512, 512, 3, 3)] * 20
+    mus = [torch.randn(s, device=dev) * 0.05 for s in shapes]
+    rhos = [torch.randn(s, device=dev) - 4 for s in shapes]
+    gr = [(torch.zeros_like(m), torch.zeros_like(m)) for m in mus]
+    n = sum(m.numel() for m in mus)
+    plan = ops.KlPlan(list(zip(mus, rhos)), dev)
+    ms = timeit(lambda: plan.run(0.0, 1.0), 5)
+    print(f"kl fwd n={n}: {ms:.3f} ms  {n * 8 / ms / 1e6:.1f} GB/s (8 B/param)", flush=True)
+    plan2 = ops.KlPlan(list(zip(mus, rhos)), dev, grads=gr)
+    ms = timeit(lambda: plan2.run(0.0, 1.0, grad_scale=1e-3), 5)
+    print(f"kl fwd+bwd n={n}: {ms:.3f} ms  {n * 24 / ms / 1e6:.1f} GB/s (24 B/param)", flush=True)
+
+
+def sample():
+    for shape, G in (((512, 512, 3, 3), 10), ((2048, 1024, 1, 1), 10), ((64, 64, 3, 3), 10)):
+        mu = torch.randn(shape, device=dev) * 0.05
+        rho = torch.randn(shape, device=dev) - 4
+        n = mu.numel()
+        out = torch.empty(G, shape[0], n // shape[0], device=dev, dtype=torch.float16)
+        ms = timeit(lambda: ops.sample_weights_f16(mu, rho, G, seed=1, layer_id=3, out=out), 5)
+        print(f"sample_weights {shape} G={G} philox: {ms:.3f} ms  {(n * 8 + G * n * 2) / ms / 1e6:.1f} GB/s "
+              f"({G * n / ms / 1e6:.1f} Gweights/s)", flush=True)
+
+
+def layers():
+    G, B = 4, 256
+    for (M, N, K) in [(B * 4096, 256, 64), (B * 4096, 64, 256), (B * 4096, 64, 64), (B * 1024, 512, 128),
+                      (B * 1024, 128, 512), (B * 256, 1024, 256), (B * 256, 256, 1024), (B * 64, 2048, 512),
+                      (B * 64, 512, 2048)]:
+        gemm(G, M, N, K, 3)
+    gemm(G, B * 16384, 64, 152, 3, shared=True)
+    for (H, Cin, Cout, k, s) in [(64, 64, 64, 3, 1), (64, 128, 128, 3, 2), (32, 128, 128, 3, 1), (32, 256, 256, 3, 2),
+                                 (16, 256, 256, 3, 1), (16, 512, 512, 3, 2), (8, 512, 512, 3, 1), (64, 256, 512, 1, 2)]:
+        conv(G, B, H, H, Cin, Cout, k, s, k // 2, 3)
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    a = [int(x) for x in sys.argv[2:]]
+    {"gemm": gemm, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers}[cmd](*a)
