@@ -85,11 +85,12 @@ int mauv_stem_im2col_f16(const float* x_nchw, int B, int C, int H, int W, int kh
 long long mauv_bn_finalize_ws_bytes(int G, int m_tiles, int C);
 /* scale_shift: [G][C][2] fp32 (y*scale+shift == gamma*(y-mean)/sqrt(var+eps)+beta, biased var);
  * running_mean/var (nullable) receive the G sequential momentum updates (unbiased var) the
- * reference's G passes would apply; batch_stats (nullable): [G][C][2] = (mean, biased var). */
+ * reference's G passes would apply and num_batches_tracked (nullable, int64) += G;
+ * batch_stats (nullable): [G][C][2] = (mean, biased var). G <= 64 per call. */
 int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long long count,
                      const float* gamma, const float* beta, float eps, float momentum,
-                     float* running_mean, float* running_var, float* scale_shift, float* batch_stats,
-                     void* ws, void* stream);
+                     float* running_mean, float* running_var, long long* num_batches_tracked,
+                     float* scale_shift, float* batch_stats, void* ws, void* stream);
 /* out = relu?( y*ss + [residual] + [y2*ss2] ), all [G][M][C] fp16. */
 int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residual, const void* y2,
                     const float* scale_shift2, int relu, int G, long long M, int C, void* out, void* stream);

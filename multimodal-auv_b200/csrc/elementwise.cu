@@ -89,39 +89,51 @@ bn_partial_reduce_kernel(const float2* __restrict__ partial, int m_tiles, int C,
   }
 }
 
-// Stage 2: per-(sample, channel) scale/shift + the G sequential running-stat updates (momentum, unbiased var).
-__global__ void __launch_bounds__(128)
+// Stage 2: per-(sample, channel) scale/shift in parallel over (32 channels x samples), then the G sequential
+// running-stat updates (momentum, unbiased variance) and the num_batches_tracked increment of G reference passes.
+constexpr int BN_MAX_G = 64;
+__global__ void __launch_bounds__(512)
 bn_finalize_kernel(const double2* __restrict__ partial, int G, int splits, int C, long long count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                   float2* __restrict__ scale_shift, float2* __restrict__ batch_stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float rm = running_mean ? running_mean[c] : 0.f;
-  float rv = running_var ? running_var[c] : 1.f;
-  const float ga = gamma ? gamma[c] : 1.f;
-  const float be = beta ? beta[c] : 0.f;
-  for (int g = 0; g < G; ++g) {
-    double s1 = 0.0, s2 = 0.0;
-    const double2* pp = partial + static_cast<long long>(g) * splits * C + c;
-    for (int t = 0; t < splits; ++t) {
-      const double2 v = pp[static_cast<long long>(t) * C];
-      s1 += v.x;
-      s2 += v.y;
+                   long long* __restrict__ num_batches_tracked, float2* __restrict__ scale_shift,
+                   float2* __restrict__ batch_stats) {
+  __shared__ float2 mv[BN_MAX_G][32];   // (mean, unbiased var) per sample for the running-stat replay
+  const int cx = threadIdx.x, gy = threadIdx.y;
+  const int c = blockIdx.x * 32 + cx;
+  if (c < C) {
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    for (int g = gy; g < G; g += blockDim.y) {
+      double s1 = 0.0, s2 = 0.0;
+      const double2* pp = partial + static_cast<long long>(g) * splits * C + c;
+      for (int t = 0; t < splits; ++t) {
+        const double2 v = pp[static_cast<long long>(t) * C];
+        s1 += v.x;
+        s2 += v.y;
+      }
+      const double mean = s1 / static_cast<double>(count);
+      double var = s2 / static_cast<double>(count) - mean * mean;  // biased (normalisation)
+      if (var < 0.0) var = 0.0;
+      const float inv_std = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float sc = ga * inv_std;
+      scale_shift[static_cast<long long>(g) * C + c] = make_float2(sc, be - static_cast<float>(mean) * sc);
+      if (batch_stats) batch_stats[static_cast<long long>(g) * C + c] = make_float2(static_cast<float>(mean), static_cast<float>(var));
+      const double unbiased = count > 1 ? var * static_cast<double>(count) / static_cast<double>(count - 1) : var;
+      mv[g][cx] = make_float2(static_cast<float>(mean), static_cast<float>(unbiased));
     }
-    const double mean = s1 / static_cast<double>(count);
-    double var = s2 / static_cast<double>(count) - mean * mean;  // biased (normalisation)
-    if (var < 0.0) var = 0.0;
-    const float inv_std = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = ga * inv_std;
-    scale_shift[static_cast<long long>(g) * C + c] = make_float2(sc, be - static_cast<float>(mean) * sc);
-    if (batch_stats) batch_stats[static_cast<long long>(g) * C + c] = make_float2(static_cast<float>(mean), static_cast<float>(var));
-    const double unbiased = count > 1 ? var * static_cast<double>(count) / static_cast<double>(count - 1) : var;
-    rm = (1.f - momentum) * rm + momentum * static_cast<float>(mean);
-    rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  __syncthreads();
+  if (gy == 0 && c < C && running_mean && running_var) {
+    float rm = running_mean[c], rv = running_var[c];
+    for (int g = 0; g < G; ++g) {
+      rm = (1.f - momentum) * rm + momentum * mv[g][cx].x;
+      rv = (1.f - momentum) * rv + momentum * mv[g][cx].y;
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+  if (num_batches_tracked && blockIdx.x == 0 && cx == 0 && gy == 0) *num_batches_tracked += G;
 }
 
 // ---------------------------------------------------------------------------
@@ -335,20 +347,22 @@ long long mauv_bn_finalize_ws_bytes(int G, int m_tiles, int C) {
 
 int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long long count,
                      const float* gamma, const float* beta, float eps, float momentum,
-                     float* running_mean, float* running_var, float* scale_shift, float* batch_stats,
-                     void* ws, void* stream) {
+                     float* running_mean, float* running_var, long long* num_batches_tracked,
+                     float* scale_shift, float* batch_stats, void* ws, void* stream) {
   MAUV_CHECK_ARG(stats_partial && scale_shift && ws && G >= 1 && m_tiles >= 1 && C >= 1 && count >= 1,
                  "mauv_bn_finalize: bad argument");
+  MAUV_CHECK_ARG(G <= BN_MAX_G, "mauv_bn_finalize: at most %d samples per call (got %d)", BN_MAX_G, G);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int splits = bn_splits(m_tiles);
   dim3 grid((C + 31) / 32, splits, G);
   bn_partial_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(stats_partial), m_tiles, C, splits,
                                                  static_cast<double2*>(ws));
   MAUV_LAUNCH_CHECK("bn_partial_reduce_kernel");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(static_cast<const double2*>(ws), G, splits, C, count, gamma, beta,
-                                                      eps, momentum, running_mean, running_var,
-                                                      reinterpret_cast<float2*>(scale_shift),
-                                                      reinterpret_cast<float2*>(batch_stats));
+  dim3 fblock(32, G < 16 ? G : 16);
+  bn_finalize_kernel<<<(C + 31) / 32, fblock, 0, st>>>(static_cast<const double2*>(ws), G, splits, C, count, gamma, beta,
+                                                       eps, momentum, running_mean, running_var, num_batches_tracked,
+                                                       reinterpret_cast<float2*>(scale_shift),
+                                                       reinterpret_cast<float2*>(batch_stats));
   MAUV_LAUNCH_CHECK("bn_finalize_kernel");
   return MAUV_OK;
 }

@@ -12,11 +12,12 @@
 // F.conv2d / F.linear per MC pass (bayesian-torch conv_variational.py forward;
 // called from models/base_models.py:74-90 through torchvision resnet.py:143-165).
 //
-// Structure (one persistent CTA per SM, 8 warps):
+// Structure (one persistent CTA per SM, 12 warps):
 //   warp 0      TMA producer   (one elected lane), kStages-deep smem ring
 //   warp 1      MMA issuer     (one elected lane), tcgen05.mma 128 x BN x 16
 //   warp 2      TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4..7  epilogue: tcgen05.ld -> fp16 store + per-channel sum / sum-of-squares
+//   warps 4..11 epilogue (two sets of 4 TMEM lane quarters, alternating 64-column blocks):
+//               tcgen05.ld -> fp16 -> swizzled smem -> TMA store, + per-channel sum / sum-of-squares
 //               (the BatchNorm batch statistics of the reference's BN-train pass)
 // Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x) with the
 // n-tile fastest so that CTAs running concurrently share their A tile in L2.
@@ -47,20 +48,22 @@ struct GemmParams {
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  // epilogue warps: one set of 4 (TMEM lane quarters) per 64-column block in flight; two sets when BN >= 128
+  static constexpr int kEpiWarps = (BN >= 128) ? 8 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging for the TMA store: per epilogue warp 2 buffers of 32 rows x 64 fp16 (128B-swizzled rows)
   static constexpr int kOutBufBytes = 32 * 64 * 2;
-  static constexpr int kOutBytes = 4 /*warps*/ * 2 /*buffers*/ * kOutBufBytes;
+  static constexpr int kOutBytes = kEpiWarps * 2 /*buffers*/ * kOutBufBytes;
   static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
   using L = SmemLayout<BN>;
@@ -99,7 +102,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(a), L::kEpiWarps);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -198,15 +201,22 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + L::kEpiWarps) {
     // ===================== epilogue =====================
     // TMEM -> registers -> fp16 -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous, clipped at
     // the tensor bounds), 64 output channels at a time per warp. The BatchNorm (sum, sum of squares) come from the
     // staged fp16 values - exactly the values the BN pass will normalise.
-    const int ew = warp - 4;  // TMEM lane quarter accessible to this warp (warp_id % 4)
+    constexpr int kEpiThreads = L::kEpiWarps * 32;
+    constexpr int kColSets = L::kEpiWarps / 4;       // column-block sets working concurrently
+    const int ew = warp & 3;                  // TMEM lane quarter accessible to this warp (warp_id % 4)
+    const int cset = (warp - 4) >> 2;         // which 64-column blocks this warp takes (cb = cset, cset + kColSets, ..)
     const uint32_t lane = lane_id();
-    const int et = threadIdx.x - 128;  // 0..127
-    const uint32_t my_out = out_base + ew * (2 * L::kOutBufBytes);
+    const int et = threadIdx.x - 128;         // 0 .. kEpiThreads-1
+    const uint32_t my_out = out_base + (warp - 4) * (2 * L::kOutBufBytes);
+    // swizzled 16-byte chunk offsets of this lane's channel pair for rows r = 0..7 (mod 8)
+    uint32_t sw_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sw_off[j] = (((lane >> 2) ^ static_cast<uint32_t>(j)) << 4) + ((lane & 3u) << 2);
     uint32_t it = 0, blk = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int g, m_tile, n_tile;
@@ -224,14 +234,14 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 64; ++cb) {
+      for (int cb = cset; cb < BN / 64; cb += kColSets) {
         const int col0 = cb * 64;
         const bool cols_ok = (n0 + col0) < p.N;     // warp uniform
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr + col0, ra);
         tmem_ld_32x32b_x32(taddr + col0 + 32, rb);
         tmem_ld_wait();
-        if (cb == BN / 64 - 1) {
+        if (cb + kColSets >= BN / 64) {
           // every TMEM read of this accumulator stage is complete -> hand it back to the MMA warp early
           tcgen05_fence_before();
           __syncwarp();
@@ -277,18 +287,35 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (p.stats) {
-          // lane j owns output channels col0 + 2j, 2j+1: column sums over the warp's valid rows
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-          const uint32_t cbase = buf + ((lane & 3u) << 2);
-          const uint32_t chunk = lane >> 2;
-#pragma unroll 8
-          for (int r = 0; r < rmax; ++r) {
-            uint32_t w;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + r * 128u + ((chunk ^ (r & 7u)) << 4)));
+          // lane j owns output channels col0 + 2j, 2j+1: column sums over the warp's valid rows, packed fp32x2 math
+          unsigned long long sa = 0ull, sb = 0ull, qa = 0ull, qb = 0ull;   // (s0,s1) / (q0,q1), two chains for ILP
+          auto acc2 = [&](uint32_t w, unsigned long long& s2, unsigned long long& q2) {
             const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-            s0 += f.x; q0 = fmaf(f.x, f.x, q0);
-            s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+            const unsigned long long f2 = *reinterpret_cast<const unsigned long long*>(&f);
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(f2));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q2) : "l"(f2));
+          };
+          if (rmax == 32) {
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+              uint32_t w0, w1;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(buf + sw_off[r & 7] + r * 128u));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(buf + sw_off[(r + 1) & 7] + (r + 1) * 128u));
+              acc2(w0, sa, qa);
+              acc2(w1, sb, qb);
+            }
+          } else {
+            for (int r = 0; r < rmax; ++r) {
+              uint32_t w0;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0)
+                           : "r"(buf + ((((lane >> 2) ^ (r & 7u)) << 4) + ((lane & 3u) << 2)) + r * 128u));
+              acc2(w0, sa, qa);
+            }
           }
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(sb));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(qa) : "l"(qb));
+          const float2 sf = *reinterpret_cast<float2*>(&sa), qf = *reinterpret_cast<float2*>(&qa);
+          const float s0 = sf.x, s1 = sf.y, q0 = qf.x, q1 = qf.y;
           *reinterpret_cast<float4*>(stat_buf + (ew * BN + col0 + 2 * lane) * 2) = make_float4(s0, q0, s1, q1);
         }
         ++blk;
@@ -296,8 +323,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
       if (p.stats) {
         // combine the 4 epilogue warps and emit one deterministic partial per (tile, channel)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int j = et; j < BN; j += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int j = et; j < BN; j += kEpiThreads) {
           if (n0 + j < p.N) {
             float a = 0.f, b = 0.f;
 #pragma unroll
@@ -412,7 +439,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 256, L::kTotal, stream>>>(tmA, tmB, tmY, p);
+  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 384, L::kTotal, stream>>>(tmA, tmB, tmY, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }

@@ -11,67 +11,121 @@
 
 namespace {
 
+// One thread per batch row; the block's [128 rows x C] slab of every MC sample is fetched with 16-byte cp.async
+// into a 4-deep shared-memory ring (fully coalesced HBM reads, ~14 KB in flight per block), each thread then reads
+// its C logits with a stride-C (odd -> conflict-free) pattern. Outputs are staged through the same smem so that
+// the [B, C] arrays are written coalesced as well.
+constexpr int MC_ROWS = 128;
+constexpr int MC_STAGES = 4;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int MAXC>
-__global__ void __launch_bounds__(128)
-mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, float eps_entropy,
+__global__ void __launch_bounds__(MC_ROWS)
+mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, float eps_entropy, int vec_ok,
                  float* __restrict__ mean_prob, float* __restrict__ mean_logit,
                  long long* __restrict__ argmax_prob, long long* __restrict__ argmax_logit,
                  float* __restrict__ pred_entropy, float* __restrict__ aleatoric,
                  float* __restrict__ mutual_info, float* __restrict__ var_mean) {
-  const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  extern __shared__ __align__(16) float mc_smem[];   // [MC_STAGES][MC_ROWS * C]
+  const int tid = threadIdx.x;
+  const long long b0 = static_cast<long long>(blockIdx.x) * MC_ROWS;
+  const int rows = static_cast<int>(B - b0 < MC_ROWS ? B - b0 : MC_ROWS);
+  const int nf = rows * C;                 // floats of this block's slab per sample
+  const int slab = MC_ROWS * C;
+  const uint32_t smem0 = smem_u32(mc_smem);
+
+  auto issue = [&](int s) {
+    if (s < S) {
+      const float* src = logits + (static_cast<long long>(s) * B + b0) * C;
+      const uint32_t dst = smem0 + static_cast<uint32_t>((s % MC_STAGES) * slab) * 4u;
+      if (vec_ok) {
+        const int nv = nf >> 2;
+        for (int i = tid; i < nv; i += MC_ROWS) cp_async_16(dst + i * 16u, src + i * 4);
+        for (int i = (nv << 2) + tid; i < nf; i += MC_ROWS) cp_async_4(dst + i * 4u, src + i);
+      } else {
+        for (int i = tid; i < nf; i += MC_ROWS) cp_async_4(dst + i * 4u, src + i);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int s = 0; s < MC_STAGES - 1; ++s) issue(s);
+
+  const bool active = tid < rows;
   float sum_p[MAXC], sum_l[MAXC], wmean[MAXC], m2[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) { sum_p[c] = 0.f; sum_l[c] = 0.f; wmean[c] = 0.f; m2[c] = 0.f; }
   float sum_h = 0.f;
   for (int s = 0; s < S; ++s) {
-    const float* row = logits + (static_cast<long long>(s) * B + b) * C;
-    float x[MAXC];
-    float mx = -INFINITY;
+    issue(s + MC_STAGES - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(MC_STAGES - 1) : "memory");
+    __syncthreads();
+    if (active) {
+      const float* row = mc_smem + (s % MC_STAGES) * slab + tid * C;
+      float x[MAXC];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      x[c] = (c < C) ? __ldg(row + c) : -INFINITY;
-      mx = fmaxf(mx, x[c]);
-    }
-    float z = 0.f;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      x[c] = (c < C) ? (sum_l[c] += x[c], expf(x[c] - mx)) : 0.f;
-      z += x[c];
-    }
-    const float inv_n = 1.f / static_cast<float>(s + 1);
-    float h = 0.f;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const float pc = x[c] / z;
-        sum_p[c] += pc;
-        const float d = pc - wmean[c];
-        wmean[c] += d * inv_n;
-        m2[c] = fmaf(d, pc - wmean[c], m2[c]);
-        h -= pc * logf(pc + eps_entropy);
+      for (int c = 0; c < MAXC; ++c) {
+        x[c] = (c < C) ? row[c] : -INFINITY;
+        mx = fmaxf(mx, x[c]);
       }
+      float z = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) { sum_l[c] += x[c]; x[c] = expf(x[c] - mx); } else { x[c] = 0.f; }
+        z += x[c];
+      }
+      const float inv_n = 1.f / static_cast<float>(s + 1);
+      const float inv_z = 1.f / z;
+      float h = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const float pc = x[c] * inv_z;
+          sum_p[c] += pc;
+          const float d = pc - wmean[c];
+          wmean[c] += d * inv_n;
+          m2[c] = fmaf(d, pc - wmean[c], m2[c]);
+          h -= pc * logf(pc + eps_entropy);
+        }
+      }
+      sum_h += h;
     }
-    sum_h += h;
+    __syncthreads();   // slab s % MC_STAGES is refilled by the next iteration's issue()
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+
   const float inv_s = 1.f / static_cast<float>(S);
   const float inv_sm1 = 1.f / static_cast<float>(S - 1);  // S == 1 -> inf; 0*inf = NaN like torch.var
   float hp = 0.f, vsum = 0.f;
   float best_p = -INFINITY, best_l = -INFINITY;
   int arg_p = 0, arg_l = 0;
+  float* st_p = mc_smem;            // stage mean_prob / mean_logit for coalesced stores
+  float* st_l = mc_smem + slab;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
-    if (c < C) {
+    if (c < C && active) {
       const float mp = sum_p[c] * inv_s;
       const float ml = sum_l[c] * inv_s;
-      if (mean_prob) mean_prob[b * C + c] = mp;
-      if (mean_logit) mean_logit[b * C + c] = ml;
+      st_p[tid * C + c] = mp;
+      st_l[tid * C + c] = ml;
       hp -= mp * logf(mp + eps_entropy);
       vsum += m2[c] * inv_sm1;
       if (mp > best_p) { best_p = mp; arg_p = c; }   // first maximum wins, as torch.argmax
       if (ml > best_l) { best_l = ml; arg_l = c; }
     }
   }
+  __syncthreads();
+  if (mean_prob) for (int i = tid; i < nf; i += MC_ROWS) mean_prob[b0 * C + i] = st_p[i];
+  if (mean_logit) for (int i = tid; i < nf; i += MC_ROWS) mean_logit[b0 * C + i] = st_l[i];
+  if (!active) return;
+  const long long b = b0 + tid;
   const float al = sum_h * inv_s;
   if (argmax_prob) argmax_prob[b] = arg_p;
   if (argmax_logit) argmax_logit[b] = arg_l;
@@ -110,38 +164,58 @@ kl_kernel(const KlTensor* __restrict__ table, const long long* __restrict__ chun
     const float inv_n = 1.f / static_cast<float>(t.n);
     const float gs = grad_scale * inv_n;
     float local = 0.f;
+    constexpr int REPS = KL_CHUNK / (256 * 4);
+    float mu[REPS][4], rho[REPS][4];
+    // all loads of the chunk first (8 independent 16-byte requests per thread in flight)
 #pragma unroll
-    for (int rep = 0; rep < KL_CHUNK / (256 * 4); ++rep) {
+    for (int rep = 0; rep < REPS; ++rep) {
       const long long e0 = base + (rep * 256 + threadIdx.x) * 4;
-      if (e0 >= t.n) continue;
-      float mu[4], rho[4];
       const bool vec = (e0 + 3 < t.n) && ((reinterpret_cast<uintptr_t>(t.mu + e0) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(t.rho + e0) & 15) == 0);
       if (vec) {
-        const float4 a = *reinterpret_cast<const float4*>(t.mu + e0);
-        const float4 b = *reinterpret_cast<const float4*>(t.rho + e0);
-        mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w;
-        rho[0] = b.x; rho[1] = b.y; rho[2] = b.z; rho[3] = b.w;
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(t.mu + e0));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(t.rho + e0));
+        mu[rep][0] = a.x; mu[rep][1] = a.y; mu[rep][2] = a.z; mu[rep][3] = a.w;
+        rho[rep][0] = b.x; rho[rep][1] = b.y; rho[rep][2] = b.z; rho[rep][3] = b.w;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          mu[i] = (e0 + i < t.n) ? t.mu[e0 + i] : 0.f;
-          rho[i] = (e0 + i < t.n) ? t.rho[e0 + i] : 0.f;
+          mu[rep][i] = (e0 + i < t.n) ? t.mu[e0 + i] : 0.f;
+          rho[rep][i] = (e0 + i < t.n) ? t.rho[e0 + i] : 0.f;
         }
       }
+    }
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+      const long long e0 = base + (rep * 256 + threadIdx.x) * 4;
+      float gm[4], gr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (e0 + i < t.n) {
-          const float ex = expf(rho[i]);
-          const float sigma = log1pf(ex);
-          const float d = mu[i] - prior_mu;
-          local += log_sp - logf(sigma) + (sigma * sigma + d * d) * inv_2sp2 - 0.5f;
-          if (t.gmu) {
-            t.gmu[e0 + i] += gs * d * inv_sp2;
-            const float dsig = sigma * inv_sp2 - 1.f / sigma;
-            const float sgm = ex / (1.f + ex);       // d softplus / d rho
-            t.grho[e0 + i] += gs * dsig * (isinf(ex) ? 1.f : sgm);
-          }
+        // sigma = log1p(exp(rho)); hardware ex2/lg2 are accurate to ~1e-6 relative here, far inside the 1e-4 KL
+        // tolerance; for tiny exp(rho) (MOPED gives rho down to -46) use the series so sigma never flushes to 0.
+        const float ex = __expf(rho[rep][i]);
+        const float sigma = ex < 1e-3f ? ex * (1.f - 0.5f * ex + 0.33333333f * ex * ex) : __logf(1.f + ex);
+        const float log_sigma = ex < 1e-3f ? rho[rep][i] + __logf(1.f - 0.5f * ex + 0.33333333f * ex * ex) : __logf(sigma);
+        const float d = mu[rep][i] - prior_mu;
+        if (e0 + i < t.n) local += log_sp - log_sigma + (sigma * sigma + d * d) * inv_2sp2 - 0.5f;
+        gm[i] = gs * d * inv_sp2;
+        const float sgm = isinf(ex) ? 1.f : __fdividef(ex, 1.f + ex);   // d softplus / d rho
+        gr[i] = gs * (sigma * inv_sp2 - __fdividef(1.f, sigma)) * sgm;
+      }
+      if (t.gmu && e0 < t.n) {
+        const bool vec = (e0 + 3 < t.n) && ((reinterpret_cast<uintptr_t>(t.gmu + e0) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(t.grho + e0) & 15) == 0);
+        if (vec) {
+          float4 a = *reinterpret_cast<float4*>(t.gmu + e0);
+          float4 b = *reinterpret_cast<float4*>(t.grho + e0);
+          a.x += gm[0]; a.y += gm[1]; a.z += gm[2]; a.w += gm[3];
+          b.x += gr[0]; b.y += gr[1]; b.z += gr[2]; b.w += gr[3];
+          *reinterpret_cast<float4*>(t.gmu + e0) = a;
+          *reinterpret_cast<float4*>(t.grho + e0) = b;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (e0 + i < t.n) { t.gmu[e0 + i] += gm[i]; t.grho[e0 + i] += gr[i]; }
         }
       }
     }
@@ -176,13 +250,18 @@ int mauv_mc_reduce(const void* logits, int S, long long B, int C, int dtype, flo
   MAUV_CHECK_ARG(dtype == 0, "mauv_mc_reduce: only fp32 logits (dtype 0) are supported");
   MAUV_CHECK_ARG(C <= 32, "mauv_mc_reduce: C=%d > 32 classes not supported", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned grid = static_cast<unsigned>(ceil_div_i64(B, 128));
+  const unsigned grid = static_cast<unsigned>(ceil_div_i64(B, MC_ROWS));
   const float* lg = static_cast<const float*>(logits);
+  const int vec_ok = ((B * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(lg) & 15) == 0);
+  const size_t smem = static_cast<size_t>(MC_STAGES) * MC_ROWS * C * sizeof(float);
 #define MAUV_MC(MAXC)                                                                                   \
-  mc_reduce_kernel<MAXC><<<grid, 128, 0, st>>>(lg, S, B, C, eps_entropy, mean_prob, mean_logit,         \
-                                               argmax_prob, argmax_logit, pred_entropy, aleatoric,      \
-                                               mutual_info, var_mean)
-  if (C <= 8) MAUV_MC(8); else if (C <= 16) MAUV_MC(16); else MAUV_MC(32);
+  if (smem > 48 * 1024)                                                                                 \
+    MAUV_CUDA(cudaFuncSetAttribute(mc_reduce_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   static_cast<int>(smem)));                                            \
+  mc_reduce_kernel<MAXC><<<grid, MC_ROWS, smem, st>>>(lg, S, B, C, eps_entropy, vec_ok, mean_prob, mean_logit, \
+                                                      argmax_prob, argmax_logit, pred_entropy, aleatoric,     \
+                                                      mutual_info, var_mean)
+  if (C <= 8) { MAUV_MC(8); } else if (C <= 16) { MAUV_MC(16); } else { MAUV_MC(32); }
 #undef MAUV_MC
   MAUV_LAUNCH_CHECK("mc_reduce_kernel");
   return MAUV_OK;

@@ -139,9 +139,8 @@ class MCEngine:
         track = bn.track_running_stats and bn.running_mean is not None
         ss = ops.bn_finalize(stats, count, bn.weight.detach() if bn.weight is not None else None,
                              bn.bias.detach() if bn.bias is not None else None, bn.eps, mom,
-                             bn.running_mean if track else None, bn.running_var if track else None)
-        if track and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += G
+                             bn.running_mean if track else None, bn.running_var if track else None,
+                             num_batches_tracked=bn.num_batches_tracked if track else None)
         return ss
 
     def _conv_bn(self, c: _Conv, bn, x, G, B, s0, eps, seed):
@@ -158,10 +157,11 @@ class MCEngine:
         return y, self._bn(st, count, bn, G)
 
     # ------------------------------------------------------------------ trunk
-    def _run_trunk(self, t: _Trunk, x_nchw: torch.Tensor, G: int, s0: int, eps, seed) -> torch.Tensor:
+    def _run_trunk(self, t: _Trunk, x_nchw: torch.Tensor, G: int, s0: int, eps, seed, a0=None) -> torch.Tensor:
         B = x_nchw.shape[0]
         st = t.stem
-        a0 = ops.stem_im2col_f16(x_nchw, st.k, st.k, st.stride, st.pad)          # shared by all samples
+        if a0 is None:
+            a0 = ops.stem_im2col_f16(x_nchw, st.k, st.k, st.stride, st.pad)      # shared by all samples
         w = self._sample(st, G, s0, eps, seed)
         y, stats = ops.gemm_f16(a0, w, stats=True, shared_a=True)                # [G, B*Ho*Wo, 64]
         self.launches += 2
@@ -170,7 +170,7 @@ class MCEngine:
         ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
         x = ops.bn_relu_maxpool_f16(y.view(G * B, Ho, Wo, st.cout), ss, G)
         self.launches += 1
-        del y, a0
+        del y
         for blk in t.blocks:
             y1, ss1 = self._conv_bn(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
             a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
@@ -208,22 +208,29 @@ class MCEngine:
 
     # ------------------------------------------------------------------ public
     @torch.no_grad()
+    def stem_matrices(self, inputs: Sequence[torch.Tensor]):
+        """Explicit im2col matrices of the three 7x7/2 stems: a function of the input batch only, so one build
+        serves every MC sample (and every sample group) of the batch."""
+        xs = [x.to(self.device, F32).contiguous() for x in inputs]
+        return [ops.stem_im2col_f16(x, t.stem.k, t.stem.k, t.stem.stride, t.stem.pad) for t, x in zip(self.trunks, xs)]
+
+    @torch.no_grad()
     def forward_group(self, inputs: Sequence[torch.Tensor], G: int, sample0: int = 0, eps: Optional[dict] = None,
-                      seed: Optional[int] = None) -> torch.Tensor:
+                      seed: Optional[int] = None, stems=None) -> torch.Tensor:
         """One walk of the network for MC samples [sample0, sample0+G) -> logits [G, B, C] fp32."""
         seed = current_seed() if seed is None else seed
         xs = [x.to(self.device, F32).contiguous() for x in inputs]
         B = xs[0].shape[0]
         if self.kind == "unimodal":
             t = self.trunks[0]
-            feat = self._run_trunk(t, xs[0], G, sample0, eps, seed)
+            feat = self._run_trunk(t, xs[0], G, sample0, eps, seed, None if stems is None else stems[0])
             name, fc, _ = t.fc
             return self._linear(fc, name, feat, G, sample0, eps, seed)
         m = self.model
         concat = torch.empty((G, B, 384), dtype=F32, device=self.device)
         for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn,
                                                   ("attention_image", "attention_bathy", "attention_sss"))):
-            feat = self._run_trunk(t, x, G, sample0, eps, seed)
+            feat = self._run_trunk(t, x, G, sample0, eps, seed, None if stems is None else stems[i])
             self._attention(attn, pre, feat, G, sample0, eps, seed, concat, 128 * i)
         h = self._linear(m.fc, "fc", concat, G, sample0, eps, seed)
         h = self._linear(m.fc1, "fc1", h, G, sample0, eps, seed)
@@ -235,7 +242,8 @@ class MCEngine:
         """logits [S, B, C] for MC samples sample0 .. sample0+S-1 (eps indexed from 0 when injected)."""
         G = min(group or self.max_group, S)
         outs = []
+        stems = self.stem_matrices(inputs) if S > G else None
         for s in range(0, S, G):
             g = min(G, S - s)
-            outs.append(self.forward_group(inputs, g, sample0 + s, eps, seed))
+            outs.append(self.forward_group(inputs, g, sample0 + s, eps, seed, stems))
         return torch.cat(outs, dim=0)

@@ -179,7 +179,8 @@ def stem_im2col_f16(x_nchw: torch.Tensor, kh: int, kw: int, stride: int, pad: in
 def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.Tensor],
                 beta: Optional[torch.Tensor], eps: float = 1e-5, momentum: float = 0.1,
                 running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
-                want_batch_stats: bool = False, out: Optional[torch.Tensor] = None):
+                want_batch_stats: bool = False, out: Optional[torch.Tensor] = None,
+                num_batches_tracked: Optional[torch.Tensor] = None):
     lib = _lib.require_device()
     G, m_tiles, Cc, _ = stats_partial.shape
     if out is None:
@@ -189,7 +190,7 @@ def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.T
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=stats_partial.device)
     _run("mauv_bn_finalize", lib.mauv_bn_finalize, _ptr(stats_partial, F32), G, m_tiles, Cc, count, _ptr(gamma, F32),
                                     _ptr(beta, F32), eps, momentum, _ptr(running_mean, F32),
-                                    _ptr(running_var, F32), _ptr(out), _ptr(bs), _ptr(ws), _stream())
+                                    _ptr(running_var, F32), _ptr(num_batches_tracked, I64), _ptr(out), _ptr(bs), _ptr(ws), _stream())
     return (out, bs) if want_batch_stats else out
 
 
