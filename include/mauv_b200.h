@@ -136,6 +136,34 @@ int mauv_kl_fwd_bwd(const void* table_dev, const long long* chunk_prefix_dev, in
                     long long total_chunks, float prior_mu, float prior_sigma, float grad_scale,
                     float* kl_out, void* ws, void* stream);
 
+/* ---- K6/K7: backward of the sampled layers (autograd of the reference's loss.backward(),
+ * train/multimodal.py:138, train/unimodal.py:145): dX = conv_transpose(dY, W_s); dW_s = X^T dY;
+ * dmu += dW_s; drho += dW_s * eps_s * sigmoid(rho). Both contractions run on mauv_gemm_f16 /
+ * mauv_conv2d_im2col_f16; these are the operand builders and the fused parameter-gradient epilogue. */
+/* Same sample as mauv_sample_weights_f16 (same eps) in the data-gradient layout
+ * w_out[g][ci][(kh-1-r, kw-1-s, co)]: dX = conv(dY zero-stuffed by the stride, w_out, stride 1, pad k-1-p). */
+int mauv_sample_weights_dgrad_f16(const float* mu, const float* rho, const float* eps, uint64_t seed,
+                                  uint32_t layer_id, uint32_t sample0, int G, int cout, int cin, int kh,
+                                  int kw, void* w_out, void* stream);
+/* [N][Ho][Wo][C] fp16 -> zero-stuffed [N][Hd][Wd][C] with the input at (p*stride, q*stride). */
+int mauv_dilate_f16(const void* x, long long N, int Ho, int Wo, int C, int Hd, int Wd, int stride, void* out, void* stream);
+/* [M][C] fp16 -> [splits][C][M/splits] (pixels contiguous; values multiplied by scale): wgrad GEMM operand. */
+int mauv_transpose_chunks_f16(const void* src, long long M, int C, int splits, float scale, void* dst, void* stream);
+/* NHWC fp16 -> transposed im2col [splits][k_pad][M/splits], K order (kh, kw, cin), rows >= K zero. */
+int mauv_im2col_t_f16(const void* x, long long N, int H, int W, int Cin, int kh, int kw, int stride, int pad,
+                      int k_pad, int splits, void* dst, void* stream);
+/* dw_partial: fp16 [splits][cout][k_pad] (loss-scaled by 1/inv_scale) -> grad_mu += dW, grad_rho += dW*eps*sigmoid(rho)
+ * in the PyTorch layout; eps injected [cout*cin*kh*kw] or NULL -> Philox(seed, layer_id, sample_id). */
+int mauv_wgrad_finalize(const void* dw_partial, int splits, int cout, int cin, int kh, int kw, int k_pad, float inv_scale,
+                        const float* rho, const float* eps, uint64_t seed, uint32_t layer_id, uint32_t sample_id,
+                        float* grad_mu, float* grad_rho, void* stream);
+/* Linear layer backward, fp32, sampling fused: gx (nullable) = gy * W_s; weight and bias (nullable) parameter grads += . */
+int mauv_sampled_linear_bwd_f32(const float* x, const float* gy, const float* mu_w, const float* rho_w,
+                                const float* eps_w, const float* rho_b, const float* eps_b, uint64_t seed,
+                                uint32_t layer_id, uint32_t sample_id, int B, int in_features, int out_features,
+                                float* gx, float* grad_mu_w, float* grad_rho_w, float* grad_mu_b, float* grad_rho_b,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

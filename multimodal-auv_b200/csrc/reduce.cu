@@ -78,11 +78,11 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, fl
       float z = 0.f;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
-        if (c < C) { sum_l[c] += x[c]; x[c] = expf(x[c] - mx); } else { x[c] = 0.f; }
+        if (c < C) { sum_l[c] += x[c]; x[c] = __expf(x[c] - mx); } else { x[c] = 0.f; }
         z += x[c];
       }
       const float inv_n = 1.f / static_cast<float>(s + 1);
-      const float inv_z = 1.f / z;
+      const float inv_z = __fdividef(1.f, z);
       float h = 0.f;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
@@ -92,7 +92,7 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, fl
           const float d = pc - wmean[c];
           wmean[c] += d * inv_n;
           m2[c] = fmaf(d, pc - wmean[c], m2[c]);
-          h -= pc * logf(pc + eps_entropy);
+          h -= pc * __logf(pc + eps_entropy);
         }
       }
       sum_h += h;
@@ -115,7 +115,7 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, fl
       const float ml = sum_l[c] * inv_s;
       st_p[tid * C + c] = mp;
       st_l[tid * C + c] = ml;
-      hp -= mp * logf(mp + eps_entropy);
+      hp -= mp * __logf(mp + eps_entropy);
       vsum += m2[c] * inv_sm1;
       if (mp > best_p) { best_p = mp; arg_p = c; }   // first maximum wins, as torch.argmax
       if (ml > best_l) { best_l = ml; arg_l = c; }
@@ -143,6 +143,7 @@ constexpr int KL_CHUNK = 4096;   // elements per (block, iteration): 256 threads
 
 struct KlTensor { const float* mu; const float* rho; float* gmu; float* grho; long long n; };
 
+template <bool WITH_GRAD>
 __global__ void __launch_bounds__(256)
 kl_kernel(const KlTensor* __restrict__ table, const long long* __restrict__ chunk_prefix, int n_tensors,
           long long total_chunks, float prior_mu, float prior_sigma, float grad_scale,
@@ -198,11 +199,13 @@ kl_kernel(const KlTensor* __restrict__ table, const long long* __restrict__ chun
         const float log_sigma = ex < 1e-3f ? rho[rep][i] + __logf(1.f - 0.5f * ex + 0.33333333f * ex * ex) : __logf(sigma);
         const float d = mu[rep][i] - prior_mu;
         if (e0 + i < t.n) local += log_sp - log_sigma + (sigma * sigma + d * d) * inv_2sp2 - 0.5f;
-        gm[i] = gs * d * inv_sp2;
-        const float sgm = isinf(ex) ? 1.f : __fdividef(ex, 1.f + ex);   // d softplus / d rho
-        gr[i] = gs * (sigma * inv_sp2 - __fdividef(1.f, sigma)) * sgm;
+        if (WITH_GRAD) {
+          gm[i] = gs * d * inv_sp2;
+          const float sgm = isinf(ex) ? 1.f : __fdividef(ex, 1.f + ex);   // d softplus / d rho
+          gr[i] = gs * (sigma * inv_sp2 - __fdividef(1.f, sigma)) * sgm;
+        }
       }
-      if (t.gmu && e0 < t.n) {
+      if (WITH_GRAD && t.gmu && e0 < t.n) {
         const bool vec = (e0 + 3 < t.n) && ((reinterpret_cast<uintptr_t>(t.gmu + e0) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(t.grho + e0) & 15) == 0);
         if (vec) {
@@ -279,9 +282,14 @@ int mauv_kl_fwd_bwd(const void* table_dev, const long long* chunk_prefix_dev, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = static_cast<long long>(mauv_num_sms()) * 8;
   if (blocks > total_chunks) blocks = total_chunks;
-  kl_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const KlTensor*>(table_dev), chunk_prefix_dev,
-                                                          n_tensors, total_chunks, prior_mu, prior_sigma,
-                                                          grad_scale, static_cast<double*>(ws));
+  if (grad_scale != 0.f)
+    kl_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const KlTensor*>(table_dev), chunk_prefix_dev,
+                                                                  n_tensors, total_chunks, prior_mu, prior_sigma,
+                                                                  grad_scale, static_cast<double*>(ws));
+  else
+    kl_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const KlTensor*>(table_dev), chunk_prefix_dev,
+                                                                   n_tensors, total_chunks, prior_mu, prior_sigma,
+                                                                   grad_scale, static_cast<double*>(ws));
   MAUV_LAUNCH_CHECK("kl_kernel");
   kl_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(ws), static_cast<int>(blocks), kl_out);
   MAUV_LAUNCH_CHECK("kl_final_kernel");

@@ -23,7 +23,8 @@ struct SampleParams {
   uint32_t layer_id, sample0;
   int cout, cin, kh, kw, k_pad;
   long long n;        // cout*cin*kh*kw
-  __half* w;          // [G][cout][k_pad]
+  __half* w;          // [G][cout][k_pad]   (dgrad: [G][cin][kh*kw*cout], taps flipped)
+  int dgrad;          // 1: write the transposed + spatially flipped layout the data-gradient conv consumes
 };
 
 __device__ __forceinline__ void normals4(uint64_t seed, uint32_t layer, uint32_t sample,
@@ -45,63 +46,72 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint32_t layer, uint32_t
   z[2] = rb * c; z[3] = rb * s;
 }
 
-// Each thread handles 4 consecutive elements of the PyTorch-layout parameter tensor
-// ([cout][cin][kh][kw]) for one sample: one Philox call, vector loads of mu/rho/eps.
+// Each thread handles 4 consecutive elements of the PyTorch-layout parameter tensor ([cout][cin][kh][kw]) for ALL
+// G samples of the launch: mu/rho are read once and sigma = log1p(exp(rho)) is computed once (it does not depend on
+// the sample); per sample only one Philox4x32-10 call + two Box-Muller pairs + 4 FMAs + the fp16 store remain.
 __global__ void __launch_bounds__(256)
-sample_weights_kernel(const SampleParams p) {
-  const int g = blockIdx.y;
+sample_weights_kernel(const SampleParams p, int G) {
   const long long quad = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long e0 = quad * 4;
   if (e0 >= p.n) return;
-  float mu[4], rho[4], z[4];
+  float mu[4], sg[4];
   const bool full = (e0 + 3 < p.n);
   if (full) {
     const float4 m4 = *reinterpret_cast<const float4*>(p.mu + e0);
     const float4 r4 = *reinterpret_cast<const float4*>(p.rho + e0);
     mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
-    rho[0] = r4.x; rho[1] = r4.y; rho[2] = r4.z; rho[3] = r4.w;
+    sg[0] = softplus_ref(r4.x); sg[1] = softplus_ref(r4.y); sg[2] = softplus_ref(r4.z); sg[3] = softplus_ref(r4.w);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       mu[i] = (e0 + i < p.n) ? p.mu[e0 + i] : 0.f;
-      rho[i] = (e0 + i < p.n) ? p.rho[e0 + i] : 0.f;
+      sg[i] = (e0 + i < p.n) ? softplus_ref(p.rho[e0 + i]) : 0.f;
     }
   }
-  if (p.eps) {
-    const float* ep = p.eps + static_cast<long long>(g) * p.n + e0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) z[i] = (e0 + i < p.n) ? ep[i] : 0.f;
-  } else {
-    normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(quad), z);
-  }
-  float w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) w[i] = fmaf(softplus_ref(rho[i]), z[i], mu[i]);
-
   const int khw = p.kh * p.kw;
   const long long per_out = static_cast<long long>(p.cin) * khw;
-  __half* wg = p.w + static_cast<long long>(g) * p.cout * p.k_pad;
-  if (khw == 1 && full && (p.cin % 4 == 0)) {
-    // K order == PyTorch order: 4 consecutive k of one output channel
+  const bool direct = (!p.dgrad && khw == 1 && full && (p.cin % 4 == 0));   // K order == PyTorch order
+  long long off[4];
+  if (direct) {
     const long long co = e0 / per_out;
-    const long long k = e0 - co * per_out;
-    __half2 h0 = __floats2half2_rn(w[0], w[1]);
-    __half2 h1 = __floats2half2_rn(w[2], w[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(wg + co * p.k_pad + k) = pk;
+    off[0] = co * p.k_pad + (e0 - co * per_out);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long e = e0 + i;
-      if (e < p.n) {
-        const long long co = e / per_out;
-        const int rem = static_cast<int>(e - co * per_out);
-        const int c = rem / khw;
-        const int rs = rem - c * khw;  // r*kw + s
-        wg[co * p.k_pad + static_cast<long long>(rs) * p.cin + c] = __float2half_rn(w[i]);
-      }
+      const long long co = e / per_out;
+      const int rem = static_cast<int>(e - co * per_out);
+      const int c = rem / khw;
+      const int rs = rem - c * khw;  // r*kw + s
+      off[i] = p.dgrad ? static_cast<long long>(c) * p.k_pad + static_cast<long long>(khw - 1 - rs) * p.cout + co
+                       : co * p.k_pad + static_cast<long long>(rs) * p.cin + c;
+    }
+  }
+  const long long w_stride = p.dgrad ? static_cast<long long>(p.cin) * p.k_pad : static_cast<long long>(p.cout) * p.k_pad;
+  for (int g = 0; g < G; ++g) {
+    float z[4];
+    if (p.eps) {
+      const float* ep = p.eps + static_cast<long long>(g) * p.n + e0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = (e0 + i < p.n) ? ep[i] : 0.f;
+    } else {
+      normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(quad), z);
+    }
+    float w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = fmaf(sg[i], z[i], mu[i]);
+    __half* wg = p.w + static_cast<long long>(g) * w_stride;
+    if (direct) {
+      __half2 h0 = __floats2half2_rn(w[0], w[1]);
+      __half2 h1 = __floats2half2_rn(w[2], w[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(wg + off[0]) = pk;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e0 + i < p.n) wg[off[i]] = __float2half_rn(w[i]);
     }
   }
 }
@@ -154,10 +164,30 @@ int mauv_sample_weights_f16(const float* mu, const float* rho, const float* eps,
   p.cout = cout; p.cin = cin; p.kh = kh; p.kw = kw; p.k_pad = k_pad;
   p.n = static_cast<long long>(cout) * K;
   p.w = static_cast<__half*>(w_out);
+  p.dgrad = 0;
   const long long quads = ceil_div_i64(p.n, 4);
-  dim3 grid(static_cast<unsigned>(ceil_div_i64(quads, 256)), G);
-  sample_weights_kernel<<<grid, 256, 0, st>>>(p);
+  sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, st>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel");
+  return MAUV_OK;
+}
+
+// Same sample (same eps stream / same injected eps) in the layout of the data-gradient convolution:
+// w_out[g][ci][(kh-1-r, kw-1-s, co)] = w[g][co][ci][r][s]   -> operand [G][N=cin][K=kh*kw*cout] of
+// dX = conv(dY (zero-stuffed for stride 2), w_out, stride 1, pad k-1-p).
+int mauv_sample_weights_dgrad_f16(const float* mu, const float* rho, const float* eps, uint64_t seed,
+                                  uint32_t layer_id, uint32_t sample0, int G, int cout, int cin, int kh,
+                                  int kw, void* w_out, void* stream) {
+  MAUV_CHECK_ARG(mu && rho && w_out, "mauv_sample_weights_dgrad_f16: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && cout % 8 == 0 && cin >= 1 && kh >= 1 && kw >= 1, "mauv_sample_weights_dgrad_f16: bad shape");
+  SampleParams p;
+  p.mu = mu; p.rho = rho; p.eps = eps; p.seed = seed; p.layer_id = layer_id; p.sample0 = sample0;
+  p.cout = cout; p.cin = cin; p.kh = kh; p.kw = kw; p.k_pad = kh * kw * cout;
+  p.n = static_cast<long long>(cout) * cin * kh * kw;
+  p.w = static_cast<__half*>(w_out);
+  p.dgrad = 1;
+  const long long quads = ceil_div_i64(p.n, 4);
+  sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
+  MAUV_LAUNCH_CHECK("sample_weights_kernel(dgrad)");
   return MAUV_OK;
 }
 

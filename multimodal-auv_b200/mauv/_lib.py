@@ -39,6 +39,13 @@ SIGNATURES = {
     "mauv_tanh_add_f32": (i32, [vp, vp, i64, vp, vp]),
     "mauv_softmax_gate_f32": (i32, [vp, vp, i64, i32, vp, i32, vp]),
     "mauv_mc_reduce": (i32, [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "mauv_sample_weights_dgrad_f16": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_dilate_f16": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_transpose_chunks_f16": (i32, [vp, i64, i32, i32, f32, vp, vp]),
+    "mauv_im2col_t_f16": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_wgrad_finalize": (i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, u64, u32, u32, vp, vp, vp]),
+    "mauv_sampled_linear_bwd_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, i32,
+                                          vp, vp, vp, vp, vp, vp]),
     "mauv_kl_chunk_elems": (i32, []),
     "mauv_kl_ws_bytes": (i64, []),
     "mauv_kl_fwd_bwd": (i32, [vp, vp, i32, i64, f32, f32, f32, vp, vp, vp]),

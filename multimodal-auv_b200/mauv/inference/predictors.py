@@ -84,11 +84,44 @@ class MCPredictor:
         """Host tensors in, host results out: (class [B] int64, predictive unc. [B], aleatoric [B], MI [B])."""
         dev_in = [x.to(self.device, non_blocking=True) for x in host_inputs]
         o = self.predict_device(dev_in, eps, seed)
-        packed = torch.stack([o["argmax_prob"].to(torch.float32), o["var_mean"], o["aleatoric"],
-                              o["pred_entropy"], o["mutual_info"]], dim=1)       # one [B, 5] D2H
-        host = packed.cpu()
-        return {"predicted_class": host[:, 0].to(torch.int64), "predictive_uncertainty": host[:, 1],
-                "aleatoric_uncertainty": host[:, 2], "pred_entropy": host[:, 3], "mutual_info": host[:, 4]}
+        return _unpack_results(_pack_results(o).cpu())                       # one [B, 5] D2H
+
+
+def _pack_results(o: Dict[str, torch.Tensor]) -> torch.Tensor:
+    return torch.stack([o["argmax_prob"].to(torch.float32), o["var_mean"], o["aleatoric"],
+                        o["pred_entropy"], o["mutual_info"]], dim=1)
+
+
+def _unpack_results(host: torch.Tensor) -> Dict[str, torch.Tensor]:
+    return {"predicted_class": host[:, 0].to(torch.int64), "predictive_uncertainty": host[:, 1],
+            "aleatoric_uncertainty": host[:, 2], "pred_entropy": host[:, 3], "mutual_info": host[:, 4]}
+
+
+def predict_stream(predictor: "MCPredictor", host_batches):
+    """Pipelined predict_batch over an iterable of host batches: the H2D copy of batch i+1 runs on a copy stream
+    while batch i computes (what a DataLoader loop wants). Yields one result dict (host tensors) per batch."""
+    copy_stream = torch.cuda.Stream(device=predictor.device)
+    it = iter(host_batches)
+
+    def stage(hb):
+        with torch.cuda.stream(copy_stream):
+            dev = [x.to(predictor.device, non_blocking=True) for x in hb]
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        return dev, ev
+
+    nxt = next(it, None)
+    staged = stage(nxt) if nxt is not None else None
+    while staged is not None:
+        dev, ev = staged
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None      # overlaps with the compute below
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        o = predictor.predict_device(dev)
+        for t in dev:
+            t.record_stream(cur)
+        yield _unpack_results(_pack_results(o).cpu())
 
 
 def multimodal_predict_and_save(multimodal_model: nn.Module, dataloader, device: torch.device, csv_path: str,
@@ -107,16 +140,23 @@ def multimodal_predict_and_save(multimodal_model: nn.Module, dataloader, device:
         csv_writer.writerow(header)
         logging.info(f"CSV Header written: {header}")
         logging.info(f"Length of the dataloader: {len(dataloader)}")
-        for batch_idx, (inputs, patch_30_bathy, patch_30_sss, image_name) in enumerate(dataloader):
+        names = []
+
+        def host_batches():
+            for inputs, patch_30_bathy, patch_30_sss, image_name in dataloader:
+                names.append((inputs.size(0), image_name))
+                yield (inputs, patch_30_bathy, patch_30_sss)
+
+        for batch_idx, res in enumerate(predict_stream(predictor, host_batches())):
             logging.info(f"\n--- Processing Batch {batch_idx + 1} ---")
-            res = predictor.predict_batch((inputs, patch_30_bathy, patch_30_sss))
+            n_rows, image_name = names[batch_idx]
             print(f"Predictive Uncertainty: {res['predictive_uncertainty'].numpy()}")
             print(f"Aleatoric Uncertainty: {res['aleatoric_uncertainty'].numpy()}")
             print(f"Predicted Classes: {res['predicted_class'].numpy()}")
             cls = res["predicted_class"].tolist()
             pu = res["predictive_uncertainty"].tolist()
             au = res["aleatoric_uncertainty"].tolist()
-            for i in range(inputs.size(0)):
+            for i in range(n_rows):
                 name = image_name[i] if isinstance(image_name, (list, tuple)) else image_name
                 csv_writer.writerow([name, cls[i], pu[i], au[i]])
     logging.info("Completed: multimodal_predict_and_save")

@@ -30,7 +30,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------ launch accounting / profiling
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
-KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2, "mauv_bn_finalize": 2}
+KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2, "mauv_bn_finalize": 2, "mauv_sampled_linear_bwd_f32": 2}
 launch_count = 0
 _prof = None   # list of (name, start_event, end_event) while profiling
 
@@ -281,6 +281,76 @@ def softmax_gate_f32(score: torch.Tensor, v: torch.Tensor, out: torch.Tensor, ou
     _run("mauv_softmax_gate_f32", lib.mauv_softmax_gate_f32, _ptr(score, F32), _ptr(v, F32), rows, n,
                                          out.data_ptr() + 4 * out_col, ld, _stream())
     return out
+
+
+# ------------------------------------------------------------------ backward helpers
+def sample_weights_dgrad_f16(mu, rho, G, *, eps=None, seed=0, layer_id=0, sample0=0) -> torch.Tensor:
+    """-> [G, cin, kh*kw*cout] fp16: transposed + tap-flipped sample for the data-gradient conv."""
+    lib = _lib.require_device()
+    if mu.dim() == 2:
+        cout, cin = mu.shape
+        kh = kw = 1
+    else:
+        cout, cin, kh, kw = mu.shape
+    out = torch.empty((G, cin, kh * kw * cout), dtype=F16, device=mu.device)
+    _run("mauv_sample_weights_dgrad_f16", lib.mauv_sample_weights_dgrad_f16, _ptr(mu, F32), _ptr(rho, F32),
+         _ptr(eps, F32), seed, layer_id, sample0, G, cout, cin, kh, kw, _ptr(out), _stream())
+    return out
+
+
+def dilate_f16(x: torch.Tensor, Hd: int, Wd: int, stride: int) -> torch.Tensor:
+    lib = _lib.require_device()
+    N, Ho, Wo, Cc = x.shape
+    out = torch.empty((N, Hd, Wd, Cc), dtype=F16, device=x.device)
+    _run("mauv_dilate_f16", lib.mauv_dilate_f16, _ptr(x, F16), N, Ho, Wo, Cc, Hd, Wd, stride, _ptr(out), _stream())
+    return out
+
+
+def transpose_chunks_f16(src: torch.Tensor, splits: int, scale: float = 1.0) -> torch.Tensor:
+    """src [M, C] fp16 -> [splits, C, M/splits]"""
+    lib = _lib.require_device()
+    M, Cc = src.shape
+    out = torch.empty((splits, Cc, M // splits), dtype=F16, device=src.device)
+    _run("mauv_transpose_chunks_f16", lib.mauv_transpose_chunks_f16, _ptr(src, F16), M, Cc, splits, scale, _ptr(out), _stream())
+    return out
+
+
+def im2col_t_f16(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int, splits: int) -> torch.Tensor:
+    """x [N, H, W, Cin] fp16 -> [splits, k_pad, M/splits] transposed im2col, K order (kh, kw, cin)."""
+    lib = _lib.require_device()
+    N, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    M = N * Ho * Wo
+    k_pad = round_up(kh * kw * Cin, 8)
+    out = torch.empty((splits, k_pad, M // splits), dtype=F16, device=x.device)
+    _run("mauv_im2col_t_f16", lib.mauv_im2col_t_f16, _ptr(x, F16), N, H, W, Cin, kh, kw, stride, pad, k_pad, splits,
+         _ptr(out), _stream())
+    return out
+
+
+def wgrad_finalize(dw_partial: torch.Tensor, mu_shape, inv_scale: float, rho, grad_mu, grad_rho, *, eps=None, seed=0,
+                   layer_id=0, sample_id=0) -> None:
+    lib = _lib.require_device()
+    splits, cout, k_pad = dw_partial.shape
+    if len(mu_shape) == 2:
+        cin, kh, kw = mu_shape[1], 1, 1
+    else:
+        _, cin, kh, kw = mu_shape
+    _run("mauv_wgrad_finalize", lib.mauv_wgrad_finalize, _ptr(dw_partial, F16), splits, cout, cin, kh, kw, k_pad, inv_scale,
+         _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample_id, _ptr(grad_mu, F32), _ptr(grad_rho, F32), _stream())
+
+
+def sampled_linear_bwd_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, grad_mu_b, grad_rho_b, *, eps_w=None,
+                           eps_b=None, seed=0, layer_id=0, sample_id=0, need_gx=True):
+    """x [B, in], gy [B, out] fp32 -> gx [B, in] (or None); parameter grads accumulate in place."""
+    lib = _lib.require_device()
+    B, fin = x.shape
+    fout = gy.shape[1]
+    gx = torch.empty((B, fin), dtype=F32, device=x.device) if need_gx else None
+    _run("mauv_sampled_linear_bwd_f32", lib.mauv_sampled_linear_bwd_f32, _ptr(x, F32), _ptr(gy, F32), _ptr(mu_w, F32),
+         _ptr(rho_w, F32), _ptr(eps_w, F32), _ptr(rho_b, F32), _ptr(eps_b, F32), seed, layer_id, sample_id, B, fin, fout,
+         _ptr(gx), _ptr(grad_mu_w, F32), _ptr(grad_rho_w, F32), _ptr(grad_mu_b, F32), _ptr(grad_rho_b, F32), _stream())
+    return gx
 
 
 # ------------------------------------------------------------------ statistics

@@ -236,3 +236,124 @@ def test_full_size_properties_cfg2_shape(bu):
     perm = torch.randperm(256, generator=g).cuda()
     o2 = pred.predict_device([x[perm] for x in xs], seed=7)
     assert (o2["logits"] - o["logits"][:, perm]).abs().max().item() < 2e-2 * o["logits"].abs().max().item() + 1e-3
+
+
+# ------------------------------------------------------------------ training path (layer-level drop-in modules)
+@pytest.mark.parametrize("cfg", [
+    (64, 64, 1, 1, 0, 2, 16, 16), (64, 128, 3, 1, 1, 2, 16, 16), (128, 128, 3, 2, 1, 2, 16, 16),
+    (256, 512, 1, 2, 0, 2, 8, 8), (3, 64, 7, 2, 3, 2, 32, 32), (1, 64, 7, 2, 3, 2, 32, 32),
+])
+def test_sampled_conv_forward_backward_vs_oracle_autograd(bu, cfg):
+    """Conv2dReparameterization (drop-in module): forward, dX, dmu, drho against the oracle layer's autograd with the
+    same injected eps. Tolerance 5e-3 of the tensor max (fp16 operands in both contractions)."""
+    import bnn_oracle as O
+    from mauv.bayesian import Conv2dReparameterization
+    cin, cout, k, stride, pad, N, H, W = cfg
+    torch.manual_seed(11)
+    o = O.Conv2dReparameterization(cin, cout, k, stride=stride, padding=pad, bias=False)
+    o.dnn_to_bnn_flag = True
+    with torch.no_grad():
+        o.mu_kernel.normal_(0, 0.05)
+        o.rho_kernel.copy_(O.get_rho(o.mu_kernel, 0.5))
+    g = Conv2dReparameterization(cin, cout, k, stride=stride, padding=pad, bias=False)
+    g.dnn_to_bnn_flag = True
+    g.load_state_dict(o.state_dict())
+    g.cuda()
+    eps = torch.randn_like(o.mu_kernel)
+    x = torch.randn(N, cin, H, W)
+    need_gx = cin % 8 == 0
+    xo = x.clone().requires_grad_(need_gx)
+    o.injected_eps_kernel = eps
+    yo = o(xo)
+    gy = torch.randn_like(yo)
+    yo.backward(gy)
+    xg = x.cuda().requires_grad_(need_gx)
+    g.eps_override = (eps.cuda(), None)
+    yg = g(xg)
+    yg.backward(gy.cuda())
+    bu.FAILS.clear()
+    bu.report("conv fwd", yg, yo, 3e-3)
+    bu.report("conv grad_mu", g.mu_kernel.grad, o.mu_kernel.grad, 5e-3)
+    bu.report("conv grad_rho", g.rho_kernel.grad, o.rho_kernel.grad, 5e-3)
+    if need_gx:
+        bu.report("conv grad_x", xg.grad, xo.grad, 5e-3)
+    assert not bu.FAILS, bu.FAILS
+
+
+@pytest.mark.parametrize("cfg", [(2048, 128, 8), (384, 1284, 5), (32, 7, 3)])
+def test_sampled_linear_forward_backward_vs_oracle_autograd(bu, cfg):
+    import bnn_oracle as O
+    from mauv.bayesian import LinearReparameterization
+    fin, fout, B = cfg
+    torch.manual_seed(12)
+    o = O.LinearReparameterization(fin, fout)
+    o.dnn_to_bnn_flag = True
+    with torch.no_grad():
+        o.mu_weight.normal_(0, 0.05)
+        o.rho_weight.copy_(O.get_rho(o.mu_weight, 0.5))
+        o.mu_bias.normal_(0, 0.05)
+        o.rho_bias.copy_(O.get_rho(o.mu_bias, 0.5))
+    g = LinearReparameterization(fin, fout)
+    g.dnn_to_bnn_flag = True
+    g.load_state_dict(o.state_dict())
+    g.cuda()
+    ew, eb = torch.randn_like(o.mu_weight), torch.randn_like(o.mu_bias)
+    x = torch.randn(B, fin)
+    xo = x.clone().requires_grad_()
+    o.injected_eps_weight, o.injected_eps_bias = ew, eb
+    yo = o(xo)
+    gy = torch.randn_like(yo)
+    yo.backward(gy)
+    xg = x.cuda().requires_grad_()
+    g.eps_override = (ew.cuda(), eb.cuda())
+    yg = g(xg)
+    yg.backward(gy.cuda())
+    bu.FAILS.clear()
+    bu.report("linear fwd", yg, yo, 1e-5)
+    bu.report("linear grad_x", xg.grad, xo.grad, 1e-5)
+    for n in ("mu_weight", "rho_weight", "mu_bias", "rho_bias"):
+        bu.report(f"linear grad_{n}", getattr(g, n).grad, getattr(o, n).grad, 1e-5)
+    assert not bu.FAILS, bu.FAILS
+
+
+def test_train_step_drop_in_vs_oracle(bu):
+    """One ELBO step through the product train driver's math (S passes of the drop-in model, CE(mean logits) +
+    KL/B*2^(e+1)/2^E, backward) against the oracle's autograd, identical injected eps: loss terms agree and the
+    gradients point the same way (cosine > 0.98; the network amplifies fp16 operand rounding)."""
+    import bnn_oracle as O
+    from mauv.bayesian import bayesian_layers, get_kl_loss
+    o_model, model = bu.build_pair("multimodal")
+    B, S = 2, 2
+    img, bathy, sss, labels = O.synthetic_batch(B, size=64)
+    eps = O.draw_eps(o_model, S, seed=5)
+    o_model.train()
+    outs = []
+    for s in range(S):
+        O.inject_eps(o_model, eps, s)
+        outs.append(o_model(img, bathy, sss))
+    O.inject_eps(o_model, None, 0)
+    loss_o, ce_o, skl_o = O.elbo_loss_multimodal(torch.stack(outs), labels, O.get_kl_loss(o_model), B, 1, 20)
+    loss_o.backward()
+    layers = dict(bayesian_layers(model))
+    xs = [t.cuda() for t in (img, bathy, sss)]
+    outs = []
+    for s in range(S):
+        for name, l in layers.items():
+            e = eps[name]
+            l.eps_override = (e["w"][s].cuda(), None if e["b"] is None else e["b"][s].cuda())
+        outs.append(model(*xs))
+    out = torch.mean(torch.stack(outs), dim=0)
+    kl = get_kl_loss(model)
+    ce = torch.nn.functional.cross_entropy(out, labels.cuda())
+    loss = ce + kl / B * O.kl_weight(1, 20)
+    loss.backward()
+    assert abs(kl.item() - O.get_kl_loss(o_model).item()) < 1e-4 * kl.item()
+    assert abs(ce.item() - ce_o.item()) < 5e-3
+    od = dict(o_model.named_parameters())
+    for name in ("fc2.mu_weight", "fc2.rho_weight", "fc.mu_weight", "attention_image.key_projection.mu_weight",
+                 "image_model_feat.layer4.2.conv3.mu_kernel", "image_model_feat.layer4.2.conv3.rho_kernel",
+                 "sss_model_feat.conv1.mu_kernel", "bathy_model_feat.layer1.0.conv2.mu_kernel"):
+        gg = dict(model.named_parameters())[name].grad.detach().cpu().flatten().double()
+        go = od[name].grad.flatten().double()
+        cos = torch.dot(gg, go) / (gg.norm() * go.norm() + 1e-300)
+        assert cos > 0.98, (name, cos.item(), gg.norm().item(), go.norm().item())
