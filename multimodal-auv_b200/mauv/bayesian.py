@@ -33,6 +33,24 @@ def current_seed() -> int:
     return _global_seed
 
 
+# bayesian-torch draws eps in place into a buffer (`eps = self.eps_kernel.data.normal_()`), and the reference runs S
+# forward passes BEFORE one backward (train/multimodal.py:107-138). Autograd saved a view of that buffer for the
+# sigma*eps product, so by the time backward runs every pass's saved eps has been overwritten by the LAST pass's
+# draw: the reference's grad_rho is sum_s dW_s * eps_S * sigmoid(rho), not sum_s dW_s * eps_s * sigmoid(rho).
+# Default here is the mathematically intended gradient (each pass its own eps); set_reference_stale_eps(True)
+# reproduces the reference bit for bit in structure (used by the parity tests against the oracle).
+_stale_eps = False
+
+
+def set_reference_stale_eps(flag: bool) -> None:
+    global _stale_eps
+    _stale_eps = bool(flag)
+
+
+def reference_stale_eps() -> bool:
+    return _stale_eps
+
+
 def get_rho(sigma: torch.Tensor, delta: float) -> torch.Tensor:
     """MOPED: rho with softplus(rho) ~= delta*|w| (bayesian_torch/utils/util.py)."""
     return torch.log(torch.expm1(delta * torch.abs(sigma)) + 1e-20)

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
-from .bayesian import current_seed
+from .bayesian import current_seed, reference_stale_eps
 
 F16, F32 = torch.float16, torch.float32
 
@@ -76,6 +76,7 @@ class _SampledConv2d(torch.autograd.Function):
         layer._calls += 1
         ew, _ = _layer_eps(layer)
         ctx.layer, ctx.sid, ctx.eps_w = layer, sid, ew
+        layer._last_draw = (sid, ew, None)
         ctx.save_for_backward(x)
         return conv2d_forward(layer, x, sid, ew)
 
@@ -83,7 +84,14 @@ class _SampledConv2d(torch.autograd.Function):
     def backward(ctx, gy):
         from .backward import conv2d_backward
         (x,) = ctx.saved_tensors
-        gx, gmu, grho = conv2d_backward(ctx.layer, x, gy, ctx.sid, ctx.eps_w, ctx.needs_input_grad[0])
+        sid, ew = ctx.sid, ctx.eps_w
+        if reference_stale_eps():            # the reference's saved eps buffer holds the LAST pass's draw
+            # dX and dW must still use this pass's weights; only the eps factor of d(rho) is stale
+            gx, gmu, _ = conv2d_backward(ctx.layer, x, gy, sid, ew, ctx.needs_input_grad[0])
+            lsid, lew, _ = ctx.layer._last_draw
+            grho = rho_grad_from_dw(ctx.layer, gmu, lsid, lew)
+            return gx, gmu, grho, None
+        gx, gmu, grho = conv2d_backward(ctx.layer, x, gy, sid, ew, ctx.needs_input_grad[0])
         return gx, gmu, grho, None
 
 
@@ -94,6 +102,7 @@ class _SampledLinear(torch.autograd.Function):
         layer._calls += 1
         ew, eb = _layer_eps(layer)
         ctx.layer, ctx.sid, ctx.eps = layer, sid, (ew, eb)
+        layer._last_draw = (sid, ew, eb)
         ctx.save_for_backward(x)
         return linear_forward(layer, x, sid, ew, eb)
 
@@ -102,7 +111,24 @@ class _SampledLinear(torch.autograd.Function):
         from .backward import linear_backward
         (x,) = ctx.saved_tensors
         gx, gmw, grw, gmb, grb = linear_backward(ctx.layer, x, gy, ctx.sid, ctx.eps, ctx.needs_input_grad[0])
+        if reference_stale_eps():
+            lsid, lew, leb = ctx.layer._last_draw
+            grw = rho_grad_from_dw(ctx.layer, gmw, lsid, lew)
+            if gmb is not None:
+                grb = rho_grad_from_dw(ctx.layer, gmb, lsid, leb, bias=True)
         return gx, gmw, grw, gmb, grb, None
+
+
+def rho_grad_from_dw(layer, dw: torch.Tensor, sample_id: int, eps, bias: bool = False) -> torch.Tensor:
+    """d(rho) = dW * eps * sigmoid(rho) for a given eps draw (compat path only; the normal path fuses this)."""
+    from .bayesian import current_seed as _seed
+    if bias:
+        rho, lid = layer.rho_bias.detach(), layer.layer_uid | 0x80000000
+    else:
+        rho, lid = layer._weight_params()[1].detach(), layer.layer_uid
+    if eps is None:
+        eps = ops.philox_normal(dw.numel(), seed=_seed(), layer_id=lid, sample_id=sample_id, device=dw.device)
+    return dw * eps.reshape(dw.shape) * torch.sigmoid(rho)
 
 
 def sampled_conv2d(layer, x: torch.Tensor) -> torch.Tensor:

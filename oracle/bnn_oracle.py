@@ -50,14 +50,23 @@ def kl_div(mu_q, sigma_q, mu_p, sigma_p) -> torch.Tensor:
     return kl.mean()
 
 
+# bayesian-torch draws eps IN PLACE into a module buffer and multiplies by that buffer's `.data`
+# (`eps_kernel = self.eps_kernel.data.normal_()`), so autograd saves a view of the buffer for d(sigma*eps)/d(sigma).
+# When several forward passes precede one backward - exactly the reference's S-pass loops (train/multimodal.py:107-138,
+# train/unimodal.py:127-145) - every pass's saved eps is overwritten by the LAST draw: grad_rho = sum_s dW_s*eps_S*sig'.
+# True (default) restates that behaviour faithfully; False clones eps per pass (the mathematically intended gradient).
+STALE_EPS_QUIRK = True
+
+
 class _ReparamBase(nn.Module):
     dnn_to_bnn_flag = False
 
     def _draw(self, buf: torch.Tensor, injected: Optional[torch.Tensor]) -> torch.Tensor:
         if injected is not None:
             buf.data.copy_(injected.to(buf.dtype))
-            return buf.data
-        return buf.data.normal_()
+        else:
+            buf.data.normal_()
+        return buf.data if STALE_EPS_QUIRK else buf.data.clone()
 
 
 class Conv2dReparameterization(_ReparamBase):

@@ -343,6 +343,58 @@ def t_engine(B=2, S=2, size=64, kind="multimodal"):
     return got, ref
 
 
+def t_train(S=2, B=2, size=64):
+    """Diagnostics: per-parameter gradient agreement of one ELBO step (drop-in layers vs oracle autograd)."""
+    import bnn_oracle as O
+    from mauv.bayesian import bayesian_layers, get_kl_loss
+    o_model, model = build_pair("multimodal")
+    img, bathy, sss, labels = O.synthetic_batch(B, size=size)
+    eps = O.draw_eps(o_model, S, seed=5)
+    o_model.train()
+    outs = []
+    for s in range(S):
+        O.inject_eps(o_model, eps, s)
+        outs.append(o_model(img, bathy, sss))
+    O.inject_eps(o_model, None, 0)
+    loss_o, ce_o, skl_o = O.elbo_loss_multimodal(torch.stack(outs), labels, O.get_kl_loss(o_model), B, 1, 20)
+    loss_o.backward()
+    layers = dict(bayesian_layers(model))
+    xs = [t.to(dev) for t in (img, bathy, sss)]
+    outs_g = []
+    for s in range(S):
+        for name, l in layers.items():
+            e = eps[name]
+            l.eps_override = (e["w"][s].to(dev), None if e["b"] is None else e["b"][s].to(dev))
+        outs_g.append(model(*xs))
+    out = torch.mean(torch.stack(outs_g), dim=0)
+    kl = get_kl_loss(model)
+    ce = torch.nn.functional.cross_entropy(out, labels.to(dev))
+    loss = ce + kl / B * O.kl_weight(1, 20)
+    loss.backward()
+    print(f"S={S}: ce {ce.item():.6f} vs {ce_o.item():.6f}; kl {kl.item():.4f} vs {O.get_kl_loss(o_model).item():.4f}")
+    report("   per-pass logits", torch.stack(outs_g), torch.stack(outs), None)
+    od = dict(o_model.named_parameters())
+    gd = dict(model.named_parameters())
+    worst = []
+    for name, po in od.items():
+        if po.grad is None or gd[name].grad is None:
+            print("   missing grad:", name, po.grad is None, gd[name].grad is None)
+            continue
+        gg = gd[name].grad.detach().cpu().flatten().double()
+        go = po.grad.flatten().double()
+        cos = (torch.dot(gg, go) / (gg.norm() * go.norm() + 1e-300)).item()
+        worst.append((cos, name, gg.norm().item(), go.norm().item()))
+    worst.sort()
+    print("   lowest cosine similarities:")
+    for w in worst[:25]:
+        print("    cos=%.4f %-60s |g|=%.3e |g_ref|=%.3e" % w)
+    import statistics
+    print("   median cos", statistics.median(w[0] for w in worst), " n>0.98:", sum(w[0] > 0.98 for w in worst), "of", len(worst))
+    for name in ("fc2.mu_weight", "fc2.rho_weight", "fc2.mu_bias", "fc2.rho_bias", "fc1.rho_weight", "fc.rho_weight"):
+        w = [x for x in worst if x[1] == name][0]
+        print("    %s cos=%.4f" % (name, w[0]))
+
+
 GROUPS = {
     "simple": lambda: [run_case(f) for f in (t_philox, t_sample, t_stem, t_bn, t_pool, t_linear, t_mc, t_kl)],
     "gemm": lambda: [run_case(t_gemm, *a) for a in [
@@ -353,6 +405,7 @@ GROUPS = {
         (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
         (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),
         (1, 2, 4, 4, 512, 512, 3, 1, 1), (3, 1, 6, 6, 128, 64, 3, 2, 1)]],
+    "train": lambda: [run_case(t_train, 1), run_case(t_train, 2)],
     "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal"),
                        run_case(t_engine, 2, 2, 256, "unimodal")],
 }

@@ -316,12 +316,80 @@ def test_sampled_linear_forward_backward_vs_oracle_autograd(bu, cfg):
     assert not bu.FAILS, bu.FAILS
 
 
-def test_train_step_drop_in_vs_oracle(bu):
-    """One ELBO step through the product train driver's math (S passes of the drop-in model, CE(mean logits) +
-    KL/B*2^(e+1)/2^E, backward) against the oracle's autograd, identical injected eps: loss terms agree and the
-    gradients point the same way (cosine > 0.98; the network amplifies fp16 operand rounding)."""
+class _SmallNet(torch.nn.Module):
+    """conv3x3 -> BN -> ReLU -> conv3x3/2 -> BN -> ReLU -> conv1x1 -> BN -> avgpool -> linear (well conditioned)."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.c1 = nn.Conv2d(64, 64, 3, 1, 1, bias=False); self.b1 = nn.BatchNorm2d(64)
+        self.c2 = nn.Conv2d(64, 128, 3, 2, 1, bias=False); self.b2 = nn.BatchNorm2d(128)
+        self.c3 = nn.Conv2d(128, 64, 1, 1, 0, bias=False); self.b3 = nn.BatchNorm2d(64)
+        self.fc = nn.Linear(64, 7)
+
+    def forward(self, x):
+        x = torch.relu(self.b1(self.c1(x)))
+        x = torch.relu(self.b2(self.c2(x)))
+        x = self.b3(self.c3(x))
+        return self.fc(x.mean((2, 3)))
+
+
+@pytest.mark.parametrize("stale", [True, False])
+def test_elbo_step_small_network_all_gradients(bu, stale):
+    """S forward passes then ONE backward through drop-in layers + torch BN/ReLU, against the oracle's autograd with
+    identical injected eps: every gradient (mu, rho, BN, input path) within 2e-2 of its max. stale=True reproduces the
+    reference's saved-eps-buffer behaviour (grad_rho uses the last pass's eps), stale=False the intended gradient."""
     import bnn_oracle as O
-    from mauv.bayesian import bayesian_layers, get_kl_loss
+    import mauv.bayesian as MB
+    torch.manual_seed(21)
+    o_net = _SmallNet()
+    g_net = _SmallNet()
+    g_net.load_state_dict(o_net.state_dict())
+    O.dnn_to_bnn(o_net, O.DEFAULT_PRIOR)
+    MB.dnn_to_bnn(g_net, O.DEFAULT_PRIOR)
+    g_net.cuda().train()
+    o_net.train()
+    S, B = 3, 8
+    x = torch.randn(B, 64, 32, 32)
+    labels = torch.randint(0, 7, (B,))
+    eps = O.draw_eps(o_net, S, seed=3)
+    O.STALE_EPS_QUIRK = stale
+    MB.set_reference_stale_eps(stale)
+    try:
+        outs = []
+        for s in range(S):
+            O.inject_eps(o_net, eps, s)
+            outs.append(o_net(x))
+        O.inject_eps(o_net, None, 0)
+        loss_o, ce_o, _ = O.elbo_loss_multimodal(torch.stack(outs), labels, O.get_kl_loss(o_net), B, 10, 20)
+        loss_o.backward()
+        layers = dict(MB.bayesian_layers(g_net))
+        outs_g = []
+        for s in range(S):
+            for name, l in layers.items():
+                e = eps[name]
+                l.eps_override = (e["w"][s].cuda(), None if e["b"] is None else e["b"][s].cuda())
+            outs_g.append(g_net(x.cuda()))
+        out = torch.mean(torch.stack(outs_g), dim=0)
+        loss = torch.nn.functional.cross_entropy(out, labels.cuda()) + MB.get_kl_loss(g_net) / B * O.kl_weight(10, 20)
+        loss.backward()
+    finally:
+        O.STALE_EPS_QUIRK = True
+        MB.set_reference_stale_eps(False)
+    assert abs(loss.item() - loss_o.item()) < 2e-3 * abs(loss_o.item())
+    bu.FAILS.clear()
+    od = dict(o_net.named_parameters())
+    for name, p in g_net.named_parameters():
+        bu.report(f"grad {name} (stale={stale})", p.grad, od[name].grad, 2e-2)
+    assert not bu.FAILS, bu.FAILS
+
+
+def test_train_step_full_multimodal_head_gradients(bu):
+    """Full 174-layer multimodal net, one ELBO step (S=2, reference stale-eps semantics): loss terms and the head's
+    gradients against the oracle; trunk gradients only need to be finite here because at B=2 / 64x64 the batch-stat
+    BatchNorm stack amplifies fp16 operand rounding - trunk layers are covered layer by layer above."""
+    import bnn_oracle as O
+    import mauv.bayesian as MB
     o_model, model = bu.build_pair("multimodal")
     B, S = 2, 2
     img, bathy, sss, labels = O.synthetic_batch(B, size=64)
@@ -334,26 +402,32 @@ def test_train_step_drop_in_vs_oracle(bu):
     O.inject_eps(o_model, None, 0)
     loss_o, ce_o, skl_o = O.elbo_loss_multimodal(torch.stack(outs), labels, O.get_kl_loss(o_model), B, 1, 20)
     loss_o.backward()
-    layers = dict(bayesian_layers(model))
+    layers = dict(MB.bayesian_layers(model))
     xs = [t.cuda() for t in (img, bathy, sss)]
-    outs = []
-    for s in range(S):
-        for name, l in layers.items():
-            e = eps[name]
-            l.eps_override = (e["w"][s].cuda(), None if e["b"] is None else e["b"][s].cuda())
-        outs.append(model(*xs))
-    out = torch.mean(torch.stack(outs), dim=0)
-    kl = get_kl_loss(model)
-    ce = torch.nn.functional.cross_entropy(out, labels.cuda())
-    loss = ce + kl / B * O.kl_weight(1, 20)
-    loss.backward()
+    MB.set_reference_stale_eps(True)
+    try:
+        outs = []
+        for s in range(S):
+            for name, l in layers.items():
+                e = eps[name]
+                l.eps_override = (e["w"][s].cuda(), None if e["b"] is None else e["b"][s].cuda())
+            outs.append(model(*xs))
+        out = torch.mean(torch.stack(outs), dim=0)
+        kl = MB.get_kl_loss(model)
+        ce = torch.nn.functional.cross_entropy(out, labels.cuda())
+        loss = ce + kl / B * O.kl_weight(1, 20)
+        loss.backward()
+    finally:
+        MB.set_reference_stale_eps(False)
     assert abs(kl.item() - O.get_kl_loss(o_model).item()) < 1e-4 * kl.item()
     assert abs(ce.item() - ce_o.item()) < 5e-3
     od = dict(o_model.named_parameters())
-    for name in ("fc2.mu_weight", "fc2.rho_weight", "fc.mu_weight", "attention_image.key_projection.mu_weight",
-                 "image_model_feat.layer4.2.conv3.mu_kernel", "image_model_feat.layer4.2.conv3.rho_kernel",
-                 "sss_model_feat.conv1.mu_kernel", "bathy_model_feat.layer1.0.conv2.mu_kernel"):
-        gg = dict(model.named_parameters())[name].grad.detach().cpu().flatten().double()
+    gd = dict(model.named_parameters())
+    for name in ("fc2.mu_weight", "fc2.rho_weight", "fc2.mu_bias", "fc2.rho_bias", "fc1.mu_weight", "fc1.rho_weight",
+                 "fc.mu_weight", "fc.rho_weight"):
+        gg = gd[name].grad.detach().cpu().flatten().double()
         go = od[name].grad.flatten().double()
         cos = torch.dot(gg, go) / (gg.norm() * go.norm() + 1e-300)
-        assert cos > 0.98, (name, cos.item(), gg.norm().item(), go.norm().item())
+        assert cos > 0.98, (name, cos.item())
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    assert all(p.grad is not None for n, p in model.named_parameters())
