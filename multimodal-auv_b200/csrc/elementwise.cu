@@ -234,43 +234,51 @@ bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const 
 }
 
 // Stem tail: BN + ReLU + 3x3/2 max-pool (pad 1) in one pass.
-// y: [G*B][H][W][C] fp16 raw conv output -> out: [G*B][Ho][Wo][C].
-__global__ void __launch_bounds__(256)
+// y: [G*B][H][W][C] fp16 raw conv output -> out: [G*B][Ho][Wo][C]. One block per (image, output row): no integer
+// division in the hot loop, the three input rows are read with 9 independent 16-byte loads per thread.
+__global__ void __launch_bounds__(512)
 bn_relu_maxpool_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, int imgs_per_sample,
-                       int H, int W, int C, int Ho, int Wo, long long total_vec, uint4* __restrict__ out) {
-  const int cvec = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % cvec);
-    long long t = i / cvec;
-    const int q = static_cast<int>(t % Wo); t /= Wo;
-    const int p = static_cast<int>(t % Ho); t /= Ho;
-    const long long n = t;  // image index in [0, G*B)
-    const int g = static_cast<int>(n / imgs_per_sample);
+                       int H, int W, int C, int Ho, int Wo, uint4* __restrict__ out) {
+  const int cvec = C >> 3;
+  const int p = blockIdx.x;                  // output row
+  const long long n = blockIdx.y;            // image index in [0, G*B)
+  const int g = static_cast<int>(n / imgs_per_sample);
+  const int per_row = Wo * cvec;
+  for (int t = threadIdx.x; t < per_row; t += blockDim.x) {
+    const int cv = t % cvec;
+    const int q = t / cvec;
     float sc[8], sh[8], m[8];
-    const float2* s = ss + static_cast<long long>(g) * C + cv * 8;
+    const float4* s4 = reinterpret_cast<const float4*>(ss + static_cast<long long>(g) * C + cv * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 tt = __ldg(s + j);
-      sc[j] = tt.x; sh[j] = tt.y; m[j] = -INFINITY;
+    for (int j = 0; j < 4; ++j) {
+      const float4 tt = __ldg(s4 + j);
+      sc[2 * j] = tt.x; sh[2 * j] = tt.y; sc[2 * j + 1] = tt.z; sh[2 * j + 1] = tt.w;
     }
 #pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
     for (int dr = 0; dr < 3; ++dr) {
-      const int h = p * 2 - 1 + dr;
-      if (h < 0 || h >= H) continue;
 #pragma unroll
       for (int ds = 0; ds < 3; ++ds) {
-        const int w = q * 2 - 1 + ds;
-        if (w < 0 || w >= W) continue;
+        const int h = p * 2 - 1 + dr, w = q * 2 - 1 + ds;
+        ok[dr * 3 + ds] = (h >= 0 && h < H && w >= 0 && w < W);
+        if (ok[dr * 3 + ds]) v[dr * 3 + ds] = __ldg(y + ((n * H + h) * W + w) * cvec + cv);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (ok[k]) {
         float f[8];
-        unpack8(__ldg(y + ((n * H + h) * W + w) * cvec + cv), f);
+        unpack8(v[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(f[j], sc[j], sh[j]));
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], 0.f);  // relu(max) == max(relu)
-    out[i] = pack8(m);
+    out[((n * Ho + p) * Wo + q) * cvec + cv] = pack8(m);
   }
 }
 
@@ -398,10 +406,14 @@ int mauv_bn_relu_maxpool_f16(const void* y, const float* scale_shift, int G, int
                              int W, int C, void* out, void* stream) {
   MAUV_CHECK_ARG(y && scale_shift && out && C % 8 == 0, "mauv_bn_relu_maxpool_f16: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(G) * imgs_per_sample * Ho * Wo * (C / 8);
-  bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const long long imgs = static_cast<long long>(G) * imgs_per_sample;
+  MAUV_CHECK_ARG(imgs <= 65535, "mauv_bn_relu_maxpool_f16: at most 65535 images per call (got %lld)", imgs);
+  int threads = Wo * (C / 8);
+  threads = threads > 512 ? 512 : ((threads + 31) / 32) * 32;
+  dim3 grid(Ho, static_cast<unsigned>(imgs));
+  bn_relu_maxpool_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift), imgs_per_sample, H, W, C,
-      Ho, Wo, total, static_cast<uint4*>(out));
+      Ho, Wo, static_cast<uint4*>(out));
   MAUV_LAUNCH_CHECK("bn_relu_maxpool_kernel");
   return MAUV_OK;
 }

@@ -38,6 +38,9 @@ struct GemmParams {
   long long total_tiles;
   int a_mode;       // 0 = tiled [K, M, G] ; 1 = im2col (C, W, H, N)
   int a_batch_mul;  // 0 when A is shared by all samples (stem), else 1
+  int stack;        // > 1: the tile's BN columns hold `stack` consecutive samples of N channels each (shared A only):
+                    //      one A tile feeds `stack` samples, B rows are the flattened [G*N][K] weights
+  int g_blocks;     // ceil(G / stack)
   // im2col geometry
   int Wo, Ho, imgs_per_sample, stride, pad, kw, c_blocks;
   // outputs
@@ -118,7 +121,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // tile -> (g, m_tile, n_tile). n-tile fastest so concurrent CTAs share their A tile through L2; when A is shared
   // by all samples (stem) the sample index is the fastest instead, so the G samples of one m-tile run together.
   auto decode = [&](long long tile, int& g, int& m_tile, int& n_tile) {
-    if (p.a_batch_mul == 0) {
+    if (p.stack > 1) {              // g = first sample of the tile's sample block; a single n-tile
+      g = static_cast<int>(tile % p.g_blocks) * p.stack;
+      m_tile = static_cast<int>(tile / p.g_blocks);
+      n_tile = 0;
+    } else if (p.a_batch_mul == 0) {
       g = static_cast<int>(tile % p.G);
       const long long rem = tile / p.G;
       n_tile = static_cast<int>(rem % p.n_tiles);
@@ -166,7 +173,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                ip * p.stride - p.pad, in_, static_cast<uint16_t>(s),
                                static_cast<uint16_t>(r));
           }
-          tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, g);
+          if (p.stack > 1) tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, g * p.N, 0);   // flattened [G*N][K]
+          else tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, g);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -236,7 +244,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
       for (int cb = cset; cb < BN / 64; cb += kColSets) {
         const int col0 = cb * 64;
-        const bool cols_ok = (n0 + col0) < p.N;     // warp uniform
+        // stacked mode: this 64-column block belongs to sample gb at channel offset nb
+        const int gb = (p.stack > 1) ? g + col0 / p.N : g;
+        const int nb = (p.stack > 1) ? col0 % p.N : n0 + col0;
+        const bool cols_ok = (p.stack > 1) ? (gb < p.G) : (nb < p.N);     // warp uniform
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr + col0, ra);
         tmem_ld_32x32b_x32(taddr + col0 + 32, rb);
@@ -282,7 +293,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0 && rmax > 0) {
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmY)),
-                       "r"(buf), "r"(n0 + col0), "r"(row0), "r"(g)
+                       "r"(buf), "r"(nb), "r"(row0), "r"(gb)
                        : "memory");
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -325,7 +336,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // combine the 4 epilogue warps and emit one deterministic partial per (tile, channel)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int j = et; j < BN; j += kEpiThreads) {
-          if (n0 + j < p.N) {
+          const int gj = (p.stack > 1) ? g + j / p.N : g;
+          const int nj = (p.stack > 1) ? j % p.N : n0 + j;
+          if (nj < p.N && gj < p.G) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -333,7 +346,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               b += stat_buf[(w * BN + j) * 2 + 1];
             }
             float2* dst = reinterpret_cast<float2*>(p.stats) +
-                          (static_cast<long long>(g) * p.m_tiles + m_tile) * p.N + n0 + j;
+                          (static_cast<long long>(gj) * p.m_tiles + m_tile) * p.N + nj;
             *dst = make_float2(a, b);
           }
         }
@@ -451,13 +464,18 @@ int pick_bn(int N) {
 }
 
 int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  const int bn = pick_bn(p.N);
+  const int bn = p.stack > 1 ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
   if (int rc = make_tiled_map(&tmY, p.y, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
   p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
   p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
   p.total_tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.G;
+  if (p.stack > 1) {
+    p.n_tiles = 1;
+    p.g_blocks = static_cast<int>(ceil_div_i64(p.G, p.stack));
+    p.total_tiles = static_cast<long long>(p.m_tiles) * p.g_blocks;
+  }
   if (p.total_tiles == 0) return MAUV_OK;
   switch (bn) {
     case 64: return launch_gemm<64>(tmA, tmB, tmY, p, stream);
@@ -485,8 +503,15 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
   CUtensorMap tmA, tmB;
   const bool shared_a = (a_sample_stride == 0);
   if (int rc = make_tiled_map(&tmA, a, K, M, shared_a ? 1 : G, shared_a ? M * K : a_sample_stride, BM)) return rc;
-  if (int rc = make_tiled_map(&tmB, w, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  // shared A (stem) with narrow N: stack 256/N samples along the tile's N dimension so one A tile feeds them all
+  const int stack = (shared_a && G > 1 && !bias && N <= 128 && 256 % N == 0) ? 256 / N : 1;
+  if (stack > 1) {
+    if (int rc = make_tiled_map(&tmB, w, K, static_cast<int64_t>(G) * N, 1, static_cast<int64_t>(G) * N * K, 256)) return rc;
+  } else {
+    if (int rc = make_tiled_map(&tmB, w, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  }
   GemmParams p{};
+  p.stack = stack;
   p.M = static_cast<int>(M);
   p.N = N;
   p.k_blocks = static_cast<int>(ceil_div_i64(K, BK));
@@ -515,6 +540,7 @@ int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_p
   const int K = kh * kw * Cin;
   if (int rc = make_tiled_map(&tmB, w, K, Cout, G, static_cast<int64_t>(Cout) * K, pick_bn(Cout))) return rc;
   GemmParams p{};
+  p.stack = 1;
   p.M = imgs_per_sample * Ho * Wo;
   p.N = Cout;
   p.k_blocks = K / BK;

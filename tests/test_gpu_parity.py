@@ -88,6 +88,7 @@ def test_kl_forward_and_gradient(bu):
     (1, 128, 64, 64), (1, 128, 256, 64), (2, 300, 256, 192), (3, 1000, 512, 576), (1, 128, 2048, 512),
     (2, 4096, 64, 152, True), (1, 20000, 64, 64), (2, 256, 128, 2048, False, True), (1, 77, 72, 136),
     (1, 40000, 256, 64),   # > 148 tiles: persistent loop, TMEM double buffering
+    (5, 3000, 64, 152, True), (3, 1000, 128, 64, True), (9, 640, 64, 56, True),   # shared A: sample-stacked N tiles
 ])
 def test_tcgen05_gemm(bu, shape):
     _run(bu, bu.t_gemm, *shape)
