@@ -236,7 +236,7 @@ bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const 
 // Stem tail: BN + ReLU + 3x3/2 max-pool (pad 1) in one pass.
 // y: [G*B][H][W][C] fp16 raw conv output -> out: [G*B][Ho][Wo][C]. One block per (image, output row): no integer
 // division in the hot loop, the three input rows are read with 9 independent 16-byte loads per thread.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(128, 5)
 bn_relu_maxpool_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, int imgs_per_sample,
                        int H, int W, int C, int Ho, int Wo, uint4* __restrict__ out) {
   const int cvec = C >> 3;
@@ -408,8 +408,10 @@ int mauv_bn_relu_maxpool_f16(const void* y, const float* scale_shift, int G, int
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long imgs = static_cast<long long>(G) * imgs_per_sample;
   MAUV_CHECK_ARG(imgs <= 65535, "mauv_bn_relu_maxpool_f16: at most 65535 images per call (got %lld)", imgs);
+  // small blocks, several resident per SM: each block is one dependent load->max->store chain, so the memory
+  // latency is hidden by block-level parallelism
   int threads = Wo * (C / 8);
-  threads = threads > 512 ? 512 : ((threads + 31) / 32) * 32;
+  threads = threads > 128 ? 128 : ((threads + 31) / 32) * 32;
   dim3 grid(Ho, static_cast<unsigned>(imgs));
   bn_relu_maxpool_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift), imgs_per_sample, H, W, C,

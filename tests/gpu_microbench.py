@@ -99,6 +99,20 @@ def sample():
               f"({G * n / ms / 1e6:.1f} Gweights/s)", flush=True)
 
 
+def hbm():
+    """HBM read-only / write-only / copy bandwidth with plain torch ops (measurement aid for the roofline split)."""
+    n = 1 << 31
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    b = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: a.fill_(1), 5)
+    print(f"write-only (fill 2 GiB): {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s", flush=True)
+    af = a.view(torch.float32)
+    ms = timeit(lambda: af.sum(), 5)
+    print(f"read-only  (sum 2 GiB): {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s", flush=True)
+    ms = timeit(lambda: b.copy_(a), 5)
+    print(f"copy (2 GiB -> 2 GiB): {ms:.3f} ms  {2 * n / ms / 1e6:.1f} GB/s", flush=True)
+
+
 def layers():
     G, B = 4, 256
     for (M, N, K) in [(B * 4096, 256, 64), (B * 4096, 64, 256), (B * 4096, 64, 64), (B * 1024, 512, 128),
@@ -114,4 +128,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers}[cmd](*a)
+    {"gemm": gemm, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm}[cmd](*a)
