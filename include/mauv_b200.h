@@ -69,6 +69,12 @@ int mauv_gemm_m_tiles(long long M);
  * all samples, e.g. the stem's im2col matrix). W: [G][N][K]. bias (nullable): [G][N] fp32. */
 int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const void* bias,
                   void* y, float* stats_partial, int G, long long M, int N, int K, void* stream);
+/* Recompute scheme for a bottleneck's last 1x1 conv + BatchNorm + residual + ReLU (torchvision resnet.py:154-163),
+ * which is HBM-WRITE bound: mode 1 = batch statistics only (nothing stored, y may be NULL); mode 2 = second pass,
+ * out = relu?((A W^T) * scale + shift [+ residual]) written straight to y - the raw conv output never reaches HBM.
+ * scale_shift [G][N][2] from mauv_bn_finalize, residual [G][M][N] fp16 or NULL; N in {64, 128, k*256}. */
+int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
+                     const void* residual, int relu, int mode, int G, long long M, int N, int K, void* stream);
 /* x: [G*imgs_per_sample][H][W][Cin] NHWC fp16, fetched with im2col-mode TMA (Cin % 64 == 0);
  * W: [G][Cout][kh*kw*Cin]; y: [G*imgs_per_sample][Ho][Wo][Cout]. */
 int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,

@@ -47,11 +47,21 @@ struct GemmParams {
   __half* y;             // [G][M][N]
   float* stats;          // [G][m_tiles][N][2] or nullptr
   const float* bias;     // [G][N] or nullptr (sampled bias, linear layers)
+  // EPI == 2 (fused BatchNorm epilogue): out = relu?(acc * scale + shift [+ residual])
+  const float2* ss;      // [G][N] (scale, shift)
+  int has_res, relu;
 };
 
-template <int BN>
+// Epilogue flavours: 0 = raw fp16 store + BN statistics, 1 = BN statistics only (no output: first pass of the
+// recompute scheme), 2 = fused BN-apply (+ residual) (+ ReLU) store (second pass; no raw conv output ever hits HBM).
+enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2 };
+
+template <int BN, int EPI = 0>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  // the fused epilogue needs 3 staging buffers per warp (residual prefetch / transform / store in flight) and is
+  // only used for short-K (HBM-bound) layers, so it trades pipeline depth for staging space
+  static constexpr int kStages = (EPI == 2) ? ((BN == 256) ? 2 : 3) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
+  static constexpr int kOutBufs = (EPI == 2) ? 3 : 2;
   // epilogue warps: one set of 4 (TMEM lane quarters) per 64-column block in flight; two sets when BN >= 128
   static constexpr int kEpiWarps = (BN >= 128) ? 8 : 4;
   static constexpr int kABytes = BM * BK * 2;
@@ -59,17 +69,18 @@ struct SmemLayout {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging for the TMA store: per epilogue warp 2 buffers of 32 rows x 64 fp16 (128B-swizzled rows)
   static constexpr int kOutBufBytes = 32 * 64 * 2;
-  static constexpr int kOutBytes = kEpiWarps * 2 /*buffers*/ * kOutBufBytes;
+  static constexpr int kOutBytes = kEpiWarps * kOutBufs * kOutBufBytes;
   static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;   // pipeline + TMEM barriers, TMEM pointer, 3 residual barriers per epilogue warp
   static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes;
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
-  using L = SmemLayout<BN>;
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                   const GemmParams p) {
+  using L = SmemLayout<BN, EPI>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
 
@@ -88,6 +99,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
+  auto res_bar = [&](int w, int j) { return bar_base + 8u * (2 * kStages + 6 + w * 3 + j); };   // EPI == 2 only
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + kStages * L::kStageBytes + L::kOutBytes + L::kStatBytes + 8 * (2 * kStages + 4));
 
@@ -97,6 +109,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
+    if (EPI == EPI_FUSED_BN) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) {
@@ -107,6 +120,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), L::kEpiWarps);  // one arrive per epilogue warp
     }
+    if (EPI == EPI_FUSED_BN)
+      for (int w = 0; w < L::kEpiWarps; ++w)
+        for (int j = 0; j < 3; ++j) mbar_init(res_bar(w, j), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -225,6 +241,109 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t sw_off[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sw_off[j] = (((lane >> 2) ^ static_cast<uint32_t>(j)) << 4) + ((lane & 3u) << 2);
+    if constexpr (EPI == EPI_FUSED_BN) {
+      // ---- fused BN-apply (+ residual) (+ ReLU): out = relu?(acc * scale[g][n] + shift[g][n] + res[g][m][n]).
+      // Per warp a 3-deep ring of 32x64 fp16 staging buffers: while block b is transformed in place, the residual
+      // tile of block b+1 is already in flight (TMA load, one mbarrier per buffer) and block b-1 is being stored.
+      constexpr int kBlocksPerTile = BN / 64;
+      const int wq = warp - 4;
+      auto block_coords = [&](long long tile, int cb, int& gb, int& nb, int& row0, int& rmax) {
+        int g, m_tile, n_tile;
+        decode(tile, g, m_tile, n_tile);
+        gb = g;
+        nb = n_tile * BN + cb * 64;
+        row0 = m_tile * BM + ew * 32;
+        rmax = p.M - row0;
+        rmax = rmax < 0 ? 0 : (rmax > 32 ? 32 : rmax);
+      };
+      auto issue_residual = [&](uint32_t b, long long tile, int cb) {   // lane 0 only
+        int gb, nb, row0, rmax;
+        block_coords(tile, cb, gb, nb, row0, rmax);
+        if (p.has_res) {
+          // issued for EVERY block so that buffer b%3's barrier completes exactly once per use (parity = (b/3)&1);
+          // a slab entirely past M loads rows 0.. instead (never stored), N % BN == 0 keeps the columns in range
+          const uint32_t bar = res_bar(wq, b % 3u);
+          mbar_expect_tx(bar, L::kOutBufBytes);
+          tma_load_3d(my_out + (b % 3u) * L::kOutBufBytes, &tmR, bar, nb, rmax > 0 ? row0 : 0, gb);
+        }
+      };
+      uint32_t it = 0, b = 0;
+      if (lane == 0 && blockIdx.x < p.total_tiles) issue_residual(0, blockIdx.x, cset);
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+        mbar_wait(tmem_full_bar(acc), acc_phase);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int cb = cset; cb < kBlocksPerTile; cb += kColSets, ++b) {
+          int gb, nb, row0, rmax;
+          block_coords(tile, cb, gb, nb, row0, rmax);
+          if (lane == 0) {
+            // buffer (b+1)%3 was last used by block b-2: its store must have finished reading smem
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            long long ntile = tile;
+            int ncb = cb + kColSets;
+            if (ncb >= kBlocksPerTile) { ntile += gridDim.x; ncb = cset; }
+            if (ntile < p.total_tiles) issue_residual(b + 1, ntile, ncb);
+          }
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32b_x32(taddr + cb * 64, ra);
+          tmem_ld_32x32b_x32(taddr + cb * 64 + 32, rb);
+          tmem_ld_wait();
+          if (cb + kColSets >= kBlocksPerTile) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          }
+          const uint32_t buf = my_out + (b % 3u) * L::kOutBufBytes;
+          if (p.has_res) mbar_wait(res_bar(wq, b % 3u), (b / 3u) & 1u);
+          const float2* ssp = p.ss + static_cast<long long>(gb) * p.N + nb;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t* src = (q < 4) ? &ra[q * 8] : &rb[(q - 4) * 8];
+            const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 t = __ldg(ssp + q * 8 + j);
+              v[j] = fmaf(__uint_as_float(src[j]), t.x, t.y);
+            }
+            if (p.has_res) {
+              uint32_t r0, r1, r2, r3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+              const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h3))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (rmax > 0)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmY)),
+                           "r"(buf), "r"(nb), "r"(row0), "r"(gb)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+    } else {
     uint32_t it = 0, blk = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int g, m_tile, n_tile;
@@ -290,7 +409,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0 && rmax > 0) {
+        if (EPI == EPI_STORE_STATS && lane == 0 && rmax > 0) {
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmY)),
                        "r"(buf), "r"(nb), "r"(row0), "r"(gb)
@@ -351,6 +470,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+    }
     }
     // smem must stay valid until the last bulk stores have read it; global visibility at kernel end
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -441,18 +561,18 @@ int make_im2col_map(CUtensorMap* tm, const void* base, int64_t C, int64_t W, int
   return MAUV_OK;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const GemmParams& p,
-                cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN>,
+    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN><<<static_cast<unsigned>(grid), 384, L::kTotal, stream>>>(tmA, tmB, tmY, p);
+  gemm_f16_tc_kernel<BN, EPI><<<static_cast<unsigned>(grid), 384, L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
@@ -463,7 +583,8 @@ int pick_bn(int N) {
   return 256;
 }
 
-int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream, int epi = 0,
+             const void* residual = nullptr) {
   const int bn = p.stack > 1 ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
@@ -477,10 +598,28 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
     p.total_tiles = static_cast<long long>(p.m_tiles) * p.g_blocks;
   }
   if (p.total_tiles == 0) return MAUV_OK;
+  CUtensorMap tmR = tmY;
+  if (epi == EPI_FUSED_BN && residual) {
+    if (int rc = make_tiled_map(&tmR, residual, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
+  }
+  if (epi == EPI_STATS_ONLY) {
+    switch (bn) {
+      case 64: return launch_gemm<64, 1>(tmA, tmB, tmY, tmR, p, stream);
+      case 128: return launch_gemm<128, 1>(tmA, tmB, tmY, tmR, p, stream);
+      default: return launch_gemm<256, 1>(tmA, tmB, tmY, tmR, p, stream);
+    }
+  }
+  if (epi == EPI_FUSED_BN) {
+    switch (bn) {
+      case 64: return launch_gemm<64, 2>(tmA, tmB, tmY, tmR, p, stream);
+      case 128: return launch_gemm<128, 2>(tmA, tmB, tmY, tmR, p, stream);
+      default: return launch_gemm<256, 2>(tmA, tmB, tmY, tmR, p, stream);
+    }
+  }
   switch (bn) {
-    case 64: return launch_gemm<64>(tmA, tmB, tmY, p, stream);
-    case 128: return launch_gemm<128>(tmA, tmB, tmY, p, stream);
-    default: return launch_gemm<256>(tmA, tmB, tmY, p, stream);
+    case 64: return launch_gemm<64, 0>(tmA, tmB, tmY, tmR, p, stream);
+    case 128: return launch_gemm<128, 0>(tmA, tmB, tmY, tmR, p, stream);
+    default: return launch_gemm<256, 0>(tmA, tmB, tmY, tmR, p, stream);
   }
 }
 
@@ -522,6 +661,42 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
   p.stats = stats_partial;
   p.bias = static_cast<const float*>(bias);
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// Recompute scheme for the bottleneck's last 1x1 conv (HBM-write bound): mode 1 = statistics only (y may be NULL),
+// mode 2 = out = relu?(A*W^T * scale + shift [+ residual]) written straight to `y`; the raw conv output never
+// exists in HBM. scale_shift: [G][N][2] from mauv_bn_finalize; residual: [G][M][N] fp16 or NULL. N % 64 == 0.
+int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
+                     const void* residual, int relu, int mode, int G, long long M, int N, int K, void* stream) {
+  MAUV_CHECK_ARG(a && w, "mauv_gemm_bn_f16: null pointer");
+  MAUV_CHECK_ARG(mode == EPI_STATS_ONLY || mode == EPI_FUSED_BN, "mauv_gemm_bn_f16: mode must be 1 (stats) or 2 (fused)");
+  MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 64 && N % 64 == 0 && K >= 8 && K % 8 == 0, "mauv_gemm_bn_f16: bad shape G=%d M=%lld N=%d K=%d", G, M, N, K);
+  MAUV_CHECK_ARG(N % pick_bn(N) == 0, "mauv_gemm_bn_f16: N must be 64, 128 or a multiple of 256 (got %d)", N);
+  MAUV_CHECK_ARG(mode != EPI_STATS_ONLY || stats_partial, "mauv_gemm_bn_f16: stats buffer required in mode 1");
+  MAUV_CHECK_ARG(mode != EPI_FUSED_BN || (y && scale_shift), "mauv_gemm_bn_f16: y and scale_shift required in mode 2");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tiled_map(&tmA, a, K, M, G, M * K, BM)) return rc;
+  if (int rc = make_tiled_map(&tmB, w, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  GemmParams p{};
+  p.stack = 1;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.k_blocks = static_cast<int>(ceil_div_i64(K, BK));
+  p.G = G;
+  p.a_mode = 0;
+  p.a_batch_mul = 1;
+  // in mode 1 nothing is stored; the output map still needs a valid base address -> reuse A's
+  p.y = static_cast<__half*>(mode == EPI_FUSED_BN ? y : const_cast<void*>(a));
+  p.stats = mode == EPI_STATS_ONLY ? stats_partial : nullptr;
+  p.bias = nullptr;
+  p.ss = reinterpret_cast<const float2*>(scale_shift);
+  p.has_res = residual != nullptr;
+  p.relu = relu;
+  if (mode == EPI_STATS_ONLY) {
+    // the Y map describes [G][M][N]; with y aliased to A it is never written (EPI 1 issues no store)
+  }
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream), mode, residual);
 }
 
 int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,

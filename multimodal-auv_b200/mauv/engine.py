@@ -88,6 +88,10 @@ class MCEngine:
             raise _lib.MauvError("MCEngine: move the model to a CUDA device first (there is no CPU path)")
         self.device = p.device
         self.launches = 0
+        # recompute-fusion of conv3 + bn3 + residual + ReLU (removes the y3 write and re-read) for bottlenecks whose
+        # conv3 has K <= fuse_conv3_max_k (layer1/layer2: HBM-write bound; deeper ones are tensor bound)
+        self.fuse_conv3 = True
+        self.fuse_conv3_max_k = 128
 
     # ------------------------------------------------------------------ planning
     def _conv(self, layer: nn.Module, name: str) -> _Conv:
@@ -176,6 +180,17 @@ class MCEngine:
             a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
             y2, ss2 = self._conv_bn(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
             a2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True)
+            if blk.down is None and self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k:
+                # HBM-write-bound tail of the bottleneck: recompute scheme. Pass 1 = statistics of conv3 only,
+                # pass 2 = conv3 again with BN-apply + residual + ReLU in the epilogue; y3 never reaches HBM.
+                c3 = blk.conv3
+                w3 = self._sample(c3, G, s0, eps, seed)
+                NB, H, W, Cm = a2.shape
+                a2v = a2.view(G, B * H * W, Cm)
+                ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), B * H * W, blk.bn3, G)
+                x = ops.gemm_bn_act_f16(a2v, w3, ss3, residual=x.view(G, B * H * W, c3.cout), relu=True).view(NB, H, W, c3.cout)
+                self.launches += 2
+                continue
             y3, ss3 = self._conv_bn(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
             if blk.down is not None:
                 yd, ssd = self._conv_bn(blk.down, blk.down_bn, x, G, B, s0, eps, seed)

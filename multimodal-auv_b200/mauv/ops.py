@@ -138,6 +138,32 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] =
     return out, (stats_out if stats else None)
 
 
+def gemm_stats_f16(a: torch.Tensor, w: torch.Tensor, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First pass of the recompute scheme: BN partial statistics of A*W^T without storing it. a [G,M,K], w [G,N,K]."""
+    lib = _lib.require_device()
+    G, N, K = w.shape
+    M = a.shape[1]
+    if stats_out is None:
+        stats_out = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a.device)
+    _run("mauv_gemm_bn_f16", lib.mauv_gemm_bn_f16, _ptr(a, F16), _ptr(w, F16), None, _ptr(stats_out, F32), None, None, 0, 1,
+         G, M, N, K, _stream(), tag=f"stats G{G} M{M} N{N} K{K}" if _prof is not None else None)
+    return stats_out
+
+
+def gemm_bn_act_f16(a: torch.Tensor, w: torch.Tensor, ss: torch.Tensor, *, residual: Optional[torch.Tensor] = None,
+                    relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Second pass: out = relu?((A W^T) * scale + shift [+ residual]) -> [G, M, N] fp16."""
+    lib = _lib.require_device()
+    G, N, K = w.shape
+    M = a.shape[1]
+    if out is None:
+        out = torch.empty((G, M, N), dtype=F16, device=a.device)
+    _run("mauv_gemm_bn_f16", lib.mauv_gemm_bn_f16, _ptr(a, F16), _ptr(w, F16), _ptr(out, F16), None, _ptr(ss, F32),
+         _ptr(residual, F16), int(relu), 2, G, M, N, K, _stream(),
+         tag=f"fused G{G} M{M} N{N} K{K} res{int(residual is not None)}" if _prof is not None else None)
+    return out
+
+
 def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int, stride: int, pad: int, *,
                       stats: bool = False, out: Optional[torch.Tensor] = None,
                       stats_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

@@ -252,6 +252,32 @@ def t_gemm(G, M, N, K, shared=False, bias=False):
         print("   bad rows (first 16):", rows[:16].tolist(), " bad cols (first 16):", cols[:16].tolist())
 
 
+def t_gemm_bn(G, M, N, K, res=True):
+    """Recompute scheme: stats-only pass + fused BN/residual/ReLU pass == gemm -> BN(train) -> +res -> relu."""
+    torch.manual_seed(9)
+    a = (torch.randn(G, M, K, device=dev) * 0.5).half()
+    w = (torch.randn(G, N, K, device=dev) * 0.1).half()
+    r = torch.randn(G, M, N, device=dev).half() if res else None
+    gamma = torch.rand(N, device=dev) + 0.5
+    beta = torch.randn(N, device=dev)
+    st = ops.gemm_stats_f16(a, w)
+    ss = ops.bn_finalize(st, M, gamma, beta)
+    out = ops.gemm_bn_act_f16(a, w, ss, residual=r, relu=True)
+    torch.cuda.synchronize()
+    y = torch.einsum("gmk,gnk->gmn", a.float(), w.float())
+    ref = torch.stack([F.batch_norm(y[g], None, None, gamma, beta, True, 0.1, 1e-5) for g in range(G)])
+    if res:
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    ok = report(f"gemm_bn fused G={G} M={M} N={N} K={K} res={res}", out, ref, 4e-3)
+    report("   stats sum", st[..., 0].sum(1), y.sum(1), 3e-3)
+    if not ok:
+        err = (out.float() - ref).abs()
+        bad = (err > 4e-3 * ref.abs().max()).nonzero()
+        print("   n_bad:", bad.shape[0], "of", err.numel(), " first:", bad[:6].tolist(),
+              " bad rows:", torch.unique(bad[:, 1])[:12].tolist(), " bad cols:", torch.unique(bad[:, 2])[:12].tolist())
+
+
 def t_conv(G, B, H, W, Cin, Cout, k, stride, pad):
     torch.manual_seed(8)
     x = (torch.randn(G * B, H, W, Cin, device=dev) * 0.5).half()
@@ -401,6 +427,9 @@ GROUPS = {
         (1, 128, 64, 64), (1, 128, 128, 64), (1, 128, 256, 64), (1, 256, 128, 128), (2, 300, 256, 192),
         (3, 1000, 512, 576), (1, 128, 2048, 512), (2, 4096, 64, 152, True), (1, 20000, 64, 64),
         (2, 256, 128, 2048, False, True), (1, 77, 72, 136)]],
+    "gemm_bn": lambda: [run_case(t_gemm_bn, *a) for a in [
+        (2, 1000, 256, 64), (3, 4096, 512, 128), (1, 40, 64, 64), (2, 20000, 256, 64), (1, 300, 128, 128, False),
+        (4, 65536, 256, 64)]],
     "conv": lambda: [run_case(t_conv, *a) for a in [
         (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
         (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),

@@ -95,6 +95,15 @@ def test_tcgen05_gemm(bu, shape):
 
 
 @pytest.mark.parametrize("shape", [
+    (2, 1000, 256, 64), (3, 4096, 512, 128), (1, 40, 64, 64), (2, 20000, 256, 64), (1, 300, 128, 128, False),
+    (4, 65536, 256, 64),
+])
+def test_tcgen05_gemm_fused_batchnorm_residual_epilogue(bu, shape):
+    """conv3 recompute scheme (stats-only pass + fused BN / residual / ReLU store) == gemm -> BN(train) -> +res -> relu"""
+    _run(bu, bu.t_gemm_bn, *shape)
+
+
+@pytest.mark.parametrize("shape", [
     (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1), (1, 1, 16, 16, 256, 512, 1, 2, 0),
     (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1), (1, 2, 4, 4, 512, 512, 3, 1, 1),
     (3, 1, 6, 6, 128, 64, 3, 2, 1),
