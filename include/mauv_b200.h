@@ -73,6 +73,7 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
  * which is HBM-WRITE bound: mode 1 = batch statistics only (nothing stored, y may be NULL); mode 2 = second pass,
  * out = relu?((A W^T) * scale + shift [+ residual]) written straight to y - the raw conv output never reaches HBM.
  * scale_shift [G][N][2] from mauv_bn_finalize, residual [G][M][N] fp16 or NULL; N in {64, 128, k*256}. */
+int mauv_gemm_bn_stats_tiles(long long M);   /* leading dim of stats_partial in mode 1: [G][tiles][N][2] */
 int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
                      const void* residual, int relu, int mode, int G, long long M, int N, int K, void* stream);
 /* x: [G*imgs_per_sample][H][W][Cin] NHWC fp16, fetched with im2col-mode TMA (Cin % 64 == 0);

@@ -54,7 +54,10 @@ struct GemmParams {
 
 // Epilogue flavours: 0 = raw fp16 store + BN statistics, 1 = BN statistics only (no output: first pass of the
 // recompute scheme), 2 = fused BN-apply (+ residual) (+ ReLU) store (second pass; no raw conv output ever hits HBM).
-enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2 };
+enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2, EPI_STATS_T = 3 };
+// EPI_STATS_T: statistics pass with the operand roles swapped (MMA-M = output channels, MMA-N = pixels): a TMEM lane
+// is a channel, so every epilogue thread sums its own channel over the tile's pixels in registers - no shuffles, no
+// shared memory, no output. Pixels past M are zero-filled by TMA and contribute nothing.
 
 template <int BN, int EPI = 0>
 struct SmemLayout {
@@ -118,7 +121,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), L::kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(a), EPI == EPI_STATS_T ? 4 : L::kEpiWarps);  // one arrive per epilogue warp
     }
     if (EPI == EPI_FUSED_BN)
       for (int w = 0; w < L::kEpiWarps; ++w)
@@ -137,7 +140,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // tile -> (g, m_tile, n_tile). n-tile fastest so concurrent CTAs share their A tile through L2; when A is shared
   // by all samples (stem) the sample index is the fastest instead, so the G samples of one m-tile run together.
   auto decode = [&](long long tile, int& g, int& m_tile, int& n_tile) {
-    if (p.stack > 1) {              // g = first sample of the tile's sample block; a single n-tile
+    if (EPI == EPI_STATS_T) {       // channel tile fastest: the (big) pixel operand is fetched from HBM once
+      m_tile = static_cast<int>(tile % p.m_tiles);
+      const long long rem = tile / p.m_tiles;
+      n_tile = static_cast<int>(rem % p.n_tiles);
+      g = static_cast<int>(rem / p.n_tiles);
+    } else if (p.stack > 1) {       // g = first sample of the tile's sample block; a single n-tile
       g = static_cast<int>(tile % p.g_blocks) * p.stack;
       m_tile = static_cast<int>(tile / p.g_blocks);
       n_tile = 0;
@@ -236,12 +244,49 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int cset = (warp - 4) >> 2;         // which 64-column blocks this warp takes (cb = cset, cset + kColSets, ..)
     const uint32_t lane = lane_id();
     const int et = threadIdx.x - 128;         // 0 .. kEpiThreads-1
-    const uint32_t my_out = out_base + (warp - 4) * (2 * L::kOutBufBytes);
+    const uint32_t my_out = out_base + (warp - 4) * (L::kOutBufs * L::kOutBufBytes);
     // swizzled 16-byte chunk offsets of this lane's channel pair for rows r = 0..7 (mod 8)
     uint32_t sw_off[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sw_off[j] = (((lane >> 2) ^ static_cast<uint32_t>(j)) << 4) + ((lane & 3u) << 2);
-    if constexpr (EPI == EPI_FUSED_BN) {
+    if constexpr (EPI == EPI_STATS_T) {
+      if (warp < 8) {   // one warp per TMEM lane quarter (= 32 channels) is enough: pure register accumulation
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+          int g, m_tile, n_tile;
+          decode(tile, g, m_tile, n_tile);          // m_tile: channel tile, n_tile: pixel tile
+          const uint32_t acc = it & 1u;
+          const uint32_t acc_phase = (it >> 1) & 1u;
+          const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+          mbar_wait(tmem_full_bar(acc), acc_phase);
+          tcgen05_fence_after();
+          unsigned long long s2 = 0ull, q2 = 0ull;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              // the stored activations are fp16: take the statistics of the rounded values, as the other epilogues do
+              const __half2 h = __floats2half2_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+              const float2 f = __half22float2(h);
+              const unsigned long long f2 = *reinterpret_cast<const unsigned long long*>(&f);
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(f2));
+              asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q2) : "l"(f2));
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          const float2 sf = *reinterpret_cast<float2*>(&s2), qf = *reinterpret_cast<float2*>(&q2);
+          const int ch = m_tile * BM + ew * 32 + static_cast<int>(lane);
+          if (ch < p.M)   // p.M = channels, p.n_tiles = pixel tiles in this mode
+            reinterpret_cast<float2*>(p.stats)[(static_cast<long long>(g) * p.n_tiles + n_tile) * p.M + ch] =
+                make_float2(sf.x + sf.y, qf.x + qf.y);
+        }
+      }
+    } else if constexpr (EPI == EPI_FUSED_BN) {
       // ---- fused BN-apply (+ residual) (+ ReLU): out = relu?(acc * scale[g][n] + shift[g][n] + res[g][m][n]).
       // Per warp a 3-deep ring of 32x64 fp16 staging buffers: while block b is transformed in place, the residual
       // tile of block b+1 is already in flight (TMA load, one mbarrier per buffer) and block b-1 is being stored.
@@ -585,7 +630,7 @@ int pick_bn(int N) {
 
 int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream, int epi = 0,
              const void* residual = nullptr) {
-  const int bn = p.stack > 1 ? 256 : pick_bn(p.N);
+  const int bn = (p.stack > 1 || epi == EPI_STATS_T) ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
   if (int rc = make_tiled_map(&tmY, p.y, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
@@ -609,6 +654,7 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
       default: return launch_gemm<256, 1>(tmA, tmB, tmY, tmR, p, stream);
     }
   }
+  if (epi == EPI_STATS_T) return launch_gemm<256, 3>(tmA, tmB, tmY, tmR, p, stream);
   if (epi == EPI_FUSED_BN) {
     switch (bn) {
       case 64: return launch_gemm<64, 2>(tmA, tmB, tmY, tmR, p, stream);
@@ -629,6 +675,8 @@ extern "C" {
 
 // Number of 128-row tiles per sample: the leading dimension of the BN partial-statistics buffer.
 int mauv_gemm_m_tiles(long long M) { return static_cast<int>(ceil_div_i64(M, BM)); }
+// Row tiles of the statistics buffer written by mauv_gemm_bn_f16 mode 1 (256 pixels per tile).
+int mauv_gemm_bn_stats_tiles(long long M) { return static_cast<int>(ceil_div_i64(M, 256)); }
 
 int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const void* bias,
                   void* y, float* stats_partial, int G, long long M, int N, int K, void* stream) {
@@ -676,6 +724,29 @@ int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial
   MAUV_CHECK_ARG(mode != EPI_FUSED_BN || (y && scale_shift), "mauv_gemm_bn_f16: y and scale_shift required in mode 2");
   if (int rc = load_driver_entry_points()) return rc;
   CUtensorMap tmA, tmB;
+  if (mode == EPI_STATS_ONLY) {
+    // statistics pass: swap the operand roles (MMA-M = channels, MMA-N = pixels), see EPI_STATS_T.
+    // stats layout: [G][ceil(M/256)][N] float2 (mauv_gemm_bn_stats_tiles(M) pixel tiles)
+    if (int rc = make_tiled_map(&tmA, w, K, N, G, static_cast<int64_t>(N) * K, BM)) return rc;
+    if (int rc = make_tiled_map(&tmB, a, K, M, G, M * K, 256)) return rc;
+    GemmParams q{};
+    q.stack = 1;
+    q.M = N;                               // channels
+    q.N = static_cast<int>(M);             // pixels
+    q.k_blocks = static_cast<int>(ceil_div_i64(K, BK));
+    q.G = G;
+    q.a_mode = 0;
+    q.a_batch_mul = 1;
+    q.y = static_cast<__half*>(const_cast<void*>(a));   // never written
+    q.stats = stats_partial;
+    // the (unused) output map must still be encodable: describe it over A's bytes with legal extents
+    CUtensorMap tmY;
+    if (int rc = make_tiled_map(&tmY, a, K, M, G, M * K, 32)) return rc;
+    q.m_tiles = static_cast<int>(ceil_div_i64(q.M, BM));
+    q.n_tiles = static_cast<int>(ceil_div_i64(q.N, 256));
+    q.total_tiles = static_cast<long long>(q.m_tiles) * q.n_tiles * q.G;
+    return launch_gemm<256, 3>(tmA, tmB, tmY, tmY, q, static_cast<cudaStream_t>(stream));
+  }
   if (int rc = make_tiled_map(&tmA, a, K, M, G, M * K, BM)) return rc;
   if (int rc = make_tiled_map(&tmB, w, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
   GemmParams p{};

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mauv_philox_normal_f32": (i32, [u64, u32, u32, i64, vp, vp]),
     "mauv_gemm_m_tiles": (i32, [i64]),
     "mauv_gemm_f16": (i32, [vp, i64, vp, vp, vp, vp, i32, i64, i32, i32, vp]),
+    "mauv_gemm_bn_stats_tiles": (i32, [i64]),
     "mauv_gemm_bn_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
     "mauv_conv2d_im2col_f16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mauv_stem_im2col_f16": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),

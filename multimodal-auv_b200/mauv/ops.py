@@ -144,7 +144,7 @@ def gemm_stats_f16(a: torch.Tensor, w: torch.Tensor, stats_out: Optional[torch.T
     G, N, K = w.shape
     M = a.shape[1]
     if stats_out is None:
-        stats_out = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a.device)
+        stats_out = torch.empty((G, (M + 255) // 256, N, 2), dtype=F32, device=a.device)
     _run("mauv_gemm_bn_f16", lib.mauv_gemm_bn_f16, _ptr(a, F16), _ptr(w, F16), None, _ptr(stats_out, F32), None, None, 0, 1,
          G, M, N, K, _stream(), tag=f"stats G{G} M{M} N{N} K{K}" if _prof is not None else None)
     return stats_out
