@@ -260,22 +260,27 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
           mbar_wait(tmem_full_bar(acc), acc_phase);
           tcgen05_fence_after();
-          unsigned long long s2 = 0ull, q2 = 0ull;
+          unsigned long long s2 = 0ull, q2 = 0ull, s3 = 0ull, q3 = 0ull;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
+          for (int c = 0; c < BN / 64; ++c) {
+            uint32_t r[32], t[32];
+            tmem_ld_32x32b_x32(taddr + c * 64, r);        // two loads in flight per wait
+            tmem_ld_32x32b_x32(taddr + c * 64 + 32, t);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              // the stored activations are fp16: take the statistics of the rounded values, as the other epilogues do
-              const __half2 h = __floats2half2_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-              const float2 f = __half22float2(h);
-              const unsigned long long f2 = *reinterpret_cast<const unsigned long long*>(&f);
+              // consecutive accumulator registers are used directly as packed fp32x2 operands
+              unsigned long long f2, g2;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "r"(r[j]), "r"(r[j + 1]));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(g2) : "r"(t[j]), "r"(t[j + 1]));
               asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(f2));
               asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q2) : "l"(f2));
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s3) : "l"(g2));
+              asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q3) : "l"(g2));
             }
           }
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(s3));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q2) : "l"(q3));
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
