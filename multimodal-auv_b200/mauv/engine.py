@@ -91,7 +91,7 @@ class MCEngine:
         # recompute-fusion of conv3 + bn3 + residual + ReLU (removes the y3 write and re-read) for bottlenecks whose
         # conv3 has K <= fuse_conv3_max_k (layer1/layer2: HBM-write bound; deeper ones are tensor bound)
         self.fuse_conv3 = True
-        self.fuse_conv3_max_k = int(__import__('os').environ.get('MAUV_FUSE_CONV3_MAX_K', '128'))
+        self.fuse_conv3_max_k = int(__import__('os').environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
 
     # ------------------------------------------------------------------ planning
     def _conv(self, layer: nn.Module, name: str) -> _Conv:

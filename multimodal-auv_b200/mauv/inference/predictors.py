@@ -98,30 +98,42 @@ def _unpack_results(host: torch.Tensor) -> Dict[str, torch.Tensor]:
 
 
 def predict_stream(predictor: "MCPredictor", host_batches):
-    """Pipelined predict_batch over an iterable of host batches: the H2D copy of batch i+1 runs on a copy stream
-    while batch i computes (what a DataLoader loop wants). Yields one result dict (host tensors) per batch."""
-    copy_stream = torch.cuda.Stream(device=predictor.device)
+    """Pipelined predict_batch over an iterable of host batches: the H2D copy of batch i+1 runs on a copy stream into
+    a second set of device buffers while batch i computes (what a DataLoader loop wants). Two pre-allocated buffer
+    sets are recycled, so the steady state makes no allocator calls. Yields one result dict (host tensors) per batch."""
+    dev = predictor.device
+    copy_stream = torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream(dev)
+    slots = [None, None]                 # per slot: list of device tensors
+    free_ev = [None, None]               # compute-stream event: slot no longer read
     it = iter(host_batches)
 
-    def stage(hb):
+    def stage(hb, k):
+        if slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slots[k], hb)):
+            slots[k] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in hb]
+        if free_ev[k] is not None:
+            copy_stream.wait_event(free_ev[k])
         with torch.cuda.stream(copy_stream):
-            dev = [x.to(predictor.device, non_blocking=True) for x in hb]
+            for d, h in zip(slots[k], hb):
+                d.copy_(h, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(copy_stream)
-        return dev, ev
+        return ev
 
+    k = 0
     nxt = next(it, None)
-    staged = stage(nxt) if nxt is not None else None
-    while staged is not None:
-        dev, ev = staged
+    ready = stage(nxt, k) if nxt is not None else None
+    while ready is not None:
+        cur_k, cur_ready = k, ready
         nxt = next(it, None)
-        staged = stage(nxt) if nxt is not None else None      # overlaps with the compute below
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev)
-        o = predictor.predict_device(dev)
-        for t in dev:
-            t.record_stream(cur)
-        yield _unpack_results(_pack_results(o).cpu())
+        k ^= 1
+        ready = stage(nxt, k) if nxt is not None else None       # overlaps with the compute below
+        compute.wait_event(cur_ready)
+        o = predictor.predict_device(slots[cur_k])
+        packed = _pack_results(o)
+        free_ev[cur_k] = torch.cuda.Event()
+        free_ev[cur_k].record(compute)
+        yield _unpack_results(packed.cpu())
 
 
 def multimodal_predict_and_save(multimodal_model: nn.Module, dataloader, device: torch.device, csv_path: str,

@@ -60,6 +60,12 @@ STALE_EPS_QUIRK = True
 
 class _ReparamBase(nn.Module):
     dnn_to_bnn_flag = False
+    # test aid (not reference behaviour): round the sampled weight to fp16, the operand precision of the CUDA
+    # tensor-core path, so that tests can separate "engine logic" from "operand precision" (emulate_fp16_pipeline)
+    round_weight_fp16 = False
+
+    def _maybe_round(self, w: torch.Tensor) -> torch.Tensor:
+        return w.half().to(w.dtype) if self.round_weight_fp16 else w
 
     def _draw(self, buf: torch.Tensor, injected: Optional[torch.Tensor]) -> torch.Tensor:
         if injected is not None:
@@ -129,7 +135,7 @@ class Conv2dReparameterization(_ReparamBase):
             return_kl = False
         sigma_weight = torch.log1p(torch.exp(self.rho_kernel))
         eps_kernel = self._draw(self.eps_kernel, self.injected_eps_kernel)
-        weight = self.mu_kernel + (sigma_weight * eps_kernel)
+        weight = self._maybe_round(self.mu_kernel + (sigma_weight * eps_kernel))
         if return_kl:
             kl_weight = kl_div(self.mu_kernel, sigma_weight, self.prior_weight_mu, self.prior_weight_sigma)
         bias = None
@@ -396,6 +402,36 @@ def define_models(num_classes: int, prior: dict = DEFAULT_PRIOR, seed: Optional[
 # --------------------------------------------------------------------------------------
 # eps capture / injection
 # --------------------------------------------------------------------------------------
+
+
+def emulate_fp16_pipeline(model: nn.Module, unrounded_convs=()):
+    """Test aid: make the oracle round exactly where the CUDA engine stores fp16 - conv operands (inputs and sampled
+    weights), raw conv outputs (except `unrounded_convs`: the convs whose BatchNorm is fused into the GEMM epilogue),
+    max-pool and bottleneck outputs - while BatchNorm, the head and all statistics stay fp32 as in the engine.
+    Differences that remain against the engine are accumulation order only. Returns the hook handles."""
+    from torchvision.models.resnet import Bottleneck
+    hs = []
+
+    def r16(t):
+        return t.half().float()
+
+    for name, m in model.named_modules():
+        if hasattr(m, "mu_kernel"):
+            m.round_weight_fp16 = True
+            hs.append(m.register_forward_pre_hook(lambda mod, inp: tuple(r16(i) for i in inp)))
+            if name not in unrounded_convs:
+                hs.append(m.register_forward_hook(lambda mod, inp, out: r16(out)))
+        elif isinstance(m, (Bottleneck, nn.MaxPool2d)):
+            hs.append(m.register_forward_hook(lambda mod, inp, out: r16(out)))
+    return hs
+
+
+def stop_emulation(model: nn.Module, hooks) -> None:
+    for h in hooks:
+        h.remove()
+    for m in model.modules():
+        if hasattr(m, "mu_kernel"):
+            m.round_weight_fp16 = False
 
 
 def bayesian_layers(model: nn.Module) -> List[tuple]:

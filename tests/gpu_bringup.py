@@ -356,6 +356,23 @@ def t_engine(B=2, S=2, size=64, kind="multimodal"):
     got = eng.forward_mc([t.to(dev) for t in inputs], S, eps=eps)
     torch.cuda.synchronize()
     print(f"   engine time {time.time() - t0:.2f}s")
+    # precision-matched oracle: rounds to fp16 exactly where the engine stores fp16 -> isolates the engine LOGIC
+    fused = set()
+    if eng.fuse_conv3:
+        for t in eng.trunks:
+            for blk in t.blocks:
+                if blk.down is None and blk.conv3.cin <= eng.fuse_conv3_max_k:
+                    fused.add(blk.conv3.name)
+    o_model.load_state_dict(sd0)
+    hooks = O.emulate_fp16_pipeline(o_model, fused)
+    matched = O.mc_logits(o_model, inputs, S, eps)
+    O.stop_emulation(o_model, hooks)
+    merr = (got.cpu() - matched).abs().max().item()
+    mok = merr <= 2e-3 * max(matched.abs().max().item(), 1e-3) + 1e-4
+    print(f"engine {kind} B={B} size={size} logits vs precision-matched oracle: max_abs_err={merr:.3e} "
+          f"(|logit| max {matched.abs().max().item():.3f}; bound 2e-3 rel)  {'[OK]' if mok else '[FAIL]'}", flush=True)
+    if not mok:
+        FAILS.append((f"engine {kind} matched", f"err {merr}"))
     err = (got.cpu() - ref).abs().max().item()
     ok = err <= 3.0 * calib + 1e-4
     print(f"engine {kind} B={B} size={size} logits vs oracle fp32: max_abs_err={err:.3e} (bound 3x calib = {3 * calib:.3e})"
