@@ -171,6 +171,31 @@ int mauv_sampled_linear_bwd_f32(const float* x, const float* gy, const float* mu
                                 float* gx, float* grad_mu_w, float* grad_rho_w, float* grad_mu_b, float* grad_rho_b,
                                 void* stream);
 
+/* ---- fp16x3 validation mode ------------------------------------------------------------------------
+ * Every value travels as an fp16 (hi | lo) pair (hi + lo ~ 22 mantissa bits) and a*w is contracted as
+ * a_hi*w_hi + a_lo*w_hi + a_hi*w_lo by the SAME tcgen05 kernel over K-concatenated operands
+ * A' = [a_hi | a_lo | a_hi] (the third block re-reads the first), W' = [w_hi | w_hi | w_lo]; the epilogue writes the
+ * fp32 accumulator as a (hi | lo) pair. ~3x the work of the fast path; exists so that the whole engine can be checked
+ * against the fp32 reference at rtol 1e-3 through every layer. */
+/* a2 [G][M][2K] (hi | lo), K % 64 == 0 (a_sample_stride 0 = shared); w3 [G][N][3K]; y2 [G][M][2N]. */
+int mauv_gemm_x3_f16(const void* a2, long long a_sample_stride, const void* w3, void* y2, float* stats_partial, int G,
+                     long long M, int N, int K, void* stream);
+/* x2 [G*imgs][H][W][2Cin]; w3 [G][Cout][kh*kw*3*Cin] (per tap: hi | hi | lo); y2 [G*imgs][Ho][Wo][2Cout]. */
+int mauv_conv2d_im2col_x3_f16(const void* x2, const void* w3, void* y2, float* stats_partial, int G, int imgs_per_sample,
+                              int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, void* stream);
+/* scale * (mu + log1p(exp(rho)) * eps) split into [hi | hi | lo]; per_tap = 0: flat over K padded to kp (% 64),
+ * row length 3*kp; per_tap = 1: per filter tap, row length kh*kw*3*cin. */
+int mauv_sample_weights_x3_f16(const float* mu, const float* rho, const float* eps, uint64_t seed, uint32_t layer_id,
+                               uint32_t sample0, int G, int cout, int cin, int kh, int kw, int kp, int per_tap,
+                               float scale, void* w_out, void* stream);
+int mauv_stem_im2col_x3_f16(const float* x_nchw, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int kp,
+                            void* out, void* stream);
+int mauv_bn_act_x3_f16(const void* y2, const float* scale_shift, const void* residual2, const void* y2b,
+                       const float* scale_shift2, int relu, int G, long long M, int C, void* out2, void* stream);
+int mauv_bn_relu_maxpool_x3_f16(const void* y2, const float* scale_shift, int G, int imgs_per_sample, int H, int W, int C,
+                                void* out2, void* stream);
+int mauv_avgpool_x3_f16(const void* x2, long long N, int HW, int C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

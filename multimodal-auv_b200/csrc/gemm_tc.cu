@@ -50,6 +50,10 @@ struct GemmParams {
   // EPI == 2 (fused BatchNorm epilogue): out = relu?(acc * scale + shift [+ residual])
   const float2* ss;      // [G][N] (scale, shift)
   int has_res, relu;
+  // fp16x3 validation mode (K-concatenated hi/lo operands, see mauv_gemm_x3_f16):
+  int a_wrap_kb;         // tiled A: k-block count after which A's column coordinate wraps to 0 (0 = never)
+  int a_cwrap;           // im2col A: channel-block period of A (0 = never)
+  int split;             // epilogue writes (hi | lo) fp16 pairs: hi at column n, lo at column N + n
 };
 
 // Epilogue flavours: 0 = raw fp16 store + BN statistics, 1 = BN statistics only (no output: first pass of the
@@ -187,10 +191,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t b_dst = a_dst + L::kABytes;
           mbar_expect_tx(full_bar(stage), L::kStageBytes);
           if (p.a_mode == 0) {
-            tma_load_3d(a_dst, &tmA, full_bar(stage), kb * BK, m0, g * p.a_batch_mul);
+            const int akb = p.a_wrap_kb ? kb % p.a_wrap_kb : kb;
+            tma_load_3d(a_dst, &tmA, full_bar(stage), akb * BK, m0, g * p.a_batch_mul);
           } else {
             const int tap = kb / p.c_blocks;
-            const int cb = kb - tap * p.c_blocks;
+            int cb = kb - tap * p.c_blocks;
+            if (p.a_cwrap) cb %= p.a_cwrap;
             const int r = tap / p.kw;
             const int s = tap - r * p.kw;
             tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), cb * BK, iq * p.stride - p.pad,
@@ -440,9 +446,14 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (n0 + col0 + 32 + j < p.N) rb[j] = __float_as_uint(__uint_as_float(rb[j]) + bias[col0 + 32 + j]);
           }
         }
-        const uint32_t buf = my_out + (blk & 1u) * L::kOutBufBytes;
-        // the TMA store issued from this buffer two blocks ago must have finished reading it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // split (fp16x3 validation) mode uses both buffers per block: hi and lo halves of the fp32 accumulator
+        const uint32_t buf = p.split ? my_out : my_out + (blk & 1u) * L::kOutBufBytes;
+        const uint32_t buf_lo = my_out + L::kOutBufBytes;
+        // the TMA store issued from this buffer two blocks ago (split: both previous stores) must have finished reading it
+        if (lane == 0) {
+          if (p.split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -451,11 +462,24 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]), __uint_as_float(src[3]));
           __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]), __uint_as_float(src[5]));
           __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]), __uint_as_float(src[7]));
-          const uint32_t dst = buf + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+          const uint32_t off = lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
                        "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
                        "r"(*reinterpret_cast<uint32_t*>(&h3))
                        : "memory");
+          if (p.split) {
+            const __half2 hh[4] = {h0, h1, h2, h3};
+            uint32_t lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(hh[j]);
+              __half2 l = __floats2half2_rn(__uint_as_float(src[2 * j]) - f.x, __uint_as_float(src[2 * j + 1]) - f.y);
+              lo[j] = *reinterpret_cast<uint32_t*>(&l);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                         "r"(lo[3])
+                         : "memory");
+          }
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -464,13 +488,24 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                            reinterpret_cast<uint64_t>(&tmY)),
                        "r"(buf), "r"(nb), "r"(row0), "r"(gb)
                        : "memory");
+          if (p.split)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmY)),
+                         "r"(buf_lo), "r"(p.N + nb), "r"(row0), "r"(gb)
+                         : "memory");
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (p.stats) {
           // lane j owns output channels col0 + 2j, 2j+1: column sums over the warp's valid rows, packed fp32x2 math
           unsigned long long sa = 0ull, sb = 0ull, qa = 0ull, qb = 0ull;   // (s0,s1) / (q0,q1), two chains for ILP
-          auto acc2 = [&](uint32_t w, unsigned long long& s2, unsigned long long& q2) {
-            const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+          auto acc2 = [&](uint32_t w, unsigned long long& s2, unsigned long long& q2, uint32_t off = 0) {
+            float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+            if (p.split) {      // statistics of the full-precision value hi + lo
+              uint32_t wl;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wl) : "r"(buf_lo + off));
+              const float2 fl = __half22float2(*reinterpret_cast<__half2*>(&wl));
+              f.x += fl.x; f.y += fl.y;
+            }
             const unsigned long long f2 = *reinterpret_cast<const unsigned long long*>(&f);
             asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(f2));
             asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q2) : "l"(f2));
@@ -481,15 +516,15 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               uint32_t w0, w1;
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(buf + sw_off[r & 7] + r * 128u));
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(buf + sw_off[(r + 1) & 7] + (r + 1) * 128u));
-              acc2(w0, sa, qa);
-              acc2(w1, sb, qb);
+              acc2(w0, sa, qa, sw_off[r & 7] + r * 128u);
+              acc2(w1, sb, qb, sw_off[(r + 1) & 7] + (r + 1) * 128u);
             }
           } else {
             for (int r = 0; r < rmax; ++r) {
               uint32_t w0;
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0)
                            : "r"(buf + ((((lane >> 2) ^ (r & 7u)) << 4) + ((lane & 3u) << 2)) + r * 128u));
-              acc2(w0, sa, qa);
+              acc2(w0, sa, qa, ((((lane >> 2) ^ (r & 7u)) << 4) + ((lane & 3u) << 2)) + r * 128u);
             }
           }
           asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(sb));
@@ -638,7 +673,8 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
   const int bn = (p.stack > 1 || epi == EPI_STATS_T) ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
-  if (int rc = make_tiled_map(&tmY, p.y, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
+  const int n_out = p.split ? 2 * p.N : p.N;
+  if (int rc = make_tiled_map(&tmY, p.y, n_out, p.M, p.G, static_cast<int64_t>(p.M) * n_out, 32)) return rc;
   p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
   p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
   p.total_tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.G;
@@ -713,6 +749,65 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
   p.y = static_cast<__half*>(y);
   p.stats = stats_partial;
   p.bias = static_cast<const float*>(bias);
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- fp16x3 validation mode -------------------------------------------------------------------------------------
+// a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with a = a_hi + a_lo, w = w_hi + w_lo (fp16 pairs, ~2^-22 relative): the
+// three terms are ONE contraction over a K-concatenated operand pair A' = [a_hi | a_lo | a_hi], W' = [w_hi | w_hi | w_lo].
+// Activations are stored as (hi | lo) pairs ([.., 2C]); the third block re-reads the first (A's coordinate wraps), the
+// weights are sampled straight into the 3K layout, and the epilogue writes the fp32 accumulator as a (hi | lo) pair.
+// Same tcgen05 kernel, ~3x the MMA work and bytes: this mode exists to check the engine end to end at ~fp32 accuracy.
+int mauv_gemm_x3_f16(const void* a2, long long a_sample_stride, const void* w3, void* y2, float* stats_partial, int G,
+                     long long M, int N, int K, void* stream) {
+  // a2: [G][M][2K] (hi | lo), K % 64 == 0; w3: [G][N][3K]; y2: [G][M][2N] (hi | lo)
+  MAUV_CHECK_ARG(a2 && w3 && y2, "mauv_gemm_x3_f16: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 8 && N % 8 == 0 && K >= 64 && K % 64 == 0, "mauv_gemm_x3_f16: bad shape");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  const bool shared_a = (a_sample_stride == 0);
+  if (int rc = make_tiled_map(&tmA, a2, 2 * K, M, shared_a ? 1 : G, shared_a ? M * 2 * K : a_sample_stride, BM)) return rc;
+  if (int rc = make_tiled_map(&tmB, w3, 3 * K, N, G, static_cast<int64_t>(N) * 3 * K, pick_bn(N))) return rc;
+  GemmParams p{};
+  p.stack = 1;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.k_blocks = 3 * K / BK;
+  p.a_wrap_kb = 2 * K / BK;
+  p.split = 1;
+  p.G = G;
+  p.a_mode = 0;
+  p.a_batch_mul = shared_a ? 0 : 1;
+  p.y = static_cast<__half*>(y2);
+  p.stats = stats_partial;
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+int mauv_conv2d_im2col_x3_f16(const void* x2, const void* w3, void* y2, float* stats_partial, int G, int imgs_per_sample,
+                              int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, void* stream) {
+  // x2: [G*imgs][H][W][2*Cin] (hi | lo); w3: [G][Cout][kh*kw*3*Cin] per tap (hi | hi | lo); y2: [..][Ho][Wo][2*Cout]
+  MAUV_CHECK_ARG(x2 && w3 && y2 && Cin % 64 == 0 && Cout % 8 == 0, "mauv_conv2d_im2col_x3_f16: bad argument");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_im2col_map(&tmA, x2, 2 * Cin, W, H, static_cast<int64_t>(G) * imgs_per_sample, kh, kw, stride, pad)) return rc;
+  const int K3 = kh * kw * 3 * Cin;
+  if (int rc = make_tiled_map(&tmB, w3, K3, Cout, G, static_cast<int64_t>(Cout) * K3, pick_bn(Cout))) return rc;
+  GemmParams p{};
+  p.stack = 1;
+  p.M = imgs_per_sample * Ho * Wo;
+  p.N = Cout;
+  p.k_blocks = K3 / BK;
+  p.G = G;
+  p.a_mode = 1;
+  p.a_batch_mul = 1;
+  p.Wo = Wo; p.Ho = Ho; p.imgs_per_sample = imgs_per_sample;
+  p.stride = stride; p.pad = pad; p.kw = kw;
+  p.c_blocks = 3 * Cin / BK;
+  p.a_cwrap = 2 * Cin / BK;
+  p.split = 1;
+  p.y = static_cast<__half*>(y2);
+  p.stats = stats_partial;
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 

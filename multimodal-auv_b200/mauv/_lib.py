@@ -48,6 +48,13 @@ SIGNATURES = {
     "mauv_wgrad_finalize": (i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, u64, u32, u32, vp, vp, vp]),
     "mauv_sampled_linear_bwd_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, i32,
                                           vp, vp, vp, vp, vp, vp]),
+    "mauv_gemm_x3_f16": (i32, [vp, i64, vp, vp, vp, i32, i64, i32, i32, vp]),
+    "mauv_conv2d_im2col_x3_f16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mauv_sample_weights_x3_f16": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]),
+    "mauv_stem_im2col_x3_f16": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_bn_act_x3_f16": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp]),
+    "mauv_bn_relu_maxpool_x3_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_avgpool_x3_f16": (i32, [vp, i64, i32, i32, vp, vp]),
     "mauv_kl_chunk_elems": (i32, []),
     "mauv_kl_ws_bytes": (i64, []),
     "mauv_kl_fwd_bwd": (i32, [vp, vp, i32, i64, f32, f32, f32, vp, vp, vp]),

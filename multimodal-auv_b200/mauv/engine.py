@@ -64,7 +64,7 @@ class _Trunk:
 class MCEngine:
     """Execution plan for a (Bayesian) MultiModalModel or ResNet50Custom living on a CUDA device."""
 
-    def __init__(self, model: nn.Module, max_group: int = 8):
+    def __init__(self, model: nn.Module, max_group: int = 8, precision: str = "fp16"):
         _lib.require_device()
         if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
             model = model.module
@@ -88,6 +88,11 @@ class MCEngine:
             raise _lib.MauvError("MCEngine: move the model to a CUDA device first (there is no CPU path)")
         self.device = p.device
         self.launches = 0
+        # "fp16": production path (fp16 operands, fp32 accumulate). "x3": validation path - every value is an fp16
+        # (hi | lo) pair and every product a 3-term split on the same tensor-core kernel (~fp32 accuracy, ~3x cost)
+        if precision not in ("fp16", "x3"):
+            raise _lib.MauvError("precision must be 'fp16' or 'x3'")
+        self.precision = precision
         # recompute-fusion of conv3 + bn3 + residual + ReLU (removes the y3 write and re-read) for bottlenecks whose
         # conv3 has K <= fuse_conv3_max_k (layer1/layer2: HBM-write bound; deeper ones are tensor bound)
         self.fuse_conv3 = True
@@ -160,8 +165,54 @@ class MCEngine:
         count = y.numel() // (G * c.cout)
         return y, self._bn(st, count, bn, G)
 
+    # ------------------------------------------------------------------ trunk, fp16x3 validation mode
+    def _bn_x3(self, stats, count, bn: nn.BatchNorm2d, G):
+        # the conv output carries the 2^8 weight scale: BN(256*y) with eps*2^16 == BN(y) with eps (gamma/beta unchanged);
+        # running statistics are not replayed in this mode (they do not influence train-mode outputs)
+        return ops.bn_finalize(stats, count, bn.weight.detach() if bn.weight is not None else None,
+                               bn.bias.detach() if bn.bias is not None else None, bn.eps * ops.X3_SCALE ** 2, 0.0)
+
+    def _conv_bn_x3(self, c: _Conv, bn, x2, G, B, s0, eps, seed):
+        plain = c.k == 1 and c.stride == 1 and c.pad == 0
+        w3 = ops.sample_weights_x3_f16(c.layer.mu_kernel.detach(), c.layer.rho_kernel.detach(), G, per_tap=not plain,
+                                       eps=self._eps_w(eps, c.name, s0, G), seed=seed, layer_id=c.layer_id, sample0=s0)
+        NB, H, W, C2 = x2.shape
+        if plain:
+            y2, st = ops.gemm_x3_f16(x2.view(G, B * H * W, C2), w3)
+            y2 = y2.view(NB, H, W, 2 * c.cout)
+        else:
+            y2, st = ops.conv2d_im2col_x3_f16(x2, w3, G, c.k, c.k, c.stride, c.pad)
+        count = y2.numel() // (G * 2 * c.cout)
+        return y2, self._bn_x3(st, count, bn, G)
+
+    def _run_trunk_x3(self, t: _Trunk, x_nchw: torch.Tensor, G: int, s0: int, eps, seed) -> torch.Tensor:
+        B = x_nchw.shape[0]
+        st = t.stem
+        a0 = ops.stem_im2col_x3_f16(x_nchw, st.k, st.k, st.stride, st.pad)
+        w3 = ops.sample_weights_x3_f16(st.layer.mu_kernel.detach(), st.layer.rho_kernel.detach(), G, per_tap=False,
+                                       eps=self._eps_w(eps, st.name, s0, G), seed=seed, layer_id=st.layer_id, sample0=s0)
+        y2, stats = ops.gemm_x3_f16(a0, w3, shared_a=True)
+        Ho = (x_nchw.shape[2] + 2 * st.pad - st.k) // st.stride + 1
+        Wo = (x_nchw.shape[3] + 2 * st.pad - st.k) // st.stride + 1
+        ss = self._bn_x3(stats, B * Ho * Wo, t.stem_bn, G)
+        x = ops.bn_relu_maxpool_x3_f16(y2.view(G * B, Ho, Wo, 2 * st.cout), ss, G)
+        for blk in t.blocks:
+            y1, ss1 = self._conv_bn_x3(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
+            a1 = ops.bn_act_x3_f16(y1, ss1, G, blk.conv1.cout)
+            y2, ss2 = self._conv_bn_x3(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
+            a2 = ops.bn_act_x3_f16(y2, ss2, G, blk.conv2.cout)
+            y3, ss3 = self._conv_bn_x3(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
+            if blk.down is not None:
+                yd, ssd = self._conv_bn_x3(blk.down, blk.down_bn, x, G, B, s0, eps, seed)
+                x = ops.bn_act_x3_f16(y3, ss3, G, blk.conv3.cout, y2b=yd, ss2=ssd)
+            else:
+                x = ops.bn_act_x3_f16(y3, ss3, G, blk.conv3.cout, residual=x)
+        return ops.avgpool_x3_f16(x).view(G, B, -1)
+
     # ------------------------------------------------------------------ trunk
     def _run_trunk(self, t: _Trunk, x_nchw: torch.Tensor, G: int, s0: int, eps, seed, a0=None) -> torch.Tensor:
+        if self.precision == "x3":
+            return self._run_trunk_x3(t, x_nchw, G, s0, eps, seed)
         B = x_nchw.shape[0]
         st = t.stem
         if a0 is None:

@@ -309,6 +309,90 @@ def softmax_gate_f32(score: torch.Tensor, v: torch.Tensor, out: torch.Tensor, ou
     return out
 
 
+# ------------------------------------------------------------------ fp16x3 validation mode ((hi | lo) pairs)
+X3_SCALE = 256.0   # weights are scaled by 2^8 so that their lo parts stay clear of fp16 subnormals; BN absorbs it
+
+
+def sample_weights_x3_f16(mu, rho, G, *, per_tap: bool, eps=None, seed=0, layer_id=0, sample0=0) -> torch.Tensor:
+    lib = _lib.require_device()
+    if mu.dim() == 2:
+        cout, cin = mu.shape
+        kh = kw = 1
+    else:
+        cout, cin, kh, kw = mu.shape
+    kp = round_up(cin * kh * kw, 64)
+    row = kh * kw * 3 * cin if per_tap else 3 * kp
+    out = torch.empty((G, cout, row), dtype=F16, device=mu.device)
+    _run("mauv_sample_weights_x3_f16", lib.mauv_sample_weights_x3_f16, _ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed,
+         layer_id, sample0, G, cout, cin, kh, kw, kp, int(per_tap), X3_SCALE, _ptr(out), _stream())
+    return out
+
+
+def stem_im2col_x3_f16(x_nchw: torch.Tensor, kh, kw, stride, pad) -> torch.Tensor:
+    lib = _lib.require_device()
+    B, C, H, W = x_nchw.shape
+    kp = round_up(kh * kw * C, 64)
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    out = torch.empty((B * Ho * Wo, 2 * kp), dtype=F16, device=x_nchw.device)
+    _run("mauv_stem_im2col_x3_f16", lib.mauv_stem_im2col_x3_f16, _ptr(x_nchw, F32), B, C, H, W, kh, kw, stride, pad, kp,
+         _ptr(out), _stream())
+    return out
+
+
+def gemm_x3_f16(a2: torch.Tensor, w3: torch.Tensor, *, shared_a: bool = False):
+    """a2 [G, M, 2K] (or [M, 2K] shared), w3 [G, N, 3K] -> y2 [G, M, 2N] (hi | lo), stats [G, m_tiles, N, 2]."""
+    lib = _lib.require_device()
+    G, N, K3 = w3.shape
+    K = K3 // 3
+    M = a2.shape[-2]
+    assert a2.shape[-1] == 2 * K
+    y2 = torch.empty((G, M, 2 * N), dtype=F16, device=a2.device)
+    st = torch.empty((G, gemm_m_tiles(M), N, 2), dtype=F32, device=a2.device)
+    _run("mauv_gemm_x3_f16", lib.mauv_gemm_x3_f16, _ptr(a2, F16), 0 if shared_a else M * 2 * K, _ptr(w3, F16), _ptr(y2),
+         _ptr(st), G, M, N, K, _stream())
+    return y2, st
+
+
+def conv2d_im2col_x3_f16(x2: torch.Tensor, w3: torch.Tensor, G: int, kh, kw, stride, pad):
+    """x2 [G*B, H, W, 2Cin], w3 [G, Cout, kh*kw*3*Cin] -> y2 [G*B, Ho, Wo, 2Cout], stats."""
+    lib = _lib.require_device()
+    NB, H, W, C2 = x2.shape
+    Cin, B, Cout = C2 // 2, NB // G, w3.shape[1]
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y2 = torch.empty((NB, Ho, Wo, 2 * Cout), dtype=F16, device=x2.device)
+    st = torch.empty((G, gemm_m_tiles(B * Ho * Wo), Cout, 2), dtype=F32, device=x2.device)
+    _run("mauv_conv2d_im2col_x3_f16", lib.mauv_conv2d_im2col_x3_f16, _ptr(x2, F16), _ptr(w3, F16), _ptr(y2), _ptr(st), G, B,
+         H, W, Cin, Cout, kh, kw, stride, pad, _stream())
+    return y2, st
+
+
+def bn_act_x3_f16(y2, ss, G, C, *, residual=None, y2b=None, ss2=None, relu=True) -> torch.Tensor:
+    lib = _lib.require_device()
+    M = y2.numel() // (G * 2 * C)
+    out = torch.empty_like(y2)
+    _run("mauv_bn_act_x3_f16", lib.mauv_bn_act_x3_f16, _ptr(y2, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2b, F16),
+         _ptr(ss2, F32), int(relu), G, M, C, _ptr(out), _stream())
+    return out
+
+
+def bn_relu_maxpool_x3_f16(y2, ss, G) -> torch.Tensor:
+    lib = _lib.require_device()
+    NB, H, W, C2 = y2.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = torch.empty((NB, Ho, Wo, C2), dtype=F16, device=y2.device)
+    _run("mauv_bn_relu_maxpool_x3_f16", lib.mauv_bn_relu_maxpool_x3_f16, _ptr(y2, F16), _ptr(ss, F32), G, NB // G, H, W, C2 // 2,
+         _ptr(out), _stream())
+    return out
+
+
+def avgpool_x3_f16(x2) -> torch.Tensor:
+    lib = _lib.require_device()
+    N, H, W, C2 = x2.shape
+    out = torch.empty((N, C2 // 2), dtype=F32, device=x2.device)
+    _run("mauv_avgpool_x3_f16", lib.mauv_avgpool_x3_f16, _ptr(x2, F16), N, H * W, C2 // 2, _ptr(out), _stream())
+    return out
+
+
 # ------------------------------------------------------------------ backward helpers
 def sample_weights_dgrad_f16(mu, rho, G, *, eps=None, seed=0, layer_id=0, sample0=0) -> torch.Tensor:
     """-> [G, cin, kh*kw*cout] fp16: transposed + tap-flipped sample for the data-gradient conv."""

@@ -386,6 +386,67 @@ def t_engine(B=2, S=2, size=64, kind="multimodal"):
     return got, ref
 
 
+def _split(t):
+    hi = t.half()
+    lo = (t - hi.float()).half()
+    return hi, lo
+
+
+def t_gemm_x3(G, M, N, K):
+    """fp16x3 contraction (K-concatenated hi/lo operands through the same tcgen05 kernel) vs an fp64 reference."""
+    torch.manual_seed(13)
+    a = torch.randn(G, M, K, device=dev) * 0.5
+    w = torch.randn(G, N, K, device=dev) * 0.1
+    ah, al = _split(a)
+    wh, wl = _split(w)
+    y2, st = ops.gemm_x3_f16(torch.cat([ah, al], -1).contiguous(), torch.cat([wh, wh, wl], -1).contiguous())
+    torch.cuda.synchronize()
+    got = y2[..., :N].float() + y2[..., N:].float()
+    ref = torch.einsum("gmk,gnk->gmn", a.double(), w.double())
+    report(f"gemm_x3 G={G} M={M} N={N} K={K} vs fp64", got, ref.float(), 2e-6)
+    report("   stats sum", st[..., 0].sum(1), ref.sum(1).float(), 1e-5)
+
+
+def t_conv_x3(G, B, H, W, Cin, Cout, k, stride, pad):
+    torch.manual_seed(14)
+    x = torch.randn(G * B, H, W, Cin, device=dev) * 0.5
+    w = torch.randn(G, Cout, k, k, Cin, device=dev) * 0.1
+    xh, xl = _split(x)
+    wh, wl = _split(w)
+    w3 = torch.cat([wh, wh, wl], -1).reshape(G, Cout, -1).contiguous()
+    y2, st = ops.conv2d_im2col_x3_f16(torch.cat([xh, xl], -1).contiguous(), w3, G, k, k, stride, pad)
+    torch.cuda.synchronize()
+    got = y2[..., :Cout].float() + y2[..., Cout:].float()
+    refs = []
+    for g in range(G):
+        refs.append(F.conv2d(x[g * B:(g + 1) * B].double().permute(0, 3, 1, 2), w[g].double().permute(0, 3, 1, 2), None,
+                             stride, pad).permute(0, 2, 3, 1))
+    report(f"conv_x3 G={G} B={B} {H}x{W} {Cin}->{Cout} k={k} s={stride} vs fp64", got, torch.cat(refs).float(), 2e-6)
+
+
+def t_engine_x3(B=2, S=2, size=64, kind="unimodal"):
+    """Validation mode end to end: logits within rtol 1e-3 (of the largest |logit|) of the fp32 oracle, argmax exact."""
+    import bnn_oracle as O
+    from mauv.engine import MCEngine
+    o_model, model = build_pair(kind)
+    img, bathy, sss, _ = O.synthetic_batch(B, size=size)
+    inputs = (img, bathy, sss) if kind == "multimodal" else (img,)
+    eps = O.draw_eps(o_model, S, seed=77)
+    ref = O.mc_logits(o_model, inputs, S, eps)
+    eng = MCEngine(model, precision="x3")
+    got = eng.forward_mc([t.to(dev) for t in inputs], S, eps=eps)
+    torch.cuda.synchronize()
+    err = (got.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    ok = err <= 1e-3 * scale
+    print(f"engine x3 {kind} B={B} S={S} size={size}: max_abs_err={err:.3e} |logit|max={scale:.3f} rel={err / scale:.2e} "
+          f"(north_star rtol 1e-3)  {'[OK]' if ok else '[FAIL]'}", flush=True)
+    same = bool((got.mean(0).argmax(1).cpu() == ref.mean(0).argmax(1)).all())
+    print("   argmax(mean logits) bit-exact:", same, flush=True)
+    if not ok or not same:
+        FAILS.append((f"engine x3 {kind}", f"err {err} scale {scale} argmax {same}"))
+
+
 def t_train(S=2, B=2, size=64):
     """Diagnostics: per-parameter gradient agreement of one ELBO step (drop-in layers vs oracle autograd)."""
     import bnn_oracle as O
@@ -451,6 +512,11 @@ GROUPS = {
         (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
         (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),
         (1, 2, 4, 4, 512, 512, 3, 1, 1), (3, 1, 6, 6, 128, 64, 3, 2, 1)]],
+    "x3": lambda: [run_case(t_gemm_x3, 2, 300, 256, 128), run_case(t_gemm_x3, 1, 1000, 64, 192),
+                   run_case(t_conv_x3, 2, 2, 16, 16, 64, 128, 3, 1, 1), run_case(t_conv_x3, 1, 2, 16, 16, 128, 256, 1, 2, 0),
+                   run_case(t_conv_x3, 1, 2, 8, 8, 64, 64, 3, 2, 1),
+                   run_case(t_engine_x3, 2, 2, 64, "unimodal"), run_case(t_engine_x3, 2, 2, 256, "unimodal"),
+                   run_case(t_engine_x3, 2, 2, 64, "multimodal")],
     "train": lambda: [run_case(t_train, 1), run_case(t_train, 2)],
     "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal"),
                        run_case(t_engine, 2, 2, 256, "unimodal")],
