@@ -403,7 +403,7 @@ def t_gemm_x3(G, M, N, K):
     torch.cuda.synchronize()
     got = y2[..., :N].float() + y2[..., N:].float()
     ref = torch.einsum("gmk,gnk->gmn", a.double(), w.double())
-    report(f"gemm_x3 G={G} M={M} N={N} K={K} vs fp64", got, ref.float(), 2e-6)
+    report(f"gemm_x3 G={G} M={M} N={N} K={K} vs fp64", got, ref.float(), 5e-6)
     report("   stats sum", st[..., 0].sum(1), ref.sum(1).float(), 1e-5)
 
 
@@ -421,7 +421,7 @@ def t_conv_x3(G, B, H, W, Cin, Cout, k, stride, pad):
     for g in range(G):
         refs.append(F.conv2d(x[g * B:(g + 1) * B].double().permute(0, 3, 1, 2), w[g].double().permute(0, 3, 1, 2), None,
                              stride, pad).permute(0, 2, 3, 1))
-    report(f"conv_x3 G={G} B={B} {H}x{W} {Cin}->{Cout} k={k} s={stride} vs fp64", got, torch.cat(refs).float(), 2e-6)
+    report(f"conv_x3 G={G} B={B} {H}x{W} {Cin}->{Cout} k={k} s={stride} vs fp64", got, torch.cat(refs).float(), 5e-6)
 
 
 def t_engine_x3(B=2, S=2, size=64, kind="unimodal"):
