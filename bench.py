@@ -286,6 +286,48 @@ def run_ours(args):
     return 0
 
 
+def run_train(args):
+    """cfg3-style ELBO training step through the drop-in layers (secondary workload, not the headline metric):
+    S stochastic passes of the multimodal BNN, CE(mean logits) + KL/B * 2^(e+1)/2^E, backward, Adam - the body of
+    reference train/multimodal.py:104-145 with every Bayesian layer's forward/backward on the CUDA kernels."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    from mauv import ops
+    from mauv.bayesian import get_kl_loss
+    B, S = args.batch if args.batch != B_FULL else 8, args.samples if args.samples != S_FULL else 5
+    model = build_model_cpu().cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-5)
+    xs = [x.cuda() for x in synthetic_inputs(B)]
+    labels = torch.randint(0, C_CLASSES, (B,), device="cuda")
+    kl_w = 2.0 / 2 ** 20
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        out = torch.mean(torch.stack([model(*xs) for _ in range(S)]), dim=0)
+        loss = torch.nn.functional.cross_entropy(out, labels) + get_kl_loss(model) / B * kl_w
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": "ELBO training triplets/sec (drop-in layer path)", "value": B / (ms / 1e3), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients",
+                      "config": {"workload": f"cfg3-style multimodal ELBO step B={B} S={S} 256x256 C=7, Adam"},
+                      "gpu_launches": (ops.launch_count - l0), "loss": float(loss)}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,9 +339,13 @@ def main():
     ap.add_argument("--group", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-shape kernel table on stderr")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference = BASELINE cfg2 (headline); train = cfg3-style ELBO step (secondary)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.workload == "train" and args.impl == "ours":
+        return run_train(args)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
