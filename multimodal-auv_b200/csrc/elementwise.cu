@@ -320,14 +320,6 @@ nhwc_to_nchw_f32_kernel(const __half* __restrict__ x, int C, int HW, long long t
   out[i] = __half2float(x[(n * HW + hw) * C + c]);
 }
 
-inline unsigned grid_for(long long work, int block, int waves = 8) {
-  long long blocks = ceil_div_i64(work, block);
-  const long long cap = static_cast<long long>(mauv_num_sms()) * waves;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return static_cast<unsigned>(blocks);
-}
-
 }  // namespace
 
 extern "C" {

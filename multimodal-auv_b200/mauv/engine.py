@@ -24,6 +24,12 @@ from .bayesian import bayesian_layers, current_seed
 
 F16, F32 = torch.float16, torch.float32
 
+# Test hooks (validation only): engines built by the drivers pick these up. DEFAULT_PRECISION selects the production
+# ("fp16") or validation ("x3") arithmetic; DEBUG_EPS, when set to {layer name: {"w": [S, ...], "b": [S, out] | None}},
+# replaces the in-kernel Philox eps so that a driver run can be compared with the oracle on identical noise.
+DEFAULT_PRECISION = "fp16"
+DEBUG_EPS = None
+
 
 def _one(v):
     return v[0] if isinstance(v, (tuple, list)) else v
@@ -64,7 +70,7 @@ class _Trunk:
 class MCEngine:
     """Execution plan for a (Bayesian) MultiModalModel or ResNet50Custom living on a CUDA device."""
 
-    def __init__(self, model: nn.Module, max_group: int = 8, precision: str = "fp16"):
+    def __init__(self, model: nn.Module, max_group: int = 8, precision: Optional[str] = None):
         _lib.require_device()
         if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
             model = model.module
@@ -90,6 +96,7 @@ class MCEngine:
         self.launches = 0
         # "fp16": production path (fp16 operands, fp32 accumulate). "x3": validation path - every value is an fp16
         # (hi | lo) pair and every product a 3-term split on the same tensor-core kernel (~fp32 accuracy, ~3x cost)
+        precision = precision or DEFAULT_PRECISION
         if precision not in ("fp16", "x3"):
             raise _lib.MauvError("precision must be 'fp16' or 'x3'")
         self.precision = precision
@@ -307,8 +314,10 @@ class MCEngine:
                    seed: Optional[int] = None, group: Optional[int] = None) -> torch.Tensor:
         """logits [S, B, C] for MC samples sample0 .. sample0+S-1 (eps indexed from 0 when injected)."""
         G = min(group or self.max_group, S)
+        if eps is None:
+            eps = DEBUG_EPS
         outs = []
-        stems = self.stem_matrices(inputs) if S > G else None
+        stems = self.stem_matrices(inputs) if (S > G and self.precision == "fp16") else None
         for s in range(0, S, G):
             g = min(G, S - s)
             outs.append(self.forward_group(inputs, g, sample0 + s, eps, seed, stems))

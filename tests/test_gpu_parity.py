@@ -462,3 +462,113 @@ def test_train_step_full_multimodal_head_gradients(bu):
         assert cos > 0.98, (name, cos.item())
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
     assert all(p.grad is not None for n, p in model.named_parameters())
+
+
+# ------------------------------------------------------------------ reference-facing drivers
+def _golden_models(kind):
+    """Oracle + product model carrying the weights of the reference-built golden models."""
+    import bnn_oracle as O
+    from mauv.bayesian import dnn_to_bnn
+    import mauv.models.base_models as MB
+    gold = torch.load(GOLD, weights_only=False)
+    torch.manual_seed(gold["seed_w"])
+    o_models = O.define_models(gold["C"], seed=None, unimodal=True)
+    if kind == "multimodal":
+        o = o_models["multimodal_model"]
+        m = MB.MultiModalModel(O.feature_extractor(), O.feature_extractor(), O.feature_extractor(1), gold["C"])
+    else:
+        o = o_models["image_model"]
+        m = O.ResNet50Custom(3, gold["C"])
+    dnn_to_bnn(m, O.DEFAULT_PRIOR)
+    m.load_state_dict(o.state_dict(), strict=True)
+    return gold, o, m.cuda().train()
+
+
+class _Loader(list):
+    batch_size = None
+
+
+def test_evaluate_multimodal_model_reproduces_reference_csv(bu, tmp_path):
+    """mauv.train.multimodal.evaluate_multimodal_model (product driver, S-batched engine + K5 + K4) against the CSV row
+    the REFERENCE's evaluate_multimodal_model wrote for the same weights / inputs / eps (tests/golden)."""
+    if not GOLD.exists():
+        pytest.skip("golden fixture missing")
+    import bnn_oracle as O
+    import mauv.engine as E
+    from mauv.train.multimodal import evaluate_multimodal_model
+    gold, o, model = _golden_models("multimodal")
+    img, bathy, sss, labels = O.synthetic_batch(gold["B"], seed=gold["seed_x"], size=gold["size"])
+    loader = _Loader([{"main_image": img, "label": labels, "bathy_image": bathy, "sss_image": sss}])
+    loader.batch_size = gold["B"]
+    E.DEBUG_EPS = O.draw_eps(o, gold["S"], gold["seed_eps"])
+    try:
+        csv_path = tmp_path / "logs" / "eval.csv"
+        csv_path.parent.mkdir()
+        acc = evaluate_multimodal_model(model, loader, torch.device("cuda"), epoch=0, total_num_epochs=20,
+                                        num_mc=gold["S"], model_type="multimodal", csv_path=str(csv_path))
+    finally:
+        E.DEBUG_EPS = None
+    import csv as _csv
+    rows = list(_csv.reader(open(csv_path)))
+    assert rows[0] == gold["eval_mm_csv_header"]
+    got, ref = rows[1], gold["eval_mm_csv_row"]
+    assert got[0] == ref[0] and got[1] == ref[1] and got[8:] == ref[8:]
+    assert abs(acc - gold["eval_mm_accuracy"]) < 1e-9 and abs(float(got[3]) - float(ref[3])) < 1e-9
+    for i, tol in ((2, 2e-3), (4, 2e-4), (5, 1e-4), (6, 1e-6), (7, 2e-3)):     # loss, pred. unc., MI, scaled KL, CE
+        assert abs(float(got[i]) - float(ref[i])) < tol * max(1.0, abs(float(ref[i]))), (i, got[i], ref[i])
+
+
+def test_evaluate_unimodal_model_reproduces_reference_csv_in_validation_mode(bu, tmp_path):
+    """Unimodal driver vs the reference's CSV row; the 53-layer image branch at B=2 / 64x64 is the ill-conditioned case,
+    so the engine runs in the fp16x3 validation mode here."""
+    if not GOLD.exists():
+        pytest.skip("golden fixture missing")
+    import bnn_oracle as O
+    import mauv.engine as E
+    from mauv.train.unimodal import evaluate_unimodal_model
+    gold, o, model = _golden_models("image")
+    img, bathy, sss, labels = O.synthetic_batch(gold["B"], seed=gold["seed_x"], size=gold["size"])
+    loader = _Loader([{"main_image": img, "label": labels, "bathy_image": bathy, "sss_image": sss}])
+    loader.batch_size = gold["B"]
+    E.DEBUG_EPS = O.draw_eps(o, gold["S"], gold["seed_eps"] + 1)
+    E.DEFAULT_PRECISION = "x3"
+    try:
+        csv_path = tmp_path / "ueval.csv"
+        acc = evaluate_unimodal_model(model, loader, torch.device("cuda"), epoch=0, csv_path=str(csv_path),
+                                      total_num_epochs=20, num_mc=gold["S"], model_type="image")
+    finally:
+        E.DEBUG_EPS = None
+        E.DEFAULT_PRECISION = "fp16"
+    import csv as _csv
+    rows = list(_csv.reader(open(csv_path)))
+    assert rows[0] == gold["eval_uni_csv_header"]
+    got, ref = rows[1], gold["eval_uni_csv_row"]
+    assert got[:2] == ref[:2] and abs(acc - gold["eval_uni_accuracy"]) < 1e-9
+    for i, tol in ((2, 2e-3), (4, 5e-3), (5, 1e-3)):                           # loss, var-of-probs, mean entropy
+        assert abs(float(got[i]) - float(ref[i])) < tol * max(abs(float(ref[i])), 1e-3), (i, got[i], ref[i])
+
+
+def test_multimodal_predict_and_save_writes_reference_csv_format(bu, tmp_path):
+    """Product predictor through its public signature: header, one row per image, values == the device statistics."""
+    import bnn_oracle as O
+    from mauv.bayesian import manual_seed
+    from mauv.inference.predictors import MCPredictor, multimodal_predict_and_save
+    _, model = bu.build_pair("multimodal")
+    batches = []
+    for i in range(3):
+        img, bathy, sss, _ = O.synthetic_batch(2, seed=100 + i, size=64)
+        batches.append((img, bathy, sss, [f"im_{i}_0", f"im_{i}_1"]))
+    manual_seed(7)
+    p = tmp_path / "pred.csv"
+    multimodal_predict_and_save(model, batches, torch.device("cuda"), str(p), num_mc_samples=4)
+    import csv as _csv
+    rows = list(_csv.reader(open(p)))
+    assert rows[0] == ["Image Name", "Predicted Class", "Predictive Uncertainty", "Aleatoric Uncertainty"]
+    assert [r[0] for r in rows[1:]] == [n for b in batches for n in b[3]]
+    pred = MCPredictor(model, 4)
+    for bi, b in enumerate(batches):
+        o = pred.predict_device([t.cuda() for t in b[:3]])        # same Philox seed / sample ids -> same samples
+        for j in range(2):
+            r = rows[1 + 2 * bi + j]
+            assert int(r[1]) == int(o["argmax_prob"][j])
+            assert abs(float(r[2]) - float(o["var_mean"][j])) < 1e-9 and abs(float(r[3]) - float(o["aleatoric"][j])) < 1e-7
