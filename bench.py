@@ -208,7 +208,8 @@ def run_ours(args):
     ms_e2e = timed(run_e2e, 1)
     clocks = sampler.stop() if sampler else None
 
-    # per-kernel breakdown: one extra instrumented step (CUDA events around every C-ABI launch)
+    # per-kernel breakdown: one extra instrumented step, run eagerly (CUDA events around every C-ABI launch)
+    pred.use_graph = False
     ops.start_profile()
     step_dev()
     prof = ops.stop_profile()
