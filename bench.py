@@ -209,7 +209,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     # per-kernel breakdown: one extra instrumented step, run eagerly (CUDA events around every C-ABI launch)
-    pred.use_graph = False
+    pred.use_graph = False            # profile eagerly: the event pairs cannot be recorded inside a graph replay
     ops.start_profile()
     step_dev()
     prof = ops.stop_profile()

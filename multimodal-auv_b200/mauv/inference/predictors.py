@@ -47,12 +47,15 @@ class MCPredictor:
     """H2D -> S-batched MC forward -> MC statistics -> one D2H, for one batch."""
 
     def __init__(self, model: nn.Module, num_mc_samples: int, group: int = 8, eps_entropy: float = 1e-7,
-                 use_graph: bool = True):
+                 use_graph="auto"):
         self.engine = MCEngine(model, max_group=group)
         # CUDA graph of this rank's S-pass forward (all sample groups): one replay instead of ~2.4 k Python-driven
-        # launches per sample group (414 ms of CPU enqueue time per cfg2 step, which would bound small batches and
-        # the 8-GPU sample-sharded case). Keyed by input shapes / sample range / seed; inputs are copied into static
-        # buffers. Injected-eps (validation) calls always run eagerly.
+        # launches per sample group. Python enqueues ~57 us per launch (414 ms per cfg2 step), which is hidden behind
+        # the GPU at B=256 / G=10 (93 us of GPU work per launch) but bounds small batches (cfg1) and the 8-GPU
+        # sample-sharded case (G=4); a graph of thousands of nodes on the other hand costs ~60 ms of launch latency
+        # that is exposed when every batch ends with a D2H sync. "auto" picks the graph when the estimated GPU time per
+        # launch is below the Python enqueue cost. Keyed by input shapes / sample range / seed; inputs are copied
+        # into static buffers. Injected-eps (validation) calls always run eagerly.
         self.use_graph = use_graph
         self._graphs = {}
         self.S = int(num_mc_samples)
@@ -69,7 +72,7 @@ class MCPredictor:
         lo, hi = shard_samples(self.S, self.world, self.rank)
         if hi <= lo:
             local = None
-        elif self.use_graph and eps is None:
+        elif eps is None and self._want_graph(inputs[0].shape[0], hi - lo):
             local = self._forward_graphed(inputs, lo, hi, seed)
         else:
             local = self.engine.forward_mc(inputs, hi - lo, sample0=lo, eps=eps, seed=seed)
@@ -77,6 +80,12 @@ class MCPredictor:
             return local
         C = local.shape[-1] if local is not None else self._num_classes()
         return gather_sample_blocks(local, self.S, inputs[0].shape[0], C, self.world, self.device)
+
+    def _want_graph(self, B: int, S_local: int) -> bool:
+        if self.use_graph == "auto":
+            G = min(self.engine.max_group, S_local)
+            return 0.036 * G * B < 60.0          # measured: 93 us GPU time per launch at G=10, B=256; 57 us to enqueue
+        return bool(self.use_graph)
 
     def _forward_graphed(self, inputs, lo, hi, seed):
         from .. import engine as _engine
