@@ -44,6 +44,21 @@ def gemm(G, M, N, K, iters=5, shared=False, quiet=False):
     return ms
 
 
+def gemm_bn(G, M, N, K, iters=5):
+    """conv3 recompute scheme: statistics pass + fused BN/residual/ReLU pass."""
+    a = torch.randn(G, M, K, device=dev, dtype=torch.float16)
+    w = torch.randn(G, N, K, device=dev, dtype=torch.float16)
+    r = torch.randn(G, M, N, device=dev, dtype=torch.float16)
+    ss = torch.rand(G, N, 2, device=dev)
+    out = torch.empty(G, M, N, device=dev, dtype=torch.float16)
+    st = torch.empty(G, (M + 255) // 256, N, 2, device=dev)
+    ms = timeit(lambda: ops.gemm_stats_f16(a, w, stats_out=st), iters)
+    print(f"gemm_bn stats pass G={G} M={M} N={N} K={K}: {ms:.3f} ms  {a.numel() * 2 / ms / 1e9:.2f} TB/s (reads A only)", flush=True)
+    ms = timeit(lambda: ops.gemm_bn_act_f16(a, w, ss, residual=r, relu=True, out=out), iters)
+    by = (a.numel() + 2 * out.numel()) * 2
+    print(f"gemm_bn fused pass G={G} M={M} N={N} K={K}: {ms:.3f} ms  {by / ms / 1e9:.2f} TB/s (A + residual + out)", flush=True)
+
+
 def conv(G, B, H, W, Cin, Cout, k, stride, pad, iters=5):
     x = torch.randn(G * B, H, W, Cin, device=dev, dtype=torch.float16)
     w = torch.randn(G, Cout, k * k * Cin, device=dev, dtype=torch.float16)
@@ -128,4 +143,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm}[cmd](*a)
