@@ -25,24 +25,30 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int MAXC>
+// CC > 0: class count known at compile time (fully unrolled, no predicates; CC = 7 is the reference's habitat
+// count); CC == 0: generic path for any C <= MAXC.
+template <int MAXC, int CC>
 __global__ void __launch_bounds__(MC_ROWS)
-mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, float eps_entropy, int vec_ok,
+mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, float eps_entropy, int vec_ok,
                  float* __restrict__ mean_prob, float* __restrict__ mean_logit,
                  long long* __restrict__ argmax_prob, long long* __restrict__ argmax_logit,
                  float* __restrict__ pred_entropy, float* __restrict__ aleatoric,
                  float* __restrict__ mutual_info, float* __restrict__ var_mean) {
   extern __shared__ __align__(16) float mc_smem[];   // [MC_STAGES][MC_ROWS * C]
+  const int C = CC > 0 ? CC : Crt;
+  constexpr int NC = CC > 0 ? CC : MAXC;             // unrolled trip count
   const int tid = threadIdx.x;
   const long long b0 = static_cast<long long>(blockIdx.x) * MC_ROWS;
   const int rows = static_cast<int>(B - b0 < MC_ROWS ? B - b0 : MC_ROWS);
   const int nf = rows * C;                 // floats of this block's slab per sample
   const int slab = MC_ROWS * C;
   const uint32_t smem0 = smem_u32(mc_smem);
+  const float* src0 = logits + b0 * C;
+  const long long sample_stride = B * C;
 
   auto issue = [&](int s) {
     if (s < S) {
-      const float* src = logits + (static_cast<long long>(s) * B + b0) * C;
+      const float* src = src0 + s * sample_stride;
       const uint32_t dst = smem0 + static_cast<uint32_t>((s % MC_STAGES) * slab) * 4u;
       if (vec_ok) {
         const int nv = nf >> 2;
@@ -58,41 +64,43 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, fl
   for (int s = 0; s < MC_STAGES - 1; ++s) issue(s);
 
   const bool active = tid < rows;
-  float sum_p[MAXC], sum_l[MAXC], wmean[MAXC], m2[MAXC];
+  // variance by shifted sums: d = p - p(sample 0) keeps sum(d^2) - sum(d)^2/S free of cancellation
+  float sum_p[NC], sum_l[NC], p0[NC], sd[NC], sdd[NC];
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) { sum_p[c] = 0.f; sum_l[c] = 0.f; wmean[c] = 0.f; m2[c] = 0.f; }
+  for (int c = 0; c < NC; ++c) { sum_p[c] = 0.f; sum_l[c] = 0.f; p0[c] = 0.f; sd[c] = 0.f; sdd[c] = 0.f; }
   float sum_h = 0.f;
+  const float* my_row = mc_smem + tid * C;
   for (int s = 0; s < S; ++s) {
     issue(s + MC_STAGES - 1);
     asm volatile("cp.async.wait_group %0;" ::"n"(MC_STAGES - 1) : "memory");
     __syncthreads();
     if (active) {
-      const float* row = mc_smem + (s % MC_STAGES) * slab + tid * C;
-      float x[MAXC];
+      const float* row = my_row + (s % MC_STAGES) * slab;
+      float x[NC];
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        x[c] = (c < C) ? row[c] : -INFINITY;
+      for (int c = 0; c < NC; ++c) {
+        x[c] = (CC > 0 || c < C) ? row[c] : -INFINITY;
         mx = fmaxf(mx, x[c]);
       }
       float z = 0.f;
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < C) { sum_l[c] += x[c]; x[c] = __expf(x[c] - mx); } else { x[c] = 0.f; }
+      for (int c = 0; c < NC; ++c) {
+        if (CC > 0 || c < C) { sum_l[c] += x[c]; x[c] = __expf(x[c] - mx); } else { x[c] = 0.f; }
         z += x[c];
       }
-      const float inv_n = 1.f / static_cast<float>(s + 1);
       const float inv_z = __fdividef(1.f, z);
       float h = 0.f;
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
+      for (int c = 0; c < NC; ++c) {
+        if (CC > 0 || c < C) {
           const float pc = x[c] * inv_z;
+          if (s == 0) p0[c] = pc;
           sum_p[c] += pc;
-          const float d = pc - wmean[c];
-          wmean[c] += d * inv_n;
-          m2[c] = fmaf(d, pc - wmean[c], m2[c]);
-          h -= pc * __logf(pc + eps_entropy);
+          const float d = pc - p0[c];
+          sd[c] += d;
+          sdd[c] = fmaf(d, d, sdd[c]);
+          h = fmaf(-pc, __logf(pc + eps_entropy), h);
         }
       }
       sum_h += h;
@@ -109,14 +117,14 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int C, fl
   float* st_p = mc_smem;            // stage mean_prob / mean_logit for coalesced stores
   float* st_l = mc_smem + slab;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    if (c < C && active) {
+  for (int c = 0; c < NC; ++c) {
+    if ((CC > 0 || c < C) && active) {
       const float mp = sum_p[c] * inv_s;
       const float ml = sum_l[c] * inv_s;
       st_p[tid * C + c] = mp;
       st_l[tid * C + c] = ml;
-      hp -= mp * __logf(mp + eps_entropy);
-      vsum += m2[c] * inv_sm1;
+      hp = fmaf(-mp, __logf(mp + eps_entropy), hp);
+      vsum += fmaxf(sdd[c] - sd[c] * sd[c] * inv_s, 0.f) * inv_sm1;
       if (mp > best_p) { best_p = mp; arg_p = c; }   // first maximum wins, as torch.argmax
       if (ml > best_l) { best_l = ml; arg_l = c; }
     }
@@ -195,8 +203,9 @@ kl_kernel(const KlTensor* __restrict__ table, const long long* __restrict__ chun
         // sigma = log1p(exp(rho)); hardware ex2/lg2 are accurate to ~1e-6 relative here, far inside the 1e-4 KL
         // tolerance; for tiny exp(rho) (MOPED gives rho down to -46) use the series so sigma never flushes to 0.
         const float ex = __expf(rho[rep][i]);
-        const float sigma = ex < 1e-3f ? ex * (1.f - 0.5f * ex + 0.33333333f * ex * ex) : __logf(1.f + ex);
-        const float log_sigma = ex < 1e-3f ? rho[rep][i] + __logf(1.f - 0.5f * ex + 0.33333333f * ex * ex) : __logf(sigma);
+        const bool tiny = ex < 1e-3f;   // log1p series; log(sigma) = rho + log(1 - ex/2 + ex^2/3) = rho - ex/2 + 5/24 ex^2 + O(ex^3)
+        const float sigma = tiny ? ex * fmaf(ex, fmaf(ex, 0.33333333f, -0.5f), 1.f) : __logf(1.f + ex);
+        const float log_sigma = tiny ? fmaf(ex, fmaf(ex, 0.20833333f, -0.5f), rho[rep][i]) : __logf(sigma);
         const float d = mu[rep][i] - prior_mu;
         if (e0 + i < t.n) local += log_sp - log_sigma + (sigma * sigma + d * d) * inv_2sp2 - 0.5f;
         if (WITH_GRAD) {
@@ -257,14 +266,14 @@ int mauv_mc_reduce(const void* logits, int S, long long B, int C, int dtype, flo
   const float* lg = static_cast<const float*>(logits);
   const int vec_ok = ((B * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(lg) & 15) == 0);
   const size_t smem = static_cast<size_t>(MC_STAGES) * MC_ROWS * C * sizeof(float);
-#define MAUV_MC(MAXC)                                                                                   \
-  if (smem > 48 * 1024)                                                                                 \
-    MAUV_CUDA(cudaFuncSetAttribute(mc_reduce_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                   static_cast<int>(smem)));                                            \
-  mc_reduce_kernel<MAXC><<<grid, MC_ROWS, smem, st>>>(lg, S, B, C, eps_entropy, vec_ok, mean_prob, mean_logit, \
-                                                      argmax_prob, argmax_logit, pred_entropy, aleatoric,     \
-                                                      mutual_info, var_mean)
-  if (C <= 8) { MAUV_MC(8); } else if (C <= 16) { MAUV_MC(16); } else { MAUV_MC(32); }
+#define MAUV_MC(MAXC, CC)                                                                                   \
+  if (smem > 48 * 1024)                                                                                     \
+    MAUV_CUDA(cudaFuncSetAttribute(mc_reduce_kernel<MAXC, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   static_cast<int>(smem)));                                                \
+  mc_reduce_kernel<MAXC, CC><<<grid, MC_ROWS, smem, st>>>(lg, S, B, C, eps_entropy, vec_ok, mean_prob, mean_logit, \
+                                                          argmax_prob, argmax_logit, pred_entropy, aleatoric,     \
+                                                          mutual_info, var_mean)
+  if (C == 7) { MAUV_MC(8, 7); } else if (C <= 8) { MAUV_MC(8, 0); } else if (C <= 16) { MAUV_MC(16, 0); } else { MAUV_MC(32, 0); }
 #undef MAUV_MC
   MAUV_LAUNCH_CHECK("mc_reduce_kernel");
   return MAUV_OK;
