@@ -310,7 +310,7 @@ def run_train(args):
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, S = args.batch if args.batch != B_FULL else 8, args.samples if args.samples != S_FULL else 5
     model = build_model_cpu().cuda().train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False) if world > 1 else model
     opt = torch.optim.Adam(model.parameters(), lr=5e-5)
     xs = [x.cuda() for x in synthetic_inputs(B)]
     labels = torch.randint(0, C_CLASSES, (B,), device="cuda")
