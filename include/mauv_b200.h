@@ -196,6 +196,58 @@ int mauv_bn_relu_maxpool_x3_f16(const void* y2, const float* scale_shift, int G,
                                 void* out2, void* stream);
 int mauv_avgpool_x3_f16(const void* x2, long long N, int HW, int C, float* out, void* stream);
 
+/* ---- S-batched ELBO backward (a5/a6: train/multimodal.py:104-145, train/unimodal.py:125-146) ---------
+ * The G Monte-Carlo passes of one training step are walked backwards together. Gradient tensors are fp16 NHWC with a
+ * device-resident power-of-two scale each (value = true gradient * *scale): every BatchNorm site renormalises the scale
+ * from the amax it measures, no host round trip. "Upstream" of a site = d1 (scale *s1) + optional d2 (scale *s2, e.g. the
+ * identity branch of the residual), masked by relu_out > 0 when relu_out is given. C: power of two in [64, 2048]. */
+/* number of row blocks pass 1 uses for M rows per sample (sizes `partial`: [G][blocks][3][C] floats) */
+int mauv_bn_bwd_blocks(long long M);
+/* pass 1: partial[g][blk][0..2][c] = sum dz, sum dz*y, sum dz*y2 (y2 nullable); *amax = max|dz| as float bits. */
+int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
+                       const void* y2, int G, long long M, int C, float* partial, unsigned int* amax, void* stream);
+/* pass 2: per-(sample, channel) coefficients of dy = k0*dz + k1*y + k2 for train-mode BN (batch_stats = (mean, biased var)
+ * [G][C][2] from mauv_bn_finalize); which = 1 (y) or 2 (y2); grad_gamma/grad_beta (nullable) += sum over the G samples,
+ * unscaled by *s_in; coef [G][C][4]; *kmax = max|k0| as float bits. */
+int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int which, const float* batch_stats,
+                       const float* gamma, float eps, const float* s_in, float* grad_gamma, float* grad_beta, float* coef,
+                       unsigned int* kmax, void* stream);
+/* pass 3: dy = r*(k0*dz + k1*y + k2), r = power of two bringing the bound 4*amax*kmax to `target`; *s_out = *s1 * r.
+ * Optional second BN on the same dz (y2/coef2/kmax2 -> dy2, s_out2: the downsample branch) and optional dz output
+ * (fp16 at scale *s1: the identity branch). */
+int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
+                      const void* y2, const float* coef, const float* coef2, const unsigned int* amax,
+                      const unsigned int* kmax, const unsigned int* kmax2, float target, int G, long long M, int C, void* dy,
+                      void* dy2, void* dz, float* s_out, float* s_out2, void* stream);
+/* backward of maxpool3x3/2(relu(y*scale+shift)) (torchvision resnet.py stem): dz [G*imgs][H][W][C] at scale *s1. */
+int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1, const void* d2, const float* s1,
+                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* dz, void* stream);
+/* backward of the global average pool: dfeat [N][C] fp32 -> out [N][HW][C] fp16 = dfeat/HW * r, *s_out = r (first scale). */
+int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
+                         float* s_out, void* stream);
+/* dw_partial fp16 [G*splits][cout][k_pad] (value = dW_g * *scale / inv_alpha) -> grad_mu += sum_g dW_g,
+ * grad_rho += sum_g dW_g * eps_g * sigmoid(rho); eps injected [G][n] or Philox(seed, layer_id, sample0+g).
+ * stale_eps != 0 reproduces the reference's saved-eps-buffer behaviour (every pass sees the last pass's eps). */
+int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
+                              float inv_alpha, const float* scale, const float* rho, const float* eps, uint64_t seed,
+                              uint32_t layer_id, uint32_t sample0, int stale_eps, float* grad_mu, float* grad_rho,
+                              void* stream);
+/* fusion-head linear backward over G samples (fp32, sampling fused): gx[g] (nullable; = or +=) = gy[g] * W_g;
+ * parameter grads += sum over g. Strides in elements: *_sg per sample, *_sb per row. */
+int mauv_sampled_linear_bwd_group_f32(const float* x, long long x_sg, int x_sb, const float* gy, long long gy_sg, int gy_sb,
+                                      const float* mu_w, const float* rho_w, const float* eps_w, const float* rho_b,
+                                      const float* eps_b, uint64_t seed, uint32_t layer_id, uint32_t sample0, int G, int B,
+                                      int in_features, int out_features, int stale_eps, float* gx, long long gx_sg, int gx_sb,
+                                      int accumulate_gx, float* grad_mu_w, float* grad_rho_w, float* grad_mu_b,
+                                      float* grad_rho_b, void* stream);
+/* AdditiveAttention backward pieces (models/base_models.py:43-52): d(q+k) = dt*(1-t^2); out = v*softmax(score). */
+int mauv_tanh_bwd_f32(const float* t, const float* dt, long long n, float* out, void* stream);
+int mauv_softmax_gate_bwd_f32(const float* score, const float* v, const float* dout, int ld_dout, long long rows, int n,
+                              float* dscore, float* dv, void* stream);
+/* loss = cross_entropy(mean_s logits, labels) (train/multimodal.py:118-121); dlogits [S][B][C] = d loss / d logits. */
+int mauv_ce_mean_fwd_bwd_f32(const float* logits, const long long* labels, int S, int B, int C, float* mean_logit,
+                             float* dlogits, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,694 @@
+// S-batched ELBO backward (a5/a6): the kernels between the tensor-core contractions when the G Monte-Carlo passes of one
+// training step (train/multimodal.py:104-145, train/unimodal.py:125-146) are walked backwards together:
+//   train-mode BatchNorm backward with per-(sample, channel) statistics, fused with the ReLU mask and the residual fan-in,
+//   max-pool / avg-pool backward, the grouped weight-gradient finalisation (dmu += sum_g dW_g, drho += sum_g dW_g*eps_g*sigmoid(rho)),
+//   the fp32 fusion-head backward and cross_entropy(mean_s logits).
+// Gradients travel as fp16 with a device-resident power-of-two scale per tensor (value = true gradient * scale). Every
+// BatchNorm site re-normalises the scale from the running amax without a host round trip, so the whole backward is
+// enqueued asynchronously; parameter gradients are unscaled on accumulation into fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kHalfMax = 65504.f;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    h[j] = __floats2half2_rn(fminf(fmaxf(f[2 * j], -kHalfMax), kHalfMax), fminf(fmaxf(f[2 * j + 1], -kHalfMax), kHalfMax));
+  return v;
+}
+
+// upstream gradient of a site: d1 (+ d2 brought to d1's scale), masked by the ReLU output when given
+struct Upstream {
+  const uint4* d1; const uint4* d2; const float* s1; const float* s2; const uint4* mask;
+};
+
+__device__ __forceinline__ float upstream_ratio(const Upstream& u) { return u.d2 ? (*u.s1) / (*u.s2) : 0.f; }
+
+__device__ __forceinline__ void load_dz(const Upstream& u, long long idx, float ratio, float* dz) {
+  unpack8(__ldg(u.d1 + idx), dz);
+  if (u.d2) {
+    float t[8];
+    unpack8(__ldg(u.d2 + idx), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = fmaf(ratio, t[j], dz[j]);
+  }
+  if (u.mask) {
+    float m[8];
+    unpack8(__ldg(u.mask + idx), m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = m[j] > 0.f ? dz[j] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- BN backward, pass 1: per-(sample, channel) sums
+// partial [G][nblk][3][C] = (sum dz, sum dz*y, sum dz*y2); amax = max |dz| (float bits, atomicMax)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(Upstream u, const uint4* __restrict__ y, const uint4* __restrict__ y2, long long M, int C, int nblk,
+                     long long rows_per_block, float* __restrict__ partial, unsigned* __restrict__ amax) {
+  __shared__ float red[3 * 2048];
+  const int lanes = C >> 3, rl = 256 / lanes;
+  const int cv = threadIdx.x % lanes, r = threadIdx.x / lanes;
+  const int g = blockIdx.y, b = blockIdx.x;
+  const long long row0 = b * rows_per_block;
+  const long long row1 = min(M, row0 + rows_per_block);
+  const float ratio = upstream_ratio(u);
+  float s0[8], s1[8], s2[8], mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
+  for (long long row = row0 + r; row < row1; row += rl) {
+    const long long idx = (static_cast<long long>(g) * M + row) * lanes + cv;
+    float dz[8], yv[8];
+    load_dz(u, idx, ratio, dz);
+    unpack8(__ldg(y + idx), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0[j] += dz[j];
+      s1[j] = fmaf(dz[j], yv[j], s1[j]);
+      mx = fmaxf(mx, fabsf(dz[j]));
+    }
+    if (y2) {
+      unpack8(__ldg(y2 + idx), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s2[j] = fmaf(dz[j], yv[j], s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[(r * 3 + 0) * C + cv * 8 + j] = s0[j];
+    red[(r * 3 + 1) * C + cv * 8 + j] = s1[j];
+    red[(r * 3 + 2) * C + cv * 8 + j] = s2[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float acc = 0.f;
+      for (int q = 0; q < rl; ++q) acc += red[(q * 3 + k) * C + c];
+      partial[((static_cast<long long>(g) * nblk + b) * 3 + k) * C + c] = acc;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f && isfinite(mx)) atomicMax(amax, __float_as_uint(mx));
+}
+
+// ---------------------------------------------------------------- BN backward, pass 2: coefficients + affine gradients
+// dy = k0*dz + k1*y + k2 with k0 = gamma*invstd, k1 = -k0*invstd*dgamma/M, k2 = -k0*sum(dz)/M - k1*mean
+// (dgamma = invstd*(sum dz*y - mean*sum dz)); grad_gamma += sum_g dgamma/s, grad_beta += sum_g sum(dz)/s.
+__global__ void __launch_bounds__(128)
+bn_bwd_coeffs_kernel(const float* __restrict__ partial, int G, int nblk, int C, int which, double inv_m,
+                     const float2* __restrict__ stats, const float* __restrict__ gamma, float eps,
+                     const float* __restrict__ s_in, float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
+                     float4* __restrict__ coef, unsigned* __restrict__ kmax) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float km = 0.f;
+  if (c < C) {
+    double gsum = 0.0, bsum = 0.0;
+    const double gam = gamma ? static_cast<double>(gamma[c]) : 1.0;
+    for (int g = 0; g < G; ++g) {
+      double S0 = 0.0, S1 = 0.0;
+      for (int b = 0; b < nblk; ++b) {
+        const long long base = (static_cast<long long>(g) * nblk + b) * 3 * C;
+        S0 += partial[base + c];
+        S1 += partial[base + static_cast<long long>(which) * C + c];
+      }
+      const float2 mv = stats[static_cast<long long>(g) * C + c];
+      const double mean = mv.x, invstd = 1.0 / sqrt(static_cast<double>(mv.y) + eps);
+      const double dgam = invstd * (S1 - mean * S0);
+      const double k0 = gam * invstd;
+      const double k1 = -k0 * invstd * dgam * inv_m;
+      const double k2 = -k0 * S0 * inv_m - k1 * mean;
+      coef[static_cast<long long>(g) * C + c] = make_float4(static_cast<float>(k0), static_cast<float>(k1), static_cast<float>(k2), 0.f);
+      km = fmaxf(km, fabsf(static_cast<float>(k0)));
+      gsum += dgam;
+      bsum += S0;
+    }
+    const double inv_s = 1.0 / static_cast<double>(*s_in);
+    if (grad_gamma) grad_gamma[c] += static_cast<float>(gsum * inv_s);
+    if (grad_beta) grad_beta[c] += static_cast<float>(bsum * inv_s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
+  if ((threadIdx.x & 31) == 0 && km > 0.f && isfinite(km)) atomicMax(kmax, __float_as_uint(km));
+}
+
+__device__ __forceinline__ float pow2_rescale(const unsigned* amax, const unsigned* kmax, float target) {
+  const float bound = 4.f * __uint_as_float(*amax) * __uint_as_float(*kmax);
+  if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
+  int e;
+  frexpf(target / bound, &e);
+  e = max(-60, min(60, e - 1));
+  return ldexpf(1.f, e);
+}
+
+// ---------------------------------------------------------------- BN backward, pass 3: apply
+// dy = r*(k0*dz + k1*y + k2) (fp16, scale s1*r written to s_out); optional second BN sharing dz (downsample branch);
+// optional dz output (identity branch of the residual), kept at scale s1.
+struct ApplyArgs {
+  Upstream u;
+  const uint4* y; const uint4* y2;
+  const float4* coef; const float4* coef2;
+  const unsigned* amax; const unsigned* kmax; const unsigned* kmax2;
+  float target;
+  uint4* dy; uint4* dy2; uint4* dz;
+  float* s_out; float* s_out2;
+  long long M; int C;
+};
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const ApplyArgs a) {
+  const int lanes = a.C >> 3;
+  const int g = blockIdx.y;
+  const long long vecs = a.M * lanes;
+  const long long first = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long step = static_cast<long long>(gridDim.x) * 256;
+  const int cv = static_cast<int>(first % lanes);           // invariant: 256 % lanes == 0
+  const float ratio = upstream_ratio(a.u);
+  const float r1 = pow2_rescale(a.amax, a.kmax, a.target);
+  const float r2 = a.y2 ? pow2_rescale(a.amax, a.kmax2, a.target) : 1.f;
+  if (blockIdx.x == 0 && g == 0 && threadIdx.x == 0) {
+    *a.s_out = (*a.u.s1) * r1;
+    if (a.y2) *a.s_out2 = (*a.u.s1) * r2;
+  }
+  float k0[8], k1[8], k2[8], q0[8], q1[8], q2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = a.coef[static_cast<long long>(g) * a.C + cv * 8 + j];
+    k0[j] = k.x * r1; k1[j] = k.y * r1; k2[j] = k.z * r1;
+    if (a.y2) {
+      const float4 q = a.coef2[static_cast<long long>(g) * a.C + cv * 8 + j];
+      q0[j] = q.x * r2; q1[j] = q.y * r2; q2[j] = q.z * r2;
+    }
+  }
+  const long long base = static_cast<long long>(g) * vecs;
+  for (long long i = first; i < vecs; i += step) {
+    float dz[8], yv[8], o[8];
+    load_dz(a.u, base + i, ratio, dz);
+    unpack8(__ldg(a.y + base + i), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], dz[j], fmaf(k1[j], yv[j], k2[j]));
+    a.dy[base + i] = pack8(o);
+    if (a.y2) {
+      unpack8(__ldg(a.y2 + base + i), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(q0[j], dz[j], fmaf(q1[j], yv[j], q2[j]));
+      a.dy2[base + i] = pack8(o);
+    }
+    if (a.dz) a.dz[base + i] = pack8(dz);
+  }
+}
+
+// ---------------------------------------------------------------- stem: backward of maxpool3x3/2(relu(bn(y)))
+// dz[n,h,w,c] = [z>0] * sum over the <=4 pooling windows containing (h,w) of d[n,p,q,c] * [(h,w) is the window's arg-max]
+// (first maximum in row-major scan order wins, as ATen's max_pool2d); z = relu(y*scale+shift) recomputed.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, Upstream u, int imgs_per_sample, int H, int W,
+                   int C, int Ho, int Wo, long long total, uint4* __restrict__ dz) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int lanes = C >> 3;
+  const int cv = static_cast<int>(i % lanes);
+  long long t = i / lanes;
+  const int w = static_cast<int>(t % W); t /= W;
+  const int h = static_cast<int>(t % H);
+  const long long n = t / H;
+  const int g = static_cast<int>(n / imgs_per_sample);
+  const float ratio = upstream_ratio(u);
+  float sc[8], sh[8], self[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 s = ss[static_cast<long long>(g) * C + cv * 8 + j];
+    sc[j] = s.x; sh[j] = s.y; acc[j] = 0.f;
+  }
+  {
+    float yv[8];
+    unpack8(__ldg(y + i), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) self[j] = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
+  }
+  const int p_lo = h >> 1, p_hi = min((h + 1) >> 1, Ho - 1);
+  const int q_lo = w >> 1, q_hi = min((w + 1) >> 1, Wo - 1);
+  for (int p = p_lo; p <= p_hi; ++p) {
+    for (int q = q_lo; q <= q_hi; ++q) {
+      bool is_max[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) is_max[j] = self[j] > 0.f;
+      for (int dr = 0; dr < 3; ++dr) {
+        const int hh = 2 * p - 1 + dr;
+        if (hh < 0 || hh >= H) continue;
+        for (int ds = 0; ds < 3; ++ds) {
+          const int ww = 2 * q - 1 + ds;
+          if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
+          float yv[8];
+          unpack8(__ldg(y + ((n * H + hh) * W + ww) * lanes + cv), yv);
+          const bool earlier = hh < h || (hh == h && ww < w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
+            is_max[j] = is_max[j] && (earlier ? self[j] > v : self[j] >= v);
+          }
+        }
+      }
+      float d[8];
+      Upstream un = u;
+      un.mask = nullptr;
+      load_dz(un, ((n * Ho + p) * Wo + q) * lanes + cv, ratio, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += is_max[j] ? d[j] : 0.f;
+    }
+  }
+  dz[i] = pack8(acc);
+}
+
+// ---------------------------------------------------------------- avgpool backward (+ the first loss scale)
+__global__ void __launch_bounds__(256)
+amax_f32_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ amax) {
+  float mx = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    mx = fmaxf(mx, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f && isfinite(mx)) atomicMax(amax, __float_as_uint(mx));
+}
+
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const float* __restrict__ dfeat, const unsigned* __restrict__ amax, float target, int HW, int C,
+                   long long total, __half* __restrict__ out, float* __restrict__ s_out) {
+  const float am = __uint_as_float(*amax);
+  float r = 1.f;
+  if (am > 0.f && isfinite(am)) {
+    int e;
+    frexpf(target * static_cast<float>(HW) / am, &e);
+    r = ldexpf(1.f, max(-60, min(60, e - 1)));
+  }
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0) *s_out = r;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long n = i / (static_cast<long long>(C) * HW);
+  out[i] = __float2half_rn(dfeat[n * C + c] * (r / static_cast<float>(HW)));
+}
+
+// ---------------------------------------------------------------- grouped weight-gradient finalisation
+// dw fp16 [G*splits][cout][Kp] (K order (r,s,c)), value = true dW * (*s) / inv_alpha
+__global__ void __launch_bounds__(256)
+wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, int cout, int cin, int kh, int kw, int Kp,
+                            float inv_alpha, const float* __restrict__ s, const float* __restrict__ rho,
+                            const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0, int stale,
+                            float* __restrict__ grad_mu, float* __restrict__ grad_rho) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int khw = kh * kw;
+  const long long per_out = static_cast<long long>(cin) * khw;
+  const long long n = per_out * cout;
+  if (e >= n) return;
+  const long long co = e / per_out;
+  const int rem = static_cast<int>(e - co * per_out);
+  const int c = rem / khw, rs = rem - c * khw;
+  const long long k = static_cast<long long>(rs) * cin + c;
+  float am = 0.f, ar = 0.f;
+  for (int g = 0; g < G; ++g) {
+    float d = 0.f;
+    for (int sp = 0; sp < splits; ++sp)
+      d += __half2float(dw[((static_cast<long long>(g) * splits + sp) * cout + co) * Kp + k]);
+    am += d;
+    if (!stale) {
+      const float z = eps ? eps[static_cast<long long>(g) * n + e]
+                          : philox_normal(seed, layer_id, sample0 + g, static_cast<uint64_t>(e));
+      ar = fmaf(d, z, ar);
+    }
+  }
+  if (stale) {   // reference quirk: the saved eps buffer holds the last pass's draw for every pass
+    const float z = eps ? eps[static_cast<long long>(G - 1) * n + e]
+                        : philox_normal(seed, layer_id, sample0 + G - 1, static_cast<uint64_t>(e));
+    ar = am * z;
+  }
+  const float inv = inv_alpha / (*s);
+  const float ex = expf(rho[e]);
+  const float sgm = isinf(ex) ? 1.f : ex / (1.f + ex);
+  grad_mu[e] += am * inv;
+  grad_rho[e] += ar * inv * sgm;
+}
+
+// ---------------------------------------------------------------- head backward, grouped over the G samples (fp32)
+constexpr int LT = 16;
+struct LinG {
+  const float* x; long long x_sg; int x_sb;       // [G][B][in]
+  const float* gy; long long gy_sg; int gy_sb;    // [G][B][out]
+  const float* mu_w; const float* rho_w; const float* eps_w; const float* rho_b; const float* eps_b;
+  uint64_t seed; uint32_t layer_id, sample0;
+  int G, B, in, out, stale, accumulate;
+  float* gx; long long gx_sg; int gx_sb;          // [G][B][in] (= or +=)
+  float* gmu_w; float* grho_w; float* gmu_b; float* grho_b;
+};
+
+__global__ void __launch_bounds__(256)
+linear_bwd_data_group_kernel(const LinG p) {
+  __shared__ float gs[LT][LT + 1], ws[LT][LT + 1];
+  const int tx = threadIdx.x % LT, ty = threadIdx.x / LT;
+  const int i = blockIdx.x * LT + tx, b = blockIdx.y * LT + ty, g = blockIdx.z;
+  const float* gy = p.gy + g * p.gy_sg;
+  const float* ew = p.eps_w ? p.eps_w + static_cast<long long>(g) * p.out * p.in : nullptr;
+  float acc = 0.f;
+  for (int o0 = 0; o0 < p.out; o0 += LT) {
+    const int ob = o0 + tx;
+    gs[ty][tx] = (b < p.B && ob < p.out) ? gy[static_cast<long long>(b) * p.gy_sb + ob] : 0.f;
+    const int ow = o0 + ty;
+    float w = 0.f;
+    if (ow < p.out && i < p.in) {
+      const long long e = static_cast<long long>(ow) * p.in + i;
+      const float z = ew ? ew[e] : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
+      w = fmaf(softplus_ref(p.rho_w[e]), z, p.mu_w[e]);
+    }
+    ws[ty][tx] = w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LT; ++k) acc = fmaf(gs[ty][k], ws[k][tx], acc);
+    __syncthreads();
+  }
+  if (b < p.B && i < p.in) {
+    float* o = p.gx + g * p.gx_sg + static_cast<long long>(b) * p.gx_sb + i;
+    *o = p.accumulate ? *o + acc : acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_group_kernel(const LinG p) {
+  __shared__ float gs[LT][LT + 1], xs[LT][LT + 1];
+  const int tx = threadIdx.x % LT, ty = threadIdx.x / LT;
+  const int i = blockIdx.x * LT + tx, o = blockIdx.y * LT + ty;
+  const long long e = static_cast<long long>(o) * p.in + i;
+  const bool live = o < p.out && i < p.in;
+  const bool bias_lane = p.gmu_b && blockIdx.x == 0 && tx == 0 && o < p.out;
+  float am = 0.f, ar = 0.f, bm = 0.f, br = 0.f;
+  for (int g = 0; g < p.G; ++g) {
+    const float* gy = p.gy + g * p.gy_sg;
+    const float* x = p.x + g * p.x_sg;
+    float acc = 0.f, accb = 0.f;
+    for (int b0 = 0; b0 < p.B; b0 += LT) {
+      const int bb = b0 + ty;
+      const int oo = blockIdx.y * LT + tx;
+      gs[ty][tx] = (bb < p.B && oo < p.out) ? gy[static_cast<long long>(bb) * p.gy_sb + oo] : 0.f;
+      xs[ty][tx] = (bb < p.B && i < p.in) ? x[static_cast<long long>(bb) * p.x_sb + i] : 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < LT; ++k) {
+        acc = fmaf(gs[k][ty], xs[k][tx], acc);
+        accb += gs[k][ty];
+      }
+      __syncthreads();
+    }
+    am += acc;
+    bm += accb;
+    if (!p.stale) {
+      if (live) {
+        const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e]
+                                : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
+        ar = fmaf(acc, z, ar);
+      }
+      if (bias_lane) {
+        const float z = p.eps_b ? p.eps_b[static_cast<long long>(g) * p.out + o]
+                                : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + g, static_cast<uint64_t>(o));
+        br = fmaf(accb, z, br);
+      }
+    }
+  }
+  const int gl = p.G - 1;
+  if (live) {
+    if (p.stale) {
+      const float z = p.eps_w ? p.eps_w[static_cast<long long>(gl) * p.out * p.in + e]
+                              : philox_normal(p.seed, p.layer_id, p.sample0 + gl, static_cast<uint64_t>(e));
+      ar = am * z;
+    }
+    const float ex = expf(p.rho_w[e]);
+    p.gmu_w[e] += am;
+    p.grho_w[e] += ar * (isinf(ex) ? 1.f : ex / (1.f + ex));
+  }
+  if (bias_lane) {
+    if (p.stale) {
+      const float z = p.eps_b ? p.eps_b[static_cast<long long>(gl) * p.out + o]
+                              : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + gl, static_cast<uint64_t>(o));
+      br = bm * z;
+    }
+    const float ex = expf(p.rho_b[o]);
+    p.gmu_b[o] += bm;
+    p.grho_b[o] += br * (isinf(ex) ? 1.f : ex / (1.f + ex));
+  }
+}
+
+// t = tanh(q + k): dq = dk = dt * (1 - t^2)
+__global__ void __launch_bounds__(256)
+tanh_bwd_kernel(const float* __restrict__ t, const float* __restrict__ dt, long long n, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dt[i] * (1.f - t[i] * t[i]);
+}
+
+// out = v * softmax(score): dv = dout*p ; dscore = p * (dout*v - sum_j p_j*dout_j*v_j). One warp per row.
+__global__ void __launch_bounds__(256)
+softmax_gate_bwd_kernel(const float* __restrict__ score, const float* __restrict__ v, const float* __restrict__ dout,
+                        int ld_dout, long long rows, int n, float* __restrict__ dscore, float* __restrict__ dv) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* s = score + row * n;
+  const float* vv = v + row * n;
+  const float* d = dout + row * ld_dout;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, s[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float den = 0.f, dot = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float ex = expf(s[j] - mx);
+    den += ex;
+    dot = fmaf(ex, d[j] * vv[j], dot);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  const float inv = 1.f / den;
+  dot *= inv;
+  for (int j = lane; j < n; j += 32) {
+    const float pj = expf(s[j] - mx) * inv;
+    dv[row * n + j] = d[j] * pj;
+    dscore[row * n + j] = pj * (d[j] * vv[j] - dot);
+  }
+}
+
+// loss = mean_b CE(mean_s logits[s,b,:], label_b) ; dlogits[s,b,c] = (softmax(mean)[c] - [c == label]) / (B*S)
+__global__ void __launch_bounds__(256)
+ce_mean_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int S, int B, int C,
+               float* __restrict__ mean_logit, float* __restrict__ dlogits, float* __restrict__ loss) {
+  __shared__ float warp_sum[8];
+  float local = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float m = 0.f;
+      for (int s = 0; s < S; ++s) m += logits[(static_cast<long long>(s) * B + b) * C + c];
+      m /= static_cast<float>(S);
+      mean_logit[b * C + c] = m;
+      mx = fmaxf(mx, m);
+    }
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(mean_logit[b * C + c] - mx);
+    const float lse = mx + logf(den);
+    const int lab = static_cast<int>(labels[b]);
+    local += lse - mean_logit[b * C + lab];
+    const float w = 1.f / (static_cast<float>(B) * static_cast<float>(S));
+    for (int c = 0; c < C; ++c) {
+      const float gr = (expf(mean_logit[b * C + c] - lse) - (c == lab ? 1.f : 0.f)) * w;
+      for (int s = 0; s < S; ++s) dlogits[(static_cast<long long>(s) * B + b) * C + c] = gr;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int wi = 0; wi < (blockDim.x >> 5); ++wi) t += warp_sum[wi];
+    *loss = t / static_cast<float>(B);
+  }
+}
+
+Upstream make_up(const void* d1, const void* d2, const float* s1, const float* s2, const void* mask) {
+  Upstream u;
+  u.d1 = static_cast<const uint4*>(d1); u.d2 = static_cast<const uint4*>(d2);
+  u.s1 = s1; u.s2 = s2; u.mask = static_cast<const uint4*>(mask);
+  return u;
+}
+
+bool pow2_channels(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int mauv_bn_bwd_blocks(long long M) {
+  long long nb = (M + 511) / 512;
+  return static_cast<int>(nb < 1 ? 1 : (nb > 64 ? 64 : nb));
+}
+
+int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
+                       const void* y2, int G, long long M, int C, float* partial, unsigned int* amax, void* stream) {
+  MAUV_CHECK_ARG(d1 && s1 && y && partial && amax && (!d2 || s2), "mauv_bn_bwd_reduce: null pointer");
+  MAUV_CHECK_ARG(pow2_channels(C) && G >= 1 && M >= 1, "mauv_bn_bwd_reduce: C must be a power of two in [64, 2048] (got %d)", C);
+  const int nblk = mauv_bn_bwd_blocks(M);
+  const long long rpb = (M + nblk - 1) / nblk;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MAUV_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned), st));
+  dim3 grid(nblk, G);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(make_up(d1, d2, s1, s2, relu_out), static_cast<const uint4*>(y),
+                                             static_cast<const uint4*>(y2), M, C, nblk, rpb, partial, amax);
+  MAUV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return MAUV_OK;
+}
+
+int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int which, const float* batch_stats,
+                       const float* gamma, float eps, const float* s_in, float* grad_gamma, float* grad_beta, float* coef,
+                       unsigned int* kmax, void* stream) {
+  MAUV_CHECK_ARG(partial && batch_stats && s_in && coef && kmax && (which == 1 || which == 2), "mauv_bn_bwd_coeffs: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MAUV_CUDA(cudaMemsetAsync(kmax, 0, sizeof(unsigned), st));
+  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, G, mauv_bn_bwd_blocks(M), C, which, 1.0 / static_cast<double>(M),
+                                                        reinterpret_cast<const float2*>(batch_stats), gamma, eps, s_in,
+                                                        grad_gamma, grad_beta, reinterpret_cast<float4*>(coef), kmax);
+  MAUV_LAUNCH_CHECK("bn_bwd_coeffs_kernel");
+  return MAUV_OK;
+}
+
+int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
+                      const void* y2, const float* coef, const float* coef2, const unsigned int* amax,
+                      const unsigned int* kmax, const unsigned int* kmax2, float target, int G, long long M, int C, void* dy,
+                      void* dy2, void* dz, float* s_out, float* s_out2, void* stream) {
+  MAUV_CHECK_ARG(d1 && s1 && y && coef && amax && kmax && dy && s_out && (!d2 || s2), "mauv_bn_bwd_apply: null pointer");
+  MAUV_CHECK_ARG(!y2 || (coef2 && kmax2 && dy2 && s_out2), "mauv_bn_bwd_apply: the second BatchNorm needs coef2/kmax2/dy2/s_out2");
+  MAUV_CHECK_ARG(pow2_channels(C) && G >= 1 && M >= 1, "mauv_bn_bwd_apply: C must be a power of two in [64, 2048] (got %d)", C);
+  ApplyArgs a;
+  a.u = make_up(d1, d2, s1, s2, relu_out);
+  a.y = static_cast<const uint4*>(y); a.y2 = static_cast<const uint4*>(y2);
+  a.coef = reinterpret_cast<const float4*>(coef); a.coef2 = reinterpret_cast<const float4*>(coef2);
+  a.amax = amax; a.kmax = kmax; a.kmax2 = kmax2; a.target = target;
+  a.dy = static_cast<uint4*>(dy); a.dy2 = static_cast<uint4*>(dy2); a.dz = static_cast<uint4*>(dz);
+  a.s_out = s_out; a.s_out2 = s_out2; a.M = M; a.C = C;
+  const long long vecs = M * (C / 8);
+  long long bx = ceil_div_i64(vecs, 256 * 4);
+  const long long cap = static_cast<long long>(mauv_num_sms()) * 8;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(static_cast<unsigned>(bx), G);
+  bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  MAUV_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return MAUV_OK;
+}
+
+int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1, const void* d2, const float* s1,
+                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* dz, void* stream) {
+  MAUV_CHECK_ARG(y && scale_shift && d1 && s1 && dz && (!d2 || s2) && C % 8 == 0, "mauv_maxpool_bwd_f16: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(G) * imgs_per_sample * H * W * (C / 8);
+  maxpool_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift), make_up(d1, d2, s1, s2, nullptr),
+      imgs_per_sample, H, W, C, Ho, Wo, total, static_cast<uint4*>(dz));
+  MAUV_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return MAUV_OK;
+}
+
+int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
+                         float* s_out, void* stream) {
+  MAUV_CHECK_ARG(dfeat && amax_ws && out && s_out && N >= 1 && HW >= 1 && C >= 1, "mauv_avgpool_bwd_f16: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MAUV_CUDA(cudaMemsetAsync(amax_ws, 0, sizeof(unsigned), st));
+  const long long nf = N * C;
+  const int64_t ab = ceil_div_i64(nf, 256);
+  amax_f32_kernel<<<static_cast<unsigned>(ab > 1024 ? 1024 : ab), 256, 0, st>>>(dfeat, nf, amax_ws);
+  MAUV_LAUNCH_CHECK("amax_f32_kernel");
+  const long long total = nf * HW;
+  avgpool_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, st>>>(dfeat, amax_ws, target, HW, C, total,
+                                                                                     static_cast<__half*>(out), s_out);
+  MAUV_LAUNCH_CHECK("avgpool_bwd_kernel");
+  return MAUV_OK;
+}
+
+int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
+                              float inv_alpha, const float* scale, const float* rho, const float* eps, uint64_t seed,
+                              uint32_t layer_id, uint32_t sample0, int stale_eps, float* grad_mu, float* grad_rho,
+                              void* stream) {
+  MAUV_CHECK_ARG(dw_partial && scale && rho && grad_mu && grad_rho && G >= 1 && splits >= 1, "mauv_wgrad_finalize_group: bad argument");
+  const long long n = static_cast<long long>(cout) * cin * kh * kw;
+  wgrad_finalize_group_kernel<<<static_cast<unsigned>(ceil_div_i64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
+      sample0, stale_eps, grad_mu, grad_rho);
+  MAUV_LAUNCH_CHECK("wgrad_finalize_group_kernel");
+  return MAUV_OK;
+}
+
+int mauv_sampled_linear_bwd_group_f32(const float* x, long long x_sg, int x_sb, const float* gy, long long gy_sg, int gy_sb,
+                                      const float* mu_w, const float* rho_w, const float* eps_w, const float* rho_b,
+                                      const float* eps_b, uint64_t seed, uint32_t layer_id, uint32_t sample0, int G, int B,
+                                      int in_features, int out_features, int stale_eps, float* gx, long long gx_sg, int gx_sb,
+                                      int accumulate_gx, float* grad_mu_w, float* grad_rho_w, float* grad_mu_b,
+                                      float* grad_rho_b, void* stream) {
+  MAUV_CHECK_ARG(x && gy && mu_w && rho_w && grad_mu_w && grad_rho_w && G >= 1 && G <= 65535, "mauv_sampled_linear_bwd_group_f32: bad argument");
+  MAUV_CHECK_ARG((grad_mu_b == nullptr) == (grad_rho_b == nullptr) && (grad_mu_b == nullptr || rho_b != nullptr),
+                 "mauv_sampled_linear_bwd_group_f32: bias gradient pointers go together with rho_b");
+  LinG p;
+  p.x = x; p.x_sg = x_sg; p.x_sb = x_sb; p.gy = gy; p.gy_sg = gy_sg; p.gy_sb = gy_sb;
+  p.mu_w = mu_w; p.rho_w = rho_w; p.eps_w = eps_w; p.rho_b = rho_b; p.eps_b = eps_b;
+  p.seed = seed; p.layer_id = layer_id; p.sample0 = sample0; p.G = G; p.B = B; p.in = in_features; p.out = out_features;
+  p.stale = stale_eps; p.accumulate = accumulate_gx; p.gx = gx; p.gx_sg = gx_sg; p.gx_sb = gx_sb;
+  p.gmu_w = grad_mu_w; p.grho_w = grad_rho_w; p.gmu_b = grad_mu_b; p.grho_b = grad_rho_b;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gx) {
+    dim3 g1((in_features + LT - 1) / LT, (B + LT - 1) / LT, G);
+    linear_bwd_data_group_kernel<<<g1, 256, 0, st>>>(p);
+    MAUV_LAUNCH_CHECK("linear_bwd_data_group_kernel");
+  }
+  dim3 g2((in_features + LT - 1) / LT, (out_features + LT - 1) / LT);
+  linear_bwd_weight_group_kernel<<<g2, 256, 0, st>>>(p);
+  MAUV_LAUNCH_CHECK("linear_bwd_weight_group_kernel");
+  return MAUV_OK;
+}
+
+int mauv_tanh_bwd_f32(const float* t, const float* dt, long long n, float* out, void* stream) {
+  MAUV_CHECK_ARG(t && dt && out, "mauv_tanh_bwd_f32: null pointer");
+  tanh_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, dt, n, out);
+  MAUV_LAUNCH_CHECK("tanh_bwd_kernel");
+  return MAUV_OK;
+}
+
+int mauv_softmax_gate_bwd_f32(const float* score, const float* v, const float* dout, int ld_dout, long long rows, int n,
+                              float* dscore, float* dv, void* stream) {
+  MAUV_CHECK_ARG(score && v && dout && dscore && dv && n >= 1 && ld_dout >= n, "mauv_softmax_gate_bwd_f32: bad argument");
+  softmax_gate_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      score, v, dout, ld_dout, rows, n, dscore, dv);
+  MAUV_LAUNCH_CHECK("softmax_gate_bwd_kernel");
+  return MAUV_OK;
+}
+
+int mauv_ce_mean_fwd_bwd_f32(const float* logits, const long long* labels, int S, int B, int C, float* mean_logit,
+                             float* dlogits, float* loss, void* stream) {
+  MAUV_CHECK_ARG(logits && labels && mean_logit && dlogits && loss && S >= 1 && B >= 1 && C >= 1, "mauv_ce_mean_fwd_bwd_f32: bad argument");
+  ce_mean_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, S, B, C, mean_logit, dlogits, loss);
+  MAUV_LAUNCH_CHECK("ce_mean_kernel");
+  return MAUV_OK;
+}
+
+}  // extern "C"

@@ -463,6 +463,148 @@ def sampled_linear_bwd_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, gra
     return gx
 
 
+
+# ------------------------------------------------------------------ S-batched training backward
+GRAD_TARGET = 16.0   # amax the fp16 gradient tensors are renormalised to at every BatchNorm site
+KERNELS_PER_CALL.update({"mauv_avgpool_bwd_f16": 2, "mauv_sampled_linear_bwd_group_f32": 2})
+
+
+class GradScratch:
+    """Device scalars (scales, amax / kmax bits) for one backward walk, carved from one small buffer."""
+
+    def __init__(self, device, n: int = 4096):
+        self.f = torch.zeros(n, dtype=F32, device=device)
+        self.u = self.f.view(torch.int32)
+        self.used = 0
+
+    def slot(self) -> int:
+        """-> byte address of a fresh 4-byte slot"""
+        if self.used >= self.f.numel():
+            raise _lib.MauvError("GradScratch exhausted")
+        self.used += 1
+        return self.f.data_ptr() + 4 * (self.used - 1)
+
+    def value(self, addr: int) -> float:
+        return float(self.f[(addr - self.f.data_ptr()) // 4])
+
+
+def bn_bwd_site(gs: GradScratch, d1, s1, y, batch_stats, gamma, bn_eps, grad_gamma, grad_beta, G, C, *, d2=None, s2=None,
+                relu_out=None, y2=None, batch_stats2=None, gamma2=None, bn_eps2=0.0, grad_gamma2=None, grad_beta2=None,
+                want_dz=False):
+    """Train-mode BatchNorm backward at one site (three launches + one per extra BN).
+    -> (dy, s_dy, dy2 | None, s_dy2 | None, dz | None); scales are device addresses."""
+    lib = _lib.require_device()
+    M = y.numel() // (G * C)
+    dev = y.device
+    nblk = lib.mauv_bn_bwd_blocks(M)
+    partial = torch.empty((G, nblk, 3, C), dtype=F32, device=dev)
+    amax = gs.slot()
+    st = _stream()
+    _run("mauv_bn_bwd_reduce", lib.mauv_bn_bwd_reduce, _ptr(d1, F16), _ptr(d2, F16), s1, s2, _ptr(relu_out, F16), _ptr(y, F16),
+         _ptr(y2, F16), G, M, C, _ptr(partial), amax, st)
+    coef = torch.empty((G, C, 4), dtype=F32, device=dev)
+    kmax = gs.slot()
+    _run("mauv_bn_bwd_coeffs", lib.mauv_bn_bwd_coeffs, _ptr(partial), G, M, C, 1, _ptr(batch_stats, F32), _ptr(gamma, F32), bn_eps,
+         s1, _ptr(grad_gamma, F32), _ptr(grad_beta, F32), _ptr(coef), kmax, st)
+    coef2 = kmax2 = dy2 = s_out2 = None
+    if y2 is not None:
+        coef2 = torch.empty((G, C, 4), dtype=F32, device=dev)
+        kmax2 = gs.slot()
+        _run("mauv_bn_bwd_coeffs", lib.mauv_bn_bwd_coeffs, _ptr(partial), G, M, C, 2, _ptr(batch_stats2, F32), _ptr(gamma2, F32),
+             bn_eps2, s1, _ptr(grad_gamma2, F32), _ptr(grad_beta2, F32), _ptr(coef2), kmax2, st)
+        dy2 = torch.empty_like(y2)
+        s_out2 = gs.slot()
+    dy = torch.empty_like(y)
+    dz = torch.empty_like(y) if want_dz else None
+    s_out = gs.slot()
+    _run("mauv_bn_bwd_apply", lib.mauv_bn_bwd_apply, _ptr(d1, F16), _ptr(d2, F16), s1, s2, _ptr(relu_out, F16), _ptr(y, F16),
+         _ptr(y2, F16), _ptr(coef), _ptr(coef2), amax, kmax, kmax2, GRAD_TARGET, G, M, C, _ptr(dy), _ptr(dy2), _ptr(dz), s_out,
+         s_out2, st)
+    return dy, s_out, dy2, s_out2, dz
+
+
+def maxpool_bwd_f16(y, ss, d1, s1, G, *, d2=None, s2=None) -> torch.Tensor:
+    lib = _lib.require_device()
+    NB, H, W, Cc = y.shape
+    dz = torch.empty_like(y)
+    _run("mauv_maxpool_bwd_f16", lib.mauv_maxpool_bwd_f16, _ptr(y, F16), _ptr(ss, F32), _ptr(d1, F16), _ptr(d2, F16), s1, s2, G,
+         NB // G, H, W, Cc, _ptr(dz), _stream())
+    return dz
+
+
+def avgpool_bwd_f16(gs: GradScratch, dfeat: torch.Tensor, HW: int):
+    """dfeat [N, C] fp32 -> (d [N, HW, C] fp16, scale address)"""
+    lib = _lib.require_device()
+    N, Cc = dfeat.shape
+    out = torch.empty((N, HW, Cc), dtype=F16, device=dfeat.device)
+    amax, s_out = gs.slot(), gs.slot()
+    _run("mauv_avgpool_bwd_f16", lib.mauv_avgpool_bwd_f16, _ptr(dfeat, F32), N, HW, Cc, GRAD_TARGET, amax, _ptr(out), s_out, _stream())
+    return out, s_out
+
+
+def wgrad_finalize_group(dw_partial, G, mu_shape, inv_alpha, scale_addr, rho, grad_mu, grad_rho, *, eps=None, seed=0,
+                         layer_id=0, sample0=0, stale=False) -> None:
+    lib = _lib.require_device()
+    gsplits, cout, k_pad = dw_partial.shape
+    if len(mu_shape) == 2:
+        cin, kh, kw = mu_shape[1], 1, 1
+    else:
+        _, cin, kh, kw = mu_shape
+    _run("mauv_wgrad_finalize_group", lib.mauv_wgrad_finalize_group, _ptr(dw_partial, F16), G, gsplits // G, cout, cin, kh, kw,
+         k_pad, inv_alpha, scale_addr, _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0, int(stale), _ptr(grad_mu, F32),
+         _ptr(grad_rho, F32), _stream())
+
+
+def sampled_linear_bwd_group_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, grad_mu_b, grad_rho_b, *, eps_w=None,
+                                 eps_b=None, seed=0, layer_id=0, sample0=0, stale=False, gx=None, accumulate=False,
+                                 need_gx=True):
+    """x [G, B, in], gy [G, B, out] fp32 (last-dim stride 1) -> gx [G, B, in]; parameter grads accumulate in place."""
+    lib = _lib.require_device()
+    G, B, fin = x.shape
+    fout = gy.shape[2]
+    assert x.stride(2) == 1 and gy.stride(2) == 1
+    if need_gx and gx is None:
+        gx = torch.empty((G, B, fin), dtype=F32, device=x.device)
+        accumulate = False
+    _run("mauv_sampled_linear_bwd_group_f32", lib.mauv_sampled_linear_bwd_group_f32, x.data_ptr(), x.stride(0), x.stride(1),
+         gy.data_ptr(), gy.stride(0), gy.stride(1), _ptr(mu_w, F32), _ptr(rho_w, F32), _ptr(eps_w, F32), _ptr(rho_b, F32),
+         _ptr(eps_b, F32), seed, layer_id, sample0, G, B, fin, fout, int(stale),
+         gx.data_ptr() if need_gx else None, gx.stride(0) if need_gx else 0, gx.stride(1) if need_gx else 0, int(accumulate),
+         _ptr(grad_mu_w, F32), _ptr(grad_rho_w, F32), _ptr(grad_mu_b, F32), _ptr(grad_rho_b, F32), _stream())
+    return gx if need_gx else None
+
+
+def tanh_bwd_f32(t: torch.Tensor, dt: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    out = torch.empty_like(t)
+    _run("mauv_tanh_bwd_f32", lib.mauv_tanh_bwd_f32, _ptr(t, F32), _ptr(dt, F32), t.numel(), _ptr(out), _stream())
+    return out
+
+
+def softmax_gate_bwd_f32(score: torch.Tensor, v: torch.Tensor, dout: torch.Tensor):
+    """dout: [..., n] view with last-dim stride 1 (row stride = dout.stride(-2)) -> (dscore, dv)"""
+    lib = _lib.require_device()
+    n = score.shape[-1]
+    rows = score.numel() // n
+    assert dout.stride(-1) == 1 and dout.stride(0) == dout.stride(1) * dout.shape[1]
+    dscore, dv = torch.empty_like(score), torch.empty_like(v)
+    _run("mauv_softmax_gate_bwd_f32", lib.mauv_softmax_gate_bwd_f32, _ptr(score, F32), _ptr(v, F32), dout.data_ptr(),
+         dout.stride(-2), rows, n, _ptr(dscore), _ptr(dv), _stream())
+    return dscore, dv
+
+
+def ce_mean_fwd_bwd_f32(logits: torch.Tensor, labels: torch.Tensor):
+    """logits [S, B, C] fp32, labels [B] int64 -> (loss 0-d, mean_logit [B, C], dlogits [S, B, C])"""
+    lib = _lib.require_device()
+    S, B, Cc = logits.shape
+    mean_logit = torch.empty((B, Cc), dtype=F32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    loss = torch.empty((), dtype=F32, device=logits.device)
+    _run("mauv_ce_mean_fwd_bwd_f32", lib.mauv_ce_mean_fwd_bwd_f32, _ptr(logits, F32), _ptr(labels, I64), S, B, Cc,
+         _ptr(mean_logit), _ptr(dlogits), _ptr(loss), _stream())
+    return loss, mean_logit, dlogits
+
+
 # ------------------------------------------------------------------ statistics
 def mc_reduce(logits: torch.Tensor, eps_entropy: float = 1e-7) -> dict:
     """logits [S, B, C] fp32 -> dict of all MC statistics (see include/mauv_b200.h)."""

@@ -3,6 +3,7 @@ Usage: python tests/gpu_bringup.py <group>   group in {simple, gemm, conv, engin
 Each group should be run in its own process so that a CUDA fault in one does not poison the others.
 """
 import sys
+import math
 import time
 import traceback
 from pathlib import Path
@@ -322,6 +323,19 @@ def build_pair(kind, seed=1234):
     if kind == "multimodal":
         o_model = O.define_models(7, seed=None, unimodal=False)["multimodal_model"]
         model = MB.MultiModalModel(O.feature_extractor(), O.feature_extractor(), O.feature_extractor(1), 7)
+    elif kind == "unimodal_shallow":
+        # same topology family ([2,1,1,1] bottlenecks: stem, identity + downsample blocks, every stride) but 5 blocks deep:
+        # fp16 rounding is not amplified beyond a few 1e-3, so END-TO-END gradients can be compared tightly
+        def shallow():
+            from torchvision.models.resnet import Bottleneck, ResNet
+            m = O.ResNet50Custom(3, 7)
+            m.model = ResNet(Bottleneck, [2, 1, 1, 1])
+            m.model.conv1 = torch.nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+            m.model.fc = torch.nn.Linear(2048, 7)
+            return m
+        o_model = shallow()
+        O.dnn_to_bnn(o_model, O.DEFAULT_PRIOR)
+        model = shallow()
     else:
         o_model = O.ResNet50Custom(3, 7)
         O.dnn_to_bnn(o_model, O.DEFAULT_PRIOR)
@@ -498,6 +512,233 @@ def t_train(S=2, B=2, size=64):
         print("    %s cos=%.4f" % (name, w[0]))
 
 
+def t_bn_bwd(G=3, B=4, H=8, W=8, C=64, dual=False, two_up=True):
+    """BN-backward site kernels vs torch autograd: out = relu(bn(y) + r), r = identity residual or a second bn(y2)."""
+    from mauv import ops
+    torch.manual_seed(31)
+    M = B * H * W
+    y = torch.randn(G, M, C) * 2 + 0.5
+    y2 = torch.randn(G, M, C) - 0.3
+    res = torch.randn(G, M, C)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    gamma2, beta2 = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    d1 = torch.randn(G, M, C) * 1e-3
+    d2 = torch.randn(G, M, C) * 1e-3
+    sc1, sc2 = 4096.0, 1024.0                                   # device scales of the two upstream tensors
+    yh, y2h, resh = y.half(), y2.half(), res.half()
+    d1h, d2h = (d1 * sc1).half(), (d2 * sc2).half()
+    # reference (fp64 autograd on the fp16-rounded inputs)
+    yr = yh.double().requires_grad_(); y2r = y2h.double().requires_grad_(); rr = resh.double().requires_grad_()
+    gr, br = gamma.double().requires_grad_(), beta.double().requires_grad_()
+    g2r, b2r = gamma2.double().requires_grad_(), beta2.double().requires_grad_()
+    def bn(t, g, b):
+        mean = t.mean(1, keepdim=True); var = t.var(1, unbiased=False, keepdim=True)
+        return (t - mean) / torch.sqrt(var + 1e-5) * g + b, mean.squeeze(1), var.squeeze(1)
+    z, mean, var = bn(yr, gr, br)
+    if dual:
+        z2, mean2, var2 = bn(y2r, g2r, b2r)
+        out = torch.relu(z + z2)
+    else:
+        out = torch.relu(z + rr)
+    up = d1h.double() / sc1 + (d2h.double() / sc2 if two_up else 0)
+    out.backward(up)
+    # device
+    gs = ops.GradScratch(dev)
+    gs.f[0], gs.f[1] = sc1, sc2
+    gs.used = 2
+    s1, s2 = gs.f.data_ptr(), gs.f.data_ptr() + 4
+    bs = torch.stack([mean, var], -1).float().to(dev).contiguous()
+    gg, gb = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    gg2, gb2 = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    kw = dict(d2=d2h.to(dev) if two_up else None, s2=s2 if two_up else None, relu_out=out.detach().half().to(dev).contiguous())
+    if dual:
+        bs2 = torch.stack([mean2, var2], -1).float().to(dev).contiguous()
+        kw.update(y2=y2h.to(dev), batch_stats2=bs2, gamma2=gamma2.to(dev), bn_eps2=1e-5, grad_gamma2=gg2, grad_beta2=gb2)
+    else:
+        kw.update(want_dz=True)
+    dy, s_dy, dy2, s_dy2, dz = ops.bn_bwd_site(gs, d1h.to(dev), s1, yh.to(dev), bs, gamma.to(dev), 1e-5, gg, gb, G, C, **kw)
+    tag = f"bn_bwd G={G} M={M} C={C} dual={dual} two_up={two_up}"
+    report(tag + " dy", dy.float() / gs.value(s_dy), yr.grad, 2e-3)
+    report(tag + " dgamma", gg, gr.grad, 2e-3)
+    report(tag + " dbeta", gb, br.grad, 2e-3)
+    print(f"   scales: in {sc1} -> dy {gs.value(s_dy)}  amax(dy fp16) {dy.float().abs().max().item():.2f}")
+    if dual:
+        report(tag + " dy2", dy2.float() / gs.value(s_dy2), y2r.grad, 2e-3)
+        report(tag + " dgamma2", gg2, g2r.grad, 2e-3)
+        report(tag + " dbeta2", gb2, b2r.grad, 2e-3)
+    else:
+        report(tag + " dz", dz.float() / sc1, rr.grad, 2e-3)
+
+
+def t_pool_bwd(G=2, B=2, H=16, W=16, C=64):
+    """maxpool3x3/2(relu(bn(y))) backward and avgpool backward vs torch autograd."""
+    from mauv import ops
+    torch.manual_seed(32)
+    y = torch.randn(G * B, H, W, C).half()
+    ss = torch.stack([torch.rand(G, C) + 0.5, torch.randn(G, C) * 0.3], -1).contiguous()
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    d = (torch.randn(G * B, Ho, Wo, C) * 1e-2)
+    sc = 512.0
+    dh = (d * sc).half()
+    yr = y.double().requires_grad_()
+    scale = ss[..., 0].double().repeat_interleave(B, 0)[:, None, None, :]
+    shift = ss[..., 1].double().repeat_interleave(B, 0)[:, None, None, :]
+    z = yr * scale + shift                                       # grad wrt z (pre-ReLU BN output) is what the kernel returns
+    z.retain_grad()
+    pooled = torch.nn.functional.max_pool2d(torch.relu(z).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    pooled.backward(dh.double() / sc)
+    gs = ops.GradScratch(dev)
+    gs.f[0] = sc
+    gs.used = 1
+    dz = ops.maxpool_bwd_f16(y.to(dev), ss.to(dev), dh.to(dev), gs.f.data_ptr(), G)
+    report(f"maxpool_bwd G={G} B={B} {H}x{W} C={C}", dz.float() / sc, z.grad, 2e-3)
+    dfeat = torch.randn(G * B, 256) * 1e-4
+    out, s_out = ops.avgpool_bwd_f16(gs, dfeat.to(dev), 16)
+    report("avgpool_bwd", out.float() / gs.value(s_out), (dfeat / 16)[:, None, :].expand(-1, 16, -1), 2e-3)
+    print(f"   avgpool_bwd scale {gs.value(s_out)} amax fp16 {out.float().abs().max().item():.2f}")
+
+
+def t_conv_bwd_group(G, B, H, W, Cin, Cout, k, stride, pad, stale=False):
+    """Grouped conv backward of the training engine (dW over (sample, pixel-chunk) batches -> dmu/drho; dX over the
+    re-sampled flipped weights) vs torch autograd in fp64 on the same fp16 activations / gradients and injected eps."""
+    import types
+    import bnn_oracle as O
+    from mauv.bayesian import Conv2dReparameterization
+    from mauv.engine import MCEngine, _Conv
+    from mauv.train_engine import TrainEngine, _ConvRec
+    torch.manual_seed(41)
+    layer = Conv2dReparameterization(Cin, Cout, k, stride=stride, padding=pad, bias=False)
+    with torch.no_grad():
+        layer.mu_kernel.normal_(0, 0.05)
+        layer.rho_kernel.copy_(O.get_rho(layer.mu_kernel, 0.5))
+    layer.to(dev)
+    layer.mu_kernel.grad = torch.zeros_like(layer.mu_kernel)
+    layer.rho_kernel.grad = torch.zeros_like(layer.rho_kernel)
+    eps = torch.randn(G, Cout, Cin, k, k)
+    x = torch.relu(torch.randn(G * B, H, W, Cin)).half()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    dy = torch.randn(G * B, Ho, Wo, Cout) * 1e-3
+    sc = 2048.0
+    dyh = (dy * sc).half()
+    # reference
+    mu, rho = layer.mu_kernel.detach().cpu().double(), layer.rho_kernel.detach().cpu().double()
+    mu.requires_grad_(); rho.requires_grad_()
+    xr = x.double().permute(0, 3, 1, 2).reshape(G, B, Cin, H, W).requires_grad_()
+    tot = 0
+    for g in range(G):
+        w = mu + torch.log1p(torch.exp(rho)) * eps[g].double()
+        yg = torch.nn.functional.conv2d(xr[g], w, None, stride, pad)
+        tot = tot + (yg * (dyh.double() / sc).permute(0, 3, 1, 2).reshape(G, B, Cout, Ho, Wo)[g]).sum()
+    tot.backward()
+    grho_ref = rho.grad
+    if stale:   # every pass's d(rho) uses the last pass's eps
+        grho_ref = mu.grad * eps[G - 1].double() * torch.sigmoid(rho.detach())
+    # device
+    gs = ops.GradScratch(dev)
+    gs.f[0] = sc
+    gs.used = 1
+    stub = types.SimpleNamespace(device=torch.device(dev))
+    stub._eps_w = lambda e, name, s0, g: MCEngine._eps_w(stub, e, name, s0, g)
+    c = _Conv("conv", layer, 7, Cin, Cout, k, stride, pad)
+    rec = _ConvRec(c, None, x.to(dev), None, None)
+    dx = TrainEngine._conv_backward(stub, rec, dyh.to(dev), gs.f.data_ptr(), G, 0, {"conv": {"w": eps, "b": None}}, 1, stale)
+    tag = f"conv_bwd_group G={G} B={B} {H}x{W} {Cin}->{Cout} k{k}/{stride} stale={stale}"
+    report(tag + " dx", dx.float() / sc, xr.grad.reshape(G * B, Cin, H, W).permute(0, 2, 3, 1), 3e-3)
+    report(tag + " dmu", layer.mu_kernel.grad, mu.grad, 3e-3)
+    report(tag + " drho", layer.rho_kernel.grad, grho_ref, 3e-3)
+
+
+def _grad_table(tag, named_a, named_b, show=12):
+    import statistics
+    rows = []
+    for name, ga in named_a.items():
+        gb = named_b.get(name)
+        if ga is None or gb is None:
+            print("   missing grad:", name)
+            continue
+        a, b = ga.detach().cpu().flatten().double(), gb.detach().cpu().flatten().double()
+        cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)).item()
+        rel = ((a - b).abs().max() / (b.abs().max() + 1e-300)).item()
+        rows.append((cos, rel, name, a.norm().item(), b.norm().item()))
+    rows.sort()
+    print(f"   {tag}: lowest cosine similarities")
+    for r in rows[:show]:
+        print("    cos=%.4f maxrel=%.2e %-58s |g|=%.3e |ref|=%.3e" % r)
+    med = statistics.median(r[0] for r in rows)
+    print(f"   {tag}: median cos {med:.5f}; min cos {rows[0][0]:.4f}; n(cos>0.99) {sum(r[0] > 0.99 for r in rows)} of {len(rows)}; "
+          f"median maxrel {statistics.median(r[1] for r in rows):.2e}")
+    return rows
+
+
+def t_train_engine(S=2, B=2, size=64, kind="multimodal", stale=False, vs_oracle=True):
+    """TrainEngine (S-batched forward + hand-written backward) vs the drop-in layer path (torch autograd over the same
+    CUDA layer kernels) and vs the oracle's fp32 autograd, identical injected eps."""
+    import bnn_oracle as O
+    import mauv.bayesian as MB
+    from mauv.train_engine import TrainEngine
+    o_model, model = build_pair(kind)
+    img, bathy, sss, labels = O.synthetic_batch(B, size=size)
+    ins = (img, bathy, sss) if kind == "multimodal" else (img,)
+    eps = O.draw_eps(o_model, S, seed=5)
+    kl_scale = O.kl_weight(1, 20) / B
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    O.STALE_EPS_QUIRK = stale
+    MB.set_reference_stale_eps(stale)
+    try:
+        # layer path
+        layers = dict(MB.bayesian_layers(model))
+        xs = [t.to(dev) for t in ins]
+        outs_g = []
+        for s in range(S):
+            for name, l in layers.items():
+                e = eps[name]
+                l.eps_override = (e["w"][s].to(dev), None if e["b"] is None else e["b"][s].to(dev))
+            outs_g.append(model(*xs))
+        out = torch.mean(torch.stack(outs_g), dim=0)
+        loss_l = torch.nn.functional.cross_entropy(out, labels.to(dev)) + MB.get_kl_loss(model) * kl_scale
+        model.zero_grad(set_to_none=True)
+        loss_l.backward()
+        g_layer = {n: p.grad.clone() for n, p in model.named_parameters()}
+        for l in layers.values():
+            l.eps_override = None
+        # engine
+        model.load_state_dict(state0)
+        model.zero_grad(set_to_none=True)
+        eng = TrainEngine(model)
+        res = eng.step(xs, labels, S, kl_scale, eps=eps)
+        torch.cuda.synchronize()
+        g_eng = {n: p.grad.clone() for n, p in model.named_parameters()}
+        tag = f"train_engine {kind} S={S} B={B} {size}px stale={stale}"
+        print(f"{tag}: loss engine {res['loss'].item():.6f} layer-path {loss_l.item():.6f}")
+        report(tag + " logits vs layer path", res["logits"], torch.stack(outs_g), 2e-2)
+        report(tag + " loss vs layer path", res["loss"].reshape(1), loss_l.detach().reshape(1), 2e-3)
+        rows = _grad_table("engine vs layer path", g_eng, g_layer)
+        bad = [r for r in rows if not (r[0] > 0.90)]
+        if any(not math.isfinite(r[0]) for r in rows) or len(bad) > len(rows) // 10:
+            FAILS.append((tag, f"{len(bad)} of {len(rows)} parameter gradients below cos 0.90 vs the layer path"))
+        head = [r for r in rows if not r[2].split(".")[0].endswith("_feat") and not r[2].startswith("model.layer")
+                and not r[2].startswith("model.conv1") and not r[2].startswith("model.bn1")]
+        for r in head:
+            if r[0] < 0.999:
+                FAILS.append((tag, f"head gradient {r[2]} cos {r[0]:.4f} vs the layer path"))
+        if vs_oracle:
+            o_model.train()
+            outs = []
+            for s in range(S):
+                O.inject_eps(o_model, eps, s)
+                outs.append(o_model(*ins))
+            O.inject_eps(o_model, None, 0)
+            loss_o = torch.nn.functional.cross_entropy(torch.stack(outs).mean(0), labels) + O.get_kl_loss(o_model) * kl_scale
+            loss_o.backward()
+            g_or = {n: p.grad for n, p in o_model.named_parameters()}
+            print(f"   loss oracle {loss_o.item():.6f}")
+            _grad_table("engine vs oracle", g_eng, g_or)
+            _grad_table("layer path vs oracle", g_layer, g_or, show=4)
+    finally:
+        O.STALE_EPS_QUIRK = True
+        MB.set_reference_stale_eps(False)
+
+
 GROUPS = {
     "simple": lambda: [run_case(f) for f in (t_philox, t_sample, t_stem, t_bn, t_pool, t_linear, t_mc, t_kl)],
     "gemm": lambda: [run_case(t_gemm, *a) for a in [
@@ -517,6 +758,16 @@ GROUPS = {
                    run_case(t_engine_x3, 2, 2, 64, "unimodal"), run_case(t_engine_x3, 2, 2, 256, "unimodal"),
                    run_case(t_engine_x3, 2, 2, 64, "multimodal")],
     "train": lambda: [run_case(t_train, 1), run_case(t_train, 2)],
+    "bwd_units": lambda: [run_case(t_bn_bwd, 3, 4, 8, 8, 64, False, True), run_case(t_bn_bwd, 2, 4, 8, 8, 256, True, True),
+                          run_case(t_bn_bwd, 2, 2, 4, 4, 2048, False, False), run_case(t_bn_bwd, 1, 8, 64, 64, 128, True, False),
+                          run_case(t_pool_bwd), run_case(t_pool_bwd, 1, 1, 10, 14, 64)],
+    "conv_bwd": lambda: [run_case(t_conv_bwd_group, *a) for a in [
+        (2, 2, 8, 8, 64, 256, 1, 1, 0), (3, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
+        (2, 2, 16, 16, 256, 512, 1, 2, 0), (2, 8, 32, 32, 64, 64, 3, 1, 1), (3, 2, 8, 8, 128, 64, 1, 1, 0, True),
+        (2, 8, 64, 64, 256, 64, 1, 1, 0)]],
+    "train_engine": lambda: [run_case(t_train_engine, 2, 8, 128, "unimodal_shallow"), run_case(t_train_engine, 3, 4, 64, "unimodal_shallow", True),
+                             run_case(t_train_engine, 2, 8, 128, "unimodal"), run_case(t_train_engine, 2, 2, 64, "multimodal"),
+                             run_case(t_train_engine, 3, 8, 128, "unimodal", True)],
     "engine": lambda: [run_case(t_engine, 2, 2, 64, "multimodal"), run_case(t_engine, 2, 3, 64, "unimodal"),
                        run_case(t_engine, 2, 2, 256, "unimodal")],
 }
