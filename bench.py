@@ -295,38 +295,58 @@ def run_ours(args):
 
 
 def run_train(args):
-    """cfg3-style ELBO training step through the drop-in layers (secondary workload, not the headline metric):
-    S stochastic passes of the multimodal BNN, CE(mean logits) + KL/B * 2^(e+1)/2^E, backward, Adam - the body of
-    reference train/multimodal.py:104-145 with every Bayesian layer's forward/backward on the CUDA kernels."""
+    """cfg3 ELBO training step (secondary workload, not the headline metric): S stochastic passes of the multimodal BNN,
+    CE(mean logits) + KL/B * 2^(e+1)/2^E, backward, Adam - the body of reference train/multimodal.py:104-145.
+    --train-path engine (default): the S-batched TrainEngine (one grouped forward + one grouped backward);
+    --train-path layers: the drop-in layer path (S walks of torch autograd over the per-layer CUDA kernels).
+    N > 1: the minibatch is split over the ranks (B triplets per GPU, all S samples on every rank), gradients averaged
+    with one NCCL all-reduce per step (engine) / DistributedDataParallel (layers)."""
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device")
     from mauv import ops
     from mauv.bayesian import get_kl_loss
+    from mauv.train_engine import TrainEngine
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B, S = args.batch if args.batch != B_FULL else 8, args.samples if args.samples != S_FULL else 5
+    use_engine = args.train_path == "engine"
+    B = args.batch if args.batch != B_FULL else 8
+    S = args.samples if args.samples != S_FULL else (30 if use_engine else 5)
     model = build_model_cpu().cuda().train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False) if world > 1 else model
     opt = torch.optim.Adam(model.parameters(), lr=5e-5)
     xs = [x.cuda() for x in synthetic_inputs(B)]
     labels = torch.randint(0, C_CLASSES, (B,), device="cuda")
     kl_w = 2.0 / 2 ** 20
+    if use_engine:
+        eng = TrainEngine(model)
+        eng.flatten_grads()
 
-    def step():
-        opt.zero_grad(set_to_none=False)
-        out = torch.mean(torch.stack([net(*xs) for _ in range(S)]), dim=0)
-        loss = torch.nn.functional.cross_entropy(out, labels) + get_kl_loss(model) / B * kl_w
-        loss.backward()
-        opt.step()
-        return loss
+        def step():
+            eng.zero_grad()
+            res = eng.step(xs, labels, S, kl_w / B)
+            if world > 1:
+                eng.allreduce_grads()
+            opt.step()
+            return res["loss"]
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False) if world > 1 else model
+
+        def step():
+            opt.zero_grad(set_to_none=False)
+            out = torch.mean(torch.stack([net(*xs) for _ in range(S)]), dim=0)
+            loss = torch.nn.functional.cross_entropy(out, labels) + get_kl_loss(model) / B * kl_w
+            loss.backward()
+            opt.step()
+            return loss
 
     for _ in range(max(1, args.warmup)):
         step()
     torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
     l0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -338,15 +358,32 @@ def run_train(args):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = t.item()
+    detail = None
+    if args.detail and use_engine and rank == 0:
+        ops.start_profile()
+        step()
+        prof = ops.stop_profile()
+        agg = {}
+        for k, (c, tms) in prof.items():
+            n = k.split("|")[0]
+            a = agg.get(n, (0, 0.0))
+            agg[n] = (a[0] + c, a[1] + tms)
+        detail = {k: {"calls": c, "ms": round(tms, 3)} for k, (c, tms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
     if rank != 0:
         torch.distributed.destroy_process_group()
         return 0
-    print(json.dumps({"metric": "ELBO training triplets/sec (drop-in layer path)", "value": world * B / (ms / 1e3), "unit": UNIT,
-                      "n_gpus": world, "scaling": "weak", "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                      "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients",
-                      "config": {"workload": f"cfg3-style multimodal ELBO step, {B} triplets per GPU, S={S}, 256x256, C=7, Adam, "
-                                             f"DistributedDataParallel gradient all-reduce over {world} GPU(s)"},
-                      "gpu_launches": (ops.launch_count - l0), "loss": float(loss.detach())}))
+    flops = 94.77e9 * world * B * S      # forward + dgrad + wgrad per triplet-sample
+    line = {"metric": "ELBO training triplets/sec", "value": world * B / (ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "scaling": "weak", "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients",
+            "config": {"workload": f"cfg3 multimodal ELBO step, {B} triplets per GPU, S={S}, 256x256, C=7, Adam, "
+                                   f"path={args.train_path}, gradient all-reduce over {world} GPU(s)",
+                       "triplet_samples_per_s": world * B * S / (ms / 1e3)},
+            "model_tflops": flops / (ms / 1e3) / 1e12,
+            "gpu_launches": (ops.launch_count - l0), "loss": float(loss.detach())}
+    if detail is not None:
+        line["kernel_ms_per_step"] = detail
+    print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -363,6 +400,8 @@ def main():
     ap.add_argument("--group", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="per-shape kernel table on stderr")
+    ap.add_argument("--train-path", default="engine", choices=["engine", "layers"],
+                    help="--workload train: S-batched TrainEngine (default) or the drop-in layer path")
     ap.add_argument("--workload", default="inference", choices=["inference", "train"],
                     help="inference = BASELINE cfg2 (headline); train = cfg3-style ELBO step (secondary)")
     args = ap.parse_args()

@@ -211,7 +211,7 @@ int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const fl
  * unscaled by *s_in; coef [G][C][4]; *kmax = max|k0| as float bits. */
 int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int which, const float* batch_stats,
                        const float* gamma, float eps, const float* s_in, float* grad_gamma, float* grad_beta, float* coef,
-                       unsigned int* kmax, void* stream);
+                       unsigned int* kmax, void* ws /* G*C*16 bytes, 16-byte aligned */, void* stream);
 /* pass 3: dy = r*(k0*dz + k1*y + k2), r = power of two bringing the bound 4*amax*kmax to `target`; *s_out = *s1 * r.
  * Optional second BN on the same dz (y2/coef2/kmax2 -> dy2, s_out2: the downsample branch) and optional dz output
  * (fp16 at scale *s1: the identity branch). */

@@ -70,6 +70,52 @@ im2col_t_kernel(const __half* __restrict__ x, int H, int W, int Cin, int kh, int
   dst[(sp * Kp + k) * Mc + ml] = v;
 }
 
+// Tiled version for Cin % 8 == 0 (every layer but the stems): one block moves a [64 pixels] x [64 channels] tile of one
+// filter tap through shared memory, so that both the NHWC read (channels contiguous) and the transposed write (pixels
+// contiguous) are 16-byte vector accesses. kh = kw = 1, stride 1 is the plain [M][C] -> [splits][C][Mc] transpose.
+__global__ void __launch_bounds__(256)
+im2col_t_tiled_kernel(const __half* __restrict__ x, int H, int W, int Cin, int kw, int stride, int pad, int Ho, int Wo,
+                      int Kp, long long M, int Mc, float scale, __half* __restrict__ dst) {
+  __shared__ __half tile[64][66];
+  const long long m0 = static_cast<long long>(blockIdx.x) * 64;
+  const int cblocks = (Cin + 63) >> 6;
+  const int rs = blockIdx.y / cblocks, c0 = (blockIdx.y - rs * cblocks) << 6;
+  const int r = rs / kw, s = rs - r * kw;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = (threadIdx.x >> 3) + it * 32, cv = threadIdx.x & 7;
+    const long long m = m0 + row;
+    const int c = c0 + cv * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m < M && c < Cin) {
+      const int q = static_cast<int>(m % Wo);
+      const int p = static_cast<int>((m / Wo) % Ho);
+      const long long n = m / (static_cast<long long>(Wo) * Ho);
+      const int h = p * stride - pad + r, w = q * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + h) * W + w) * Cin + c));
+    }
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(&tile[row][cv * 8]);
+    t32[0] = v.x; t32[1] = v.y; t32[2] = v.z; t32[3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int pg = threadIdx.x & 7, cl = (threadIdx.x >> 3) + it * 32;
+    const long long m = m0 + pg * 8;
+    const int c = c0 + cl;
+    if (m < M && c < Cin) {
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half hv = tile[pg * 8 + j][cl];
+        o[j] = scale == 1.f ? hv : __float2half_rn(__half2float(hv) * scale);
+      }
+      const long long sp = m / Mc, ml = m - sp * Mc;
+      *reinterpret_cast<uint4*>(dst + (sp * Kp + static_cast<long long>(rs) * Cin + c) * Mc + ml) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
 // dW partials fp16 [splits][cout][Kp] ((r,s,c) K order, scaled by `scale`) -> grad_mu += dW, grad_rho += dW*eps*sigmoid(rho)
 // in the PyTorch layout [cout][cin][kh][kw]. eps: injected [n] or Philox(seed, layer, sample, e).
 __global__ void __launch_bounds__(256)
@@ -184,9 +230,18 @@ int mauv_dilate_f16(const void* x, long long N, int Ho, int Wo, int C, int Hd, i
 
 int mauv_transpose_chunks_f16(const void* src, long long M, int C, int splits, float scale, void* dst, void* stream) {
   MAUV_CHECK_ARG(src && dst && M >= 1 && C >= 1 && splits >= 1 && M % splits == 0, "mauv_transpose_chunks_f16: bad argument");
+  const long long Mc = M / splits;
+  if (C % 8 == 0 && Mc % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    dim3 grid(static_cast<unsigned>(ceil_div_i64(M, 64)), (C + 63) / 64);
+    MAUV_CHECK_ARG(grid.y <= 65535, "mauv_transpose_chunks_f16: too many channels");
+    im2col_t_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), 1, 1, C, 1, 1, 0, 1, 1, C, M, static_cast<int>(Mc), scale, static_cast<__half*>(dst));
+    MAUV_LAUNCH_CHECK("im2col_t_tiled_kernel");
+    return MAUV_OK;
+  }
   dim3 grid(static_cast<unsigned>(ceil_div_i64(M, 32)), (C + 31) / 32);
   transpose_chunks_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(src), M, C, static_cast<int>(M / splits), scale, static_cast<__half*>(dst));
+      static_cast<const __half*>(src), M, C, static_cast<int>(Mc), scale, static_cast<__half*>(dst));
   MAUV_LAUNCH_CHECK("transpose_chunks_kernel");
   return MAUV_OK;
 }
@@ -198,6 +253,17 @@ int mauv_im2col_t_f16(const void* x, long long N, int H, int W, int Cin, int kh,
   const long long M = N * Ho * Wo;
   const int K = kh * kw * Cin;
   MAUV_CHECK_ARG(k_pad >= K && splits >= 1 && M % splits == 0 && k_pad <= 65535, "mauv_im2col_t_f16: bad argument");
+  const long long Mc = M / splits;
+  if (Cin % 8 == 0 && k_pad == K && Mc % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    dim3 tg(static_cast<unsigned>(ceil_div_i64(M, 64)), static_cast<unsigned>(kh * kw * ((Cin + 63) / 64)));
+    MAUV_CHECK_ARG(tg.y <= 65535, "mauv_im2col_t_f16: too many (tap, channel-block) pairs");
+    im2col_t_tiled_kernel<<<tg, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), H, W, Cin, kw, stride, pad, Ho, Wo, k_pad, M, static_cast<int>(Mc), 1.f,
+        static_cast<__half*>(dst));
+    MAUV_LAUNCH_CHECK("im2col_t_tiled_kernel");
+    return MAUV_OK;
+  }
   dim3 grid(static_cast<unsigned>(ceil_div_i64(M, 256)), k_pad);
   im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), H, W, Cin, kh, kw, stride, pad, Ho, Wo, K, k_pad, M, static_cast<int>(M / splits),

@@ -109,41 +109,61 @@ bn_bwd_reduce_kernel(Upstream u, const uint4* __restrict__ y, const uint4* __res
 // ---------------------------------------------------------------- BN backward, pass 2: coefficients + affine gradients
 // dy = k0*dz + k1*y + k2 with k0 = gamma*invstd, k1 = -k0*invstd*dgamma/M, k2 = -k0*sum(dz)/M - k1*mean
 // (dgamma = invstd*(sum dz*y - mean*sum dz)); grad_gamma += sum_g dgamma/s, grad_beta += sum_g sum(dz)/s.
-__global__ void __launch_bounds__(128)
-bn_bwd_coeffs_kernel(const float* __restrict__ partial, int G, int nblk, int C, int which, double inv_m,
+// grid (C/32, G), block (32 channels x 8 partial-lanes): per-(sample, channel) coefficients + (dgamma, sum dz) into tmp
+__global__ void __launch_bounds__(256)
+bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblk, int C, int which, double inv_m,
                      const float2* __restrict__ stats, const float* __restrict__ gamma, float eps,
-                     const float* __restrict__ s_in, float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
-                     float4* __restrict__ coef, unsigned* __restrict__ kmax) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+                     float4* __restrict__ coef, double2* __restrict__ tmp, unsigned* __restrict__ kmax) {
+  __shared__ double red[2][8][33];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl, g = blockIdx.y;
+  double S0 = 0.0, S1 = 0.0;
+  if (c < C) {
+    for (int b = bl; b < nblk; b += 8) {
+      const long long base = (static_cast<long long>(g) * nblk + b) * 3 * C;
+      S0 += partial[base + c];
+      S1 += partial[base + static_cast<long long>(which) * C + c];
+    }
+  }
+  red[0][bl][cl] = S0;
+  red[1][bl][cl] = S1;
+  __syncthreads();
+  if (bl != 0) return;
   float km = 0.f;
   if (c < C) {
-    double gsum = 0.0, bsum = 0.0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { S0 += red[0][q][cl]; S1 += red[1][q][cl]; }
     const double gam = gamma ? static_cast<double>(gamma[c]) : 1.0;
-    for (int g = 0; g < G; ++g) {
-      double S0 = 0.0, S1 = 0.0;
-      for (int b = 0; b < nblk; ++b) {
-        const long long base = (static_cast<long long>(g) * nblk + b) * 3 * C;
-        S0 += partial[base + c];
-        S1 += partial[base + static_cast<long long>(which) * C + c];
-      }
-      const float2 mv = stats[static_cast<long long>(g) * C + c];
-      const double mean = mv.x, invstd = 1.0 / sqrt(static_cast<double>(mv.y) + eps);
-      const double dgam = invstd * (S1 - mean * S0);
-      const double k0 = gam * invstd;
-      const double k1 = -k0 * invstd * dgam * inv_m;
-      const double k2 = -k0 * S0 * inv_m - k1 * mean;
-      coef[static_cast<long long>(g) * C + c] = make_float4(static_cast<float>(k0), static_cast<float>(k1), static_cast<float>(k2), 0.f);
-      km = fmaxf(km, fabsf(static_cast<float>(k0)));
-      gsum += dgam;
-      bsum += S0;
-    }
-    const double inv_s = 1.0 / static_cast<double>(*s_in);
-    if (grad_gamma) grad_gamma[c] += static_cast<float>(gsum * inv_s);
-    if (grad_beta) grad_beta[c] += static_cast<float>(bsum * inv_s);
+    const float2 mv = stats[static_cast<long long>(g) * C + c];
+    const double mean = mv.x, invstd = 1.0 / sqrt(static_cast<double>(mv.y) + eps);
+    const double dgam = invstd * (S1 - mean * S0);
+    const double k0 = gam * invstd;
+    const double k1 = -k0 * invstd * dgam * inv_m;
+    const double k2 = -k0 * S0 * inv_m - k1 * mean;
+    coef[static_cast<long long>(g) * C + c] = make_float4(static_cast<float>(k0), static_cast<float>(k1), static_cast<float>(k2), 0.f);
+    tmp[static_cast<long long>(g) * C + c] = make_double2(dgam, S0);
+    km = fabsf(static_cast<float>(k0));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
-  if ((threadIdx.x & 31) == 0 && km > 0.f && isfinite(km)) atomicMax(kmax, __float_as_uint(km));
+  if (cl == 0 && km > 0.f && isfinite(km)) atomicMax(kmax, __float_as_uint(km));
+}
+
+// grad_gamma += sum_g dgamma / s ; grad_beta += sum_g sum(dz) / s (fixed summation order: deterministic)
+__global__ void __launch_bounds__(128)
+bn_bwd_affine_kernel(const double2* __restrict__ tmp, int G, int C, const float* __restrict__ s_in,
+                     float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double gs = 0.0, bs = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const double2 t = tmp[static_cast<long long>(g) * C + c];
+    gs += t.x;
+    bs += t.y;
+  }
+  const double inv_s = 1.0 / static_cast<double>(*s_in);
+  if (grad_gamma) grad_gamma[c] += static_cast<float>(gs * inv_s);
+  if (grad_beta) grad_beta[c] += static_cast<float>(bs * inv_s);
 }
 
 __device__ __forceinline__ float pow2_rescale(const unsigned* amax, const unsigned* kmax, float target) {
@@ -563,14 +583,20 @@ int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const fl
 
 int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int which, const float* batch_stats,
                        const float* gamma, float eps, const float* s_in, float* grad_gamma, float* grad_beta, float* coef,
-                       unsigned int* kmax, void* stream) {
-  MAUV_CHECK_ARG(partial && batch_stats && s_in && coef && kmax && (which == 1 || which == 2), "mauv_bn_bwd_coeffs: bad argument");
+                       unsigned int* kmax, void* ws, void* stream) {
+  MAUV_CHECK_ARG(partial && batch_stats && s_in && coef && kmax && ws && (which == 1 || which == 2), "mauv_bn_bwd_coeffs: bad argument");
+  MAUV_CHECK_ARG(G >= 1 && G <= 65535, "mauv_bn_bwd_coeffs: G out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MAUV_CUDA(cudaMemsetAsync(kmax, 0, sizeof(unsigned), st));
-  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, G, mauv_bn_bwd_blocks(M), C, which, 1.0 / static_cast<double>(M),
-                                                        reinterpret_cast<const float2*>(batch_stats), gamma, eps, s_in,
-                                                        grad_gamma, grad_beta, reinterpret_cast<float4*>(coef), kmax);
+  dim3 grid((C + 31) / 32, G);
+  bn_bwd_coeffs_kernel<<<grid, 256, 0, st>>>(partial, mauv_bn_bwd_blocks(M), C, which, 1.0 / static_cast<double>(M),
+                                             reinterpret_cast<const float2*>(batch_stats), gamma, eps,
+                                             reinterpret_cast<float4*>(coef), static_cast<double2*>(ws), kmax);
   MAUV_LAUNCH_CHECK("bn_bwd_coeffs_kernel");
+  if (grad_gamma || grad_beta) {
+    bn_bwd_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(static_cast<const double2*>(ws), G, C, s_in, grad_gamma, grad_beta);
+    MAUV_LAUNCH_CHECK("bn_bwd_affine_kernel");
+  }
   return MAUV_OK;
 }
 

@@ -57,7 +57,7 @@ SIGNATURES = {
     "mauv_avgpool_x3_f16": (i32, [vp, i64, i32, i32, vp, vp]),
     "mauv_bn_bwd_blocks": (i32, [i64]),
     "mauv_bn_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp]),
-    "mauv_bn_bwd_coeffs": (i32, [vp, i32, i64, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+    "mauv_bn_bwd_coeffs": (i32, [vp, i32, i64, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp]),
     "mauv_bn_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i64, i32, vp, vp, vp, vp, vp, vp]),
     "mauv_maxpool_bwd_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "mauv_avgpool_bwd_f16": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),

@@ -466,7 +466,7 @@ def sampled_linear_bwd_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, gra
 
 # ------------------------------------------------------------------ S-batched training backward
 GRAD_TARGET = 16.0   # amax the fp16 gradient tensors are renormalised to at every BatchNorm site
-KERNELS_PER_CALL.update({"mauv_avgpool_bwd_f16": 2, "mauv_sampled_linear_bwd_group_f32": 2})
+KERNELS_PER_CALL.update({"mauv_avgpool_bwd_f16": 2, "mauv_sampled_linear_bwd_group_f32": 2, "mauv_bn_bwd_coeffs": 2})
 
 
 class GradScratch:
@@ -503,15 +503,16 @@ def bn_bwd_site(gs: GradScratch, d1, s1, y, batch_stats, gamma, bn_eps, grad_gam
     _run("mauv_bn_bwd_reduce", lib.mauv_bn_bwd_reduce, _ptr(d1, F16), _ptr(d2, F16), s1, s2, _ptr(relu_out, F16), _ptr(y, F16),
          _ptr(y2, F16), G, M, C, _ptr(partial), amax, st)
     coef = torch.empty((G, C, 4), dtype=F32, device=dev)
+    ws = torch.empty((G, C, 2), dtype=torch.float64, device=dev)
     kmax = gs.slot()
     _run("mauv_bn_bwd_coeffs", lib.mauv_bn_bwd_coeffs, _ptr(partial), G, M, C, 1, _ptr(batch_stats, F32), _ptr(gamma, F32), bn_eps,
-         s1, _ptr(grad_gamma, F32), _ptr(grad_beta, F32), _ptr(coef), kmax, st)
+         s1, _ptr(grad_gamma, F32), _ptr(grad_beta, F32), _ptr(coef), kmax, _ptr(ws), st)
     coef2 = kmax2 = dy2 = s_out2 = None
     if y2 is not None:
         coef2 = torch.empty((G, C, 4), dtype=F32, device=dev)
         kmax2 = gs.slot()
         _run("mauv_bn_bwd_coeffs", lib.mauv_bn_bwd_coeffs, _ptr(partial), G, M, C, 2, _ptr(batch_stats2, F32), _ptr(gamma2, F32),
-             bn_eps2, s1, _ptr(grad_gamma2, F32), _ptr(grad_beta2, F32), _ptr(coef2), kmax2, st)
+             bn_eps2, s1, _ptr(grad_gamma2, F32), _ptr(grad_beta2, F32), _ptr(coef2), kmax2, _ptr(ws), st)
         dy2 = torch.empty_like(y2)
         s_out2 = gs.slot()
     dy = torch.empty_like(y)

@@ -72,27 +72,43 @@ def train_multimodal_model(multimodal_model: nn.Module, dataloader, criterion: n
             kl_weight = (2 ** (epoch + 1)) / (2 ** total_num_epochs)
             module = multimodal_model.module if isinstance(
                 multimodal_model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else multimodal_model
+            engine = train_engine_for(module, criterion)
             for i, batch in enumerate(dataloader):
                 logging.info(f"Train batch {i+1}/{len(dataloader)} - Model: {model_type}")
                 inputs, labels, bathy_patch, sss_patch = _select_patches(batch, device, bathy_patch_type, sss_patch_type)
-                output_ensemble = [module(inputs, bathy_patch, sss_patch) for _ in range(num_mc)]
-                # KL(q||p) does not depend on eps: the reference's S get_kl_loss calls return the same value S times
-                # (train/multimodal.py:114,124 mean over them); one fused launch computes it once.
-                kl = get_kl_loss(module)
-                output = torch.mean(torch.stack(output_ensemble), dim=0)
-                scaled_kl = kl / dataloader.batch_size * kl_weight
-                cross_entropy_loss = criterion(output, labels)
-                loss = cross_entropy_loss + scaled_kl
-                if torch.any(torch.isnan(loss)) or torch.any(torch.isinf(loss)):
-                    logging.warning(f"Skipping batch {i} due to NaN/Inf loss: {loss}")
-                    continue
-                loss.backward()
-                if not any(torch.any(torch.isnan(p.grad)) or torch.any(torch.isinf(p.grad))
-                           for p in multimodal_model.parameters() if p.grad is not None):
-                    optimizer.step()
-                    optimizer.zero_grad()
+                if engine is not None:
+                    # S-batched step (train_engine.py): one grouped forward + one grouped backward for all num_mc passes
+                    res = engine.step((inputs, bathy_patch, sss_patch), labels, num_mc, kl_weight / dataloader.batch_size)
+                    output, cross_entropy_loss, loss = res["mean_logit"], res["ce"], res["loss"]
+                    scaled_kl = res["kl"] / dataloader.batch_size * kl_weight
+                    if not bool(torch.isfinite(loss)):
+                        logging.warning(f"Skipping batch {i} due to NaN/Inf loss: {loss}")
+                        engine.zero_grad()       # the engine has already accumulated this batch's gradients: drop them
+                        continue
+                    if bool(engine.grads_finite()):
+                        optimizer.step()
+                        engine.zero_grad()
+                    else:
+                        logging.warning("Skipping optimizer step due to NaN/Inf gradients")
                 else:
-                    logging.warning("Skipping optimizer step due to NaN/Inf gradients")
+                    output_ensemble = [module(inputs, bathy_patch, sss_patch) for _ in range(num_mc)]
+                    # KL(q||p) does not depend on eps: the reference's S get_kl_loss calls return the same value S times
+                    # (train/multimodal.py:114,124 mean over them); one fused launch computes it once.
+                    kl = get_kl_loss(module)
+                    output = torch.mean(torch.stack(output_ensemble), dim=0)
+                    scaled_kl = kl / dataloader.batch_size * kl_weight
+                    cross_entropy_loss = criterion(output, labels)
+                    loss = cross_entropy_loss + scaled_kl
+                    if torch.any(torch.isnan(loss)) or torch.any(torch.isinf(loss)):
+                        logging.warning(f"Skipping batch {i} due to NaN/Inf loss: {loss}")
+                        continue
+                    loss.backward()
+                    if not any(torch.any(torch.isnan(p.grad)) or torch.any(torch.isinf(p.grad))
+                               for p in multimodal_model.parameters() if p.grad is not None):
+                        optimizer.step()
+                        optimizer.zero_grad()
+                    else:
+                        logging.warning("Skipping optimizer step due to NaN/Inf gradients")
                 total_loss += loss.item()
                 _, predicted = torch.max(output, 1)
                 correct += (predicted == labels).sum().item()
@@ -112,6 +128,28 @@ def train_multimodal_model(multimodal_model: nn.Module, dataloader, criterion: n
         logging.error(f"Error at epoch {epoch}", exc_info=True)
         train_loss, train_accuracy = 0.0, 0.0
     return train_loss, train_accuracy
+
+
+def train_engine_for(module: nn.Module, criterion) -> Optional["TrainEngine"]:
+    """The S-batched TrainEngine for `module` (cached on it), or None when the step cannot be expressed by it: a criterion
+    other than plain mean-reduced nn.CrossEntropyLoss, a topology other than the reference's two model classes, or
+    MAUV_TRAIN_PATH=layers. None selects the drop-in layer path (same CUDA kernels, one pass at a time)."""
+    from ..train_engine import TrainEngine
+    from .._lib import MauvError
+    if os.environ.get("MAUV_TRAIN_PATH", "engine") == "layers":
+        return None
+    plain_ce = (type(criterion) is nn.CrossEntropyLoss and criterion.weight is None and criterion.reduction == "mean"
+                and getattr(criterion, "label_smoothing", 0.0) == 0.0 and criterion.ignore_index == -100)
+    if not plain_ce:
+        return None
+    eng = module.__dict__.get("_mauv_train_engine")
+    if eng is None:
+        try:
+            eng = TrainEngine(module)
+        except MauvError:
+            return None
+        module.__dict__["_mauv_train_engine"] = eng
+    return eng
 
 
 def evaluate_multimodal_model(multimodal_model: nn.Module, dataloader, device: torch.device, epoch: int,

@@ -15,7 +15,7 @@ from torch import nn
 from .. import ops
 from ..bayesian import get_kl_loss
 from ..engine import MCEngine
-from .multimodal import _confusion_matrix_png, _save_model
+from .multimodal import _confusion_matrix_png, _save_model, train_engine_for
 
 
 def _pick_input(batch, device, model_type):
@@ -44,18 +44,26 @@ def train_unimodal_model(model: nn.Module, dataloader, criterion: nn.Module, opt
             if not file_exists:
                 writer.writerow(["Epoch", "Model type", "Loss", "Accuracy", "lr"])
             total_loss, correct, total = 0, 0, 0
+            module = model.module if isinstance(model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else model
+            engine = train_engine_for(module, criterion)
             for i, batch in enumerate(dataloader):
                 logging.info(f"Train batch {i+1}/{len(dataloader)} - Model: {model_type}")
                 model_input, labels = _pick_input(batch, device, model_type)
-                optimizer.zero_grad()
-                outputs = [model(model_input) for _ in range(num_mc)]
-                kl = get_kl_loss(model)                     # eps-independent: S identical terms in the reference
-                output = torch.mean(torch.stack(outputs), dim=0)
-                scaled_kl = kl / dataloader.batch_size
-                cross_entropy_loss = criterion(output, labels)
-                loss = cross_entropy_loss + (kl_weight * scaled_kl)
-                loss.backward()
-                optimizer.step()
+                if engine is not None:
+                    engine.zero_grad()
+                    res = engine.step((model_input,), labels, num_mc, kl_weight / dataloader.batch_size)
+                    output, loss = res["mean_logit"], res["loss"]
+                    optimizer.step()
+                else:
+                    optimizer.zero_grad()
+                    outputs = [model(model_input) for _ in range(num_mc)]
+                    kl = get_kl_loss(model)                     # eps-independent: S identical terms in the reference
+                    output = torch.mean(torch.stack(outputs), dim=0)
+                    scaled_kl = kl / dataloader.batch_size
+                    cross_entropy_loss = criterion(output, labels)
+                    loss = cross_entropy_loss + (kl_weight * scaled_kl)
+                    loss.backward()
+                    optimizer.step()
                 _, predicted = output.float().max(1)
                 total_loss += loss.item()
                 correct += (predicted == labels).sum().item()

@@ -72,6 +72,7 @@ class TrainEngine(MCEngine):
         super().__init__(model, max_group=max_group, precision="fp16")
         self._kl_plan = None
         self._bayes = [l for _, l in bayesian_layers(self.model)]
+        self._sample_cursor = max([l._calls for l in self._bayes] + [0])
 
     # ------------------------------------------------------------------ forward with tape
     def _conv_bn_rec(self, c: _Conv, bn, x, G, B, s0, eps, seed) -> tuple:
@@ -279,7 +280,59 @@ class TrainEngine(MCEngine):
             tape["trunks"][i] = None          # free this trunk's activations
 
     # ------------------------------------------------------------------ public
+    def flatten_grads(self) -> torch.Tensor:
+        """Re-home every `.grad` into ONE contiguous fp32 buffer: one memset per step, one NCCL all-reduce per step."""
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        offs, tot = [], 0
+        for p in params:
+            offs.append(tot)
+            tot += (p.numel() + 31) // 32 * 32
+        flat = torch.zeros(tot, dtype=F32, device=self.device)
+        self._grad_views = []
+        for p, o in zip(params, offs):
+            v = flat[o:o + p.numel()].view_as(p)
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+            self._grad_views.append((p, v))
+        self._flat_grad = flat
+        return flat
+
+    def zero_grad(self) -> None:
+        if getattr(self, "_flat_grad", None) is not None:
+            self._flat_grad.zero_()
+            for p, v in self._grad_views:
+                p.grad = v
+        else:
+            for p in self.model.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    def allreduce_grads(self, group=None) -> None:
+        """Data-parallel exchange (minibatch split over ranks, all S samples on every rank): gradients are
+        averaged over the ranks, one NCCL all-reduce over the flat buffer."""
+        import torch.distributed as dist
+        if getattr(self, "_flat_grad", None) is None:
+            self.flatten_grads()
+        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG, group=group)
+
+    def grads_finite(self) -> torch.Tensor:
+        """0-d bool tensor (device): the reference's per-parameter NaN/Inf guard (train/multimodal.py:141-145) in one pass."""
+        if getattr(self, "_flat_grad", None) is not None:
+            return torch.isfinite(self._flat_grad).all()
+        return torch.stack([torch.isfinite(p.grad).all() for p in self.model.parameters() if p.grad is not None]).all()
+
     def _ensure_grads(self):
+        flat = getattr(self, "_flat_grad", None)
+        if flat is not None:
+            missing = [(p, v) for p, v in self._grad_views if p.grad is None]
+            if len(missing) == len(self._grad_views):
+                flat.zero_()                       # optimizer.zero_grad(set_to_none=True) dropped the views
+            for p, v in missing:
+                if len(missing) != len(self._grad_views):
+                    v.zero_()
+                p.grad = v
+            return
         for p in self.model.parameters():
             if p.requires_grad and p.grad is None:
                 p.grad = torch.zeros_like(p)
@@ -302,12 +355,20 @@ class TrainEngine(MCEngine):
         return self._kl_plan.run(self._prior[0], self._prior[1], grad_scale=grad_scale)
 
     @torch.no_grad()
-    def step(self, inputs: Sequence[torch.Tensor], labels: torch.Tensor, S: int, kl_scale: float, *, sample0: int = 0,
-             eps: Optional[dict] = None, seed: Optional[int] = None) -> dict:
+    def step(self, inputs: Sequence[torch.Tensor], labels: torch.Tensor, S: int, kl_scale: float, *,
+             sample0: Optional[int] = None, eps: Optional[dict] = None, seed: Optional[int] = None) -> dict:
         """One ELBO minibatch: loss = CE(mean_s logits_s, labels) + kl_scale * KL; gradients ACCUMULATE into `.grad`.
         -> {"loss", "ce", "kl" (unscaled), "mean_logit" [B, C]} (device tensors; nothing is synchronised)."""
         seed = current_seed() if seed is None else seed
         stale = reference_stale_eps()
+        if sample0 is None:                   # fresh Philox sample ids every step, in step with the layers' own counters
+            sample0 = self._sample_cursor
+            self._sample_cursor += S
+            for l in self._bayes:
+                l._calls += S
+        if eps is None:
+            from . import engine as _engine
+            eps = _engine.DEBUG_EPS               # test hook: injected eps instead of Philox (see engine.py)
         xs = [x.to(self.device, F32).contiguous() for x in inputs]
         labels = labels.to(self.device, torch.int64).contiguous()
         G = min(self.max_group, S)

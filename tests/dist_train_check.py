@@ -49,6 +49,30 @@ for n, g in got.items():
     worst = max(worst, ((g - ref).abs().max() / (ref.abs().max() + 1e-30)).item())
 ok = worst < 2e-2          # BN running statistics differ between the runs; gradients only through fp16 transport noise
 print(f"rank {rank}/{world}: DDP gradient == mean of shard gradients, worst rel-to-max deviation {worst:.2e} -> {ok}", flush=True)
+
+# ---- the S-batched engine: shard gradients averaged by ONE all-reduce over the flat gradient buffer
+from mauv.train_engine import TrainEngine
+eng = TrainEngine(model)
+eng.flatten_grads()
+kl_scale = O.kl_weight(1, 20) / B
+
+
+def estep(sl, reduce):
+    eng.zero_grad()
+    eng.step([t[sl].cuda() for t in (img, bathy, sss)], labels[sl], S, kl_scale, sample0=0)
+    if reduce:
+        eng.allreduce_grads()
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+e0, e1 = estep(slice(0, B // 2), False), estep(slice(B // 2, B), False)
+got = estep(slice(lo, hi), True)
+worst_e = 0.0
+for n, g in got.items():
+    ref = 0.5 * (e0[n] + e1[n])
+    worst_e = max(worst_e, ((g - ref).abs().max() / (ref.abs().max() + 1e-30)).item())
+ok_e = worst_e < 1e-5
+print(f"rank {rank}/{world}: engine all-reduced gradient == mean of shard gradients, worst deviation {worst_e:.2e} -> {ok_e}", flush=True)
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if (ok and ok_e) else 1)

@@ -670,7 +670,7 @@ def _grad_table(tag, named_a, named_b, show=12):
     return rows
 
 
-def t_train_engine(S=2, B=2, size=64, kind="multimodal", stale=False, vs_oracle=True):
+def t_train_engine(S=2, B=2, size=64, kind="multimodal", stale=False, vs_oracle=True, logit_tol=None):
     """TrainEngine (S-batched forward + hand-written backward) vs the drop-in layer path (torch autograd over the same
     CUDA layer kernels) and vs the oracle's fp32 autograd, identical injected eps."""
     import bnn_oracle as O
@@ -705,22 +705,15 @@ def t_train_engine(S=2, B=2, size=64, kind="multimodal", stale=False, vs_oracle=
         model.load_state_dict(state0)
         model.zero_grad(set_to_none=True)
         eng = TrainEngine(model)
-        res = eng.step(xs, labels, S, kl_scale, eps=eps)
+        res = eng.step(xs, labels, S, kl_scale, eps=eps, sample0=0)
         torch.cuda.synchronize()
         g_eng = {n: p.grad.clone() for n, p in model.named_parameters()}
         tag = f"train_engine {kind} S={S} B={B} {size}px stale={stale}"
         print(f"{tag}: loss engine {res['loss'].item():.6f} layer-path {loss_l.item():.6f}")
-        report(tag + " logits vs layer path", res["logits"], torch.stack(outs_g), 2e-2)
+        report(tag + " logits vs layer path", res["logits"], torch.stack(outs_g), logit_tol)
         report(tag + " loss vs layer path", res["loss"].reshape(1), loss_l.detach().reshape(1), 2e-3)
         rows = _grad_table("engine vs layer path", g_eng, g_layer)
-        bad = [r for r in rows if not (r[0] > 0.90)]
-        if any(not math.isfinite(r[0]) for r in rows) or len(bad) > len(rows) // 10:
-            FAILS.append((tag, f"{len(bad)} of {len(rows)} parameter gradients below cos 0.90 vs the layer path"))
-        head = [r for r in rows if not r[2].split(".")[0].endswith("_feat") and not r[2].startswith("model.layer")
-                and not r[2].startswith("model.conv1") and not r[2].startswith("model.bn1")]
-        for r in head:
-            if r[0] < 0.999:
-                FAILS.append((tag, f"head gradient {r[2]} cos {r[0]:.4f} vs the layer path"))
+        result = {"vs_layer": rows, "vs_oracle": None, "layer_vs_oracle": None, "res": res}
         if vs_oracle:
             o_model.train()
             outs = []
@@ -732,8 +725,9 @@ def t_train_engine(S=2, B=2, size=64, kind="multimodal", stale=False, vs_oracle=
             loss_o.backward()
             g_or = {n: p.grad for n, p in o_model.named_parameters()}
             print(f"   loss oracle {loss_o.item():.6f}")
-            _grad_table("engine vs oracle", g_eng, g_or)
-            _grad_table("layer path vs oracle", g_layer, g_or, show=4)
+            result["vs_oracle"] = _grad_table("engine vs oracle", g_eng, g_or)
+            result["layer_vs_oracle"] = _grad_table("layer path vs oracle", g_layer, g_or, show=4)
+        return result
     finally:
         O.STALE_EPS_QUIRK = True
         MB.set_reference_stale_eps(False)
