@@ -201,8 +201,11 @@ int mauv_avgpool_x3_f16(const void* x2, long long N, int HW, int C, float* out, 
  * device-resident power-of-two scale each (value = true gradient * *scale): every BatchNorm site renormalises the scale
  * from the amax it measures, no host round trip. "Upstream" of a site = d1 (scale *s1) + optional d2 (scale *s2, e.g. the
  * identity branch of the residual), masked by relu_out > 0 when relu_out is given. C: power of two in [64, 2048]. */
-/* number of row blocks pass 1 uses for M rows per sample (sizes `partial`: [G][blocks][3][C] floats) */
-int mauv_bn_bwd_blocks(long long M);
+/* number of row blocks pass 1 uses for G samples of M rows, C channels (sizes `partial`: [G][blocks][3][C] floats) */
+int mauv_bn_bwd_blocks(int G, long long M, int C);
+/* forward sample w [G][cout][kh*kw*cin] (mauv_sample_weights_f16) -> the data-gradient operand [G][cin][kh*kw*cout] with the
+ * taps flipped (same layout as mauv_sample_weights_dgrad_f16, without replaying the noise). cout, cin % 8 == 0. */
+int mauv_weights_to_dgrad_f16(const void* w, int G, int cout, int cin, int kh, int kw, void* w_out, void* stream);
 /* pass 1: partial[g][blk][0..2][c] = sum dz, sum dz*y, sum dz*y2 (y2 nullable); *amax = max|dz| as float bits. */
 int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
                        const void* y2, int G, long long M, int C, float* partial, unsigned int* amax, void* stream);
@@ -219,9 +222,11 @@ int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const flo
                       const void* y2, const float* coef, const float* coef2, const unsigned int* amax,
                       const unsigned int* kmax, const unsigned int* kmax2, float target, int G, long long M, int C, void* dy,
                       void* dy2, void* dz, float* s_out, float* s_out2, void* stream);
-/* backward of maxpool3x3/2(relu(y*scale+shift)) (torchvision resnet.py stem): dz [G*imgs][H][W][C] at scale *s1. */
+/* backward of maxpool3x3/2(relu(y*scale+shift)) (torchvision resnet.py stem): dz [G*imgs][H][W][C] at scale *s1.
+ * idx_ws: G*imgs*Ho*Wo*C bytes (per-window arg-max positions, written by the first of the two launches). */
 int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1, const void* d2, const float* s1,
-                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* dz, void* stream);
+                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* idx_ws, void* dz,
+                         void* stream);
 /* backward of the global average pool: dfeat [N][C] fp32 -> out [N][HW][C] fp16 = dfeat/HW * r, *s_out = r (first scale). */
 int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
                          float* s_out, void* stream);

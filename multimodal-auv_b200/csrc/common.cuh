@@ -276,6 +276,22 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t layer_id,
   return (which & 1u) ? rad * s : rad * c;
 }
 
+// Four N(0,1) values of one Philox counter block: elements 4*quad .. 4*quad+3 of (seed, layer, sample).
+__device__ __forceinline__ void philox_normals4(uint64_t seed, uint32_t layer_id, uint32_t sample_id, uint64_t quad,
+                                                float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), sample_id, layer_id,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float k = 1.0f / 16777216.0f;
+  const float ra = sqrtf(-2.0f * logf((static_cast<float>(r[0] >> 8) + 0.5f) * k));
+  const float rb = sqrtf(-2.0f * logf((static_cast<float>(r[2] >> 8) + 0.5f) * k));
+  float s, c;
+  sincospif(2.0f * ((static_cast<float>(r[1] >> 8) + 0.5f) * k), &s, &c);
+  z[0] = ra * c; z[1] = ra * s;
+  sincospif(2.0f * ((static_cast<float>(r[3] >> 8) + 0.5f) * k), &s, &c);
+  z[2] = rb * c; z[3] = rb * s;
+}
+
 // sigma = log1p(exp(rho)) exactly as the reference computes it (no threshold).
 __device__ __forceinline__ float softplus_ref(float rho) { return log1pf(expf(rho)); }
 

@@ -233,11 +233,53 @@ bn_bwd_apply_kernel(const ApplyArgs a) {
 }
 
 // ---------------------------------------------------------------- stem: backward of maxpool3x3/2(relu(bn(y)))
-// dz[n,h,w,c] = [z>0] * sum over the <=4 pooling windows containing (h,w) of d[n,p,q,c] * [(h,w) is the window's arg-max]
-// (first maximum in row-major scan order wins, as ATen's max_pool2d); z = relu(y*scale+shift) recomputed.
+// Pass A (pooled-output centric, the forward's access pattern): arg-max position 0..8 of every 3x3 window per channel
+// (first maximum in row-major scan order wins, as ATen's max_pool2d), 15 when the window maximum is <= 0 (ReLU kills it).
+__global__ void __launch_bounds__(128, 5)
+maxpool_argmax_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, int imgs_per_sample, int H, int W, int C,
+                      int Ho, int Wo, uint2* __restrict__ idx) {
+  const int cvec = C >> 3;
+  const int p = blockIdx.x;
+  const long long n = blockIdx.y;
+  const int g = static_cast<int>(n / imgs_per_sample);
+  const int per_row = Wo * cvec;
+  for (int t = threadIdx.x; t < per_row; t += blockDim.x) {
+    const int cv = t % cvec;
+    const int q = t / cvec;
+    float sc[8], sh[8], m[8];
+    uint32_t am[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 s = ss[static_cast<long long>(g) * C + cv * 8 + j];
+      sc[j] = s.x; sh[j] = s.y; m[j] = 0.f; am[j] = 15u;     // only strictly positive values can win
+    }
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr) {
+#pragma unroll
+      for (int ds = 0; ds < 3; ++ds) {
+        const int h = p * 2 - 1 + dr, w = q * 2 - 1 + ds;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          float f[8];
+          unpack8(__ldg(y + ((n * H + h) * W + w) * cvec + cv), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = fmaf(f[j], sc[j], sh[j]);
+            if (v > m[j]) { m[j] = v; am[j] = dr * 3 + ds; }
+          }
+        }
+      }
+    }
+    uint2 o;
+    o.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+    o.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+    idx[((n * Ho + p) * Wo + q) * cvec + cv] = o;
+  }
+}
+
+// Pass B (stem-element centric gather): dz[n,h,w,c] = sum over the <= 4 windows containing (h,w) of d[n,p,q,c] * [idx == me]
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, Upstream u, int imgs_per_sample, int H, int W,
-                   int C, int Ho, int Wo, long long total, uint4* __restrict__ dz) {
+maxpool_bwd_kernel(const uint2* __restrict__ idx, Upstream u, int H, int W, int C, int Ho, int Wo, long long total,
+                   uint4* __restrict__ dz) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int lanes = C >> 3;
@@ -246,49 +288,26 @@ maxpool_bwd_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, U
   const int w = static_cast<int>(t % W); t /= W;
   const int h = static_cast<int>(t % H);
   const long long n = t / H;
-  const int g = static_cast<int>(n / imgs_per_sample);
   const float ratio = upstream_ratio(u);
-  float sc[8], sh[8], self[8], acc[8];
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float2 s = ss[static_cast<long long>(g) * C + cv * 8 + j];
-    sc[j] = s.x; sh[j] = s.y; acc[j] = 0.f;
-  }
-  {
-    float yv[8];
-    unpack8(__ldg(y + i), yv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) self[j] = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
-  }
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const int p_lo = h >> 1, p_hi = min((h + 1) >> 1, Ho - 1);
   const int q_lo = w >> 1, q_hi = min((w + 1) >> 1, Wo - 1);
+  Upstream un = u;
+  un.mask = nullptr;
   for (int p = p_lo; p <= p_hi; ++p) {
     for (int q = q_lo; q <= q_hi; ++q) {
-      bool is_max[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) is_max[j] = self[j] > 0.f;
-      for (int dr = 0; dr < 3; ++dr) {
-        const int hh = 2 * p - 1 + dr;
-        if (hh < 0 || hh >= H) continue;
-        for (int ds = 0; ds < 3; ++ds) {
-          const int ww = 2 * q - 1 + ds;
-          if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
-          float yv[8];
-          unpack8(__ldg(y + ((n * H + hh) * W + ww) * lanes + cv), yv);
-          const bool earlier = hh < h || (hh == h && ww < w);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
-            is_max[j] = is_max[j] && (earlier ? self[j] > v : self[j] >= v);
-          }
-        }
-      }
+      const uint32_t me = static_cast<uint32_t>((h - 2 * p + 1) * 3 + (w - 2 * q + 1));
+      const long long o = ((n * Ho + p) * Wo + q) * lanes + cv;
+      const uint2 id = __ldg(idx + o);
       float d[8];
-      Upstream un = u;
-      un.mask = nullptr;
-      load_dz(un, ((n * Ho + p) * Wo + q) * lanes + cv, ratio, d);
+      load_dz(un, o, ratio, d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += is_max[j] ? d[j] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
+        acc[j] += a == me ? d[j] : 0.f;
+      }
     }
   }
   dz[i] = pack8(acc);
@@ -325,43 +344,131 @@ avgpool_bwd_kernel(const float* __restrict__ dfeat, const unsigned* __restrict__
 }
 
 // ---------------------------------------------------------------- grouped weight-gradient finalisation
-// dw fp16 [G*splits][cout][Kp] (K order (r,s,c)), value = true dW * (*s) / inv_alpha
+// dw fp16 [G*splits][cout][Kp] (K order (r,s,c)), value = true dW * (*s) / inv_alpha.
+// Block = 32 element-quads x 8 sample lanes: a thread finalises 4 consecutive PyTorch-order elements (one Philox4x32 block
+// per sample) for the samples g = lane, lane+8, ...; the 8 lanes are then summed in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, int cout, int cin, int kh, int kw, int Kp,
                             float inv_alpha, const float* __restrict__ s, const float* __restrict__ rho,
                             const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0, int stale,
                             float* __restrict__ grad_mu, float* __restrict__ grad_rho) {
-  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  __shared__ float red[8][32][9];
+  const int ql = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const long long quad = static_cast<long long>(blockIdx.x) * 32 + ql;
+  const long long e0 = quad * 4;
   const int khw = kh * kw;
   const long long per_out = static_cast<long long>(cin) * khw;
   const long long n = per_out * cout;
-  if (e >= n) return;
-  const long long co = e / per_out;
-  const int rem = static_cast<int>(e - co * per_out);
-  const int c = rem / khw, rs = rem - c * khw;
-  const long long k = static_cast<long long>(rs) * cin + c;
-  float am = 0.f, ar = 0.f;
-  for (int g = 0; g < G; ++g) {
-    float d = 0.f;
-    for (int sp = 0; sp < splits; ++sp)
-      d += __half2float(dw[((static_cast<long long>(g) * splits + sp) * cout + co) * Kp + k]);
-    am += d;
-    if (!stale) {
-      const float z = eps ? eps[static_cast<long long>(g) * n + e]
-                          : philox_normal(seed, layer_id, sample0 + g, static_cast<uint64_t>(e));
-      ar = fmaf(d, z, ar);
+  const bool any = e0 < n;
+  long long off[4];
+  bool live[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long e = e0 + i;
+    live[i] = e < n;
+    const long long ee = live[i] ? e : 0;
+    const long long co = ee / per_out;
+    const int rem = static_cast<int>(ee - co * per_out);
+    const int c = rem / khw, rs = rem - c * khw;
+    off[i] = co * Kp + static_cast<long long>(rs) * cin + c;
+  }
+  const bool vec = khw == 1 && live[3] && (cin % 4 == 0) && (Kp % 4 == 0);     // 4 consecutive k: one 8-byte load
+  const long long gstride = static_cast<long long>(cout) * Kp;
+  float am[4] = {0.f, 0.f, 0.f, 0.f}, ar[4] = {0.f, 0.f, 0.f, 0.f};
+  if (any) {
+    for (int g = gl; g < G; g += 8) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int sp = 0; sp < splits; ++sp) {
+        const __half* base = dw + (static_cast<long long>(g) * splits + sp) * gstride;
+        if (vec) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + off[0]));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+          d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] += live[i] ? __half2float(__ldg(base + off[i])) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) am[i] += d[i];
+      if (!stale) {
+        float z[4];
+        if (eps) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) z[i] = live[i] ? eps[static_cast<long long>(g) * n + e0 + i] : 0.f;
+        } else {
+          philox_normals4(seed, layer_id, sample0 + g, static_cast<uint64_t>(quad), z);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ar[i] = fmaf(d[i], z[i], ar[i]);
+      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red[gl][ql][i] = am[i]; red[gl][ql][4 + i] = ar[i]; }
+  __syncthreads();
+  if (gl != 0 || !any) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { am[i] += red[q][ql][i]; ar[i] += red[q][ql][4 + i]; }
+  }
   if (stale) {   // reference quirk: the saved eps buffer holds the last pass's draw for every pass
-    const float z = eps ? eps[static_cast<long long>(G - 1) * n + e]
-                        : philox_normal(seed, layer_id, sample0 + G - 1, static_cast<uint64_t>(e));
-    ar = am * z;
+    float z[4];
+    if (eps) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = live[i] ? eps[static_cast<long long>(G - 1) * n + e0 + i] : 0.f;
+    } else {
+      philox_normals4(seed, layer_id, sample0 + G - 1, static_cast<uint64_t>(quad), z);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ar[i] = am[i] * z[i];
   }
   const float inv = inv_alpha / (*s);
-  const float ex = expf(rho[e]);
-  const float sgm = isinf(ex) ? 1.f : ex / (1.f + ex);
-  grad_mu[e] += am * inv;
-  grad_rho[e] += ar * inv * sgm;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!live[i]) continue;
+    const float ex = expf(rho[e0 + i]);
+    const float sgm = isinf(ex) ? 1.f : ex / (1.f + ex);
+    grad_mu[e0 + i] += am[i] * inv;
+    grad_rho[e0 + i] += ar[i] * inv * sgm;
+  }
+}
+
+// forward sample w [G][cout][K = (r,s,c)] -> data-gradient operand wd [G][cin][(kh*kw-1-rs)*cout + co]: a per-(sample, tap)
+// [cout x cin] -> [cin x cout] transpose through shared memory (replaces re-sampling the weights for the backward pass)
+__global__ void __launch_bounds__(256)
+weights_to_dgrad_kernel(const __half* __restrict__ w, int cout, int cin, int khw, __half* __restrict__ wd) {
+  __shared__ __half tile[64][66];
+  const int g = blockIdx.z;
+  const int cblocks = (cin + 63) >> 6;
+  const int rs = blockIdx.y / cblocks, c0 = (blockIdx.y - rs * cblocks) << 6;
+  const int co0 = blockIdx.x << 6;
+  const long long K = static_cast<long long>(khw) * cin, Kd = static_cast<long long>(khw) * cout;
+  const __half* src = w + static_cast<long long>(g) * cout * K;
+  __half* dst = wd + static_cast<long long>(g) * cin * Kd;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = (threadIdx.x >> 3) + it * 32, cv = threadIdx.x & 7;
+    const int co = co0 + row, c = c0 + cv * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (co < cout && c < cin) v = __ldg(reinterpret_cast<const uint4*>(src + co * K + static_cast<long long>(rs) * cin + c));
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(&tile[row][cv * 8]);
+    t32[0] = v.x; t32[1] = v.y; t32[2] = v.z; t32[3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int og = threadIdx.x & 7, cl = (threadIdx.x >> 3) + it * 32;
+    const int co = co0 + og * 8, c = c0 + cl;
+    if (co < cout && c < cin) {
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = tile[og * 8 + j][cl];
+      *reinterpret_cast<uint4*>(dst + c * Kd + static_cast<long long>(khw - 1 - rs) * cout + co) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- head backward, grouped over the G samples (fp32)
@@ -561,16 +668,31 @@ bool pow2_channels(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
 
 extern "C" {
 
-int mauv_bn_bwd_blocks(long long M) {
-  long long nb = (M + 511) / 512;
+int mauv_bn_bwd_blocks(int G, long long M, int C) {
+  // enough row blocks that G * blocks fills the GPU (~8 CTAs of 256 threads per SM), at least two row sweeps per block
+  const int rl = 256 / (C >> 3 > 0 ? C >> 3 : 1);
+  long long by_rows = (M + 2LL * rl - 1) / (2LL * rl);
+  long long by_fill = (static_cast<long long>(mauv_num_sms()) * 8 + G - 1) / G;
+  long long nb = by_rows < by_fill ? by_rows : by_fill;
   return static_cast<int>(nb < 1 ? 1 : (nb > 64 ? 64 : nb));
+}
+
+int mauv_weights_to_dgrad_f16(const void* w, int G, int cout, int cin, int kh, int kw, void* w_out, void* stream) {
+  MAUV_CHECK_ARG(w && w_out && G >= 1 && G <= 65535 && cout % 8 == 0 && cin % 8 == 0, "mauv_weights_to_dgrad_f16: bad argument");
+  const int khw = kh * kw;
+  dim3 grid((cout + 63) / 64, khw * ((cin + 63) / 64), G);
+  MAUV_CHECK_ARG(grid.y <= 65535, "mauv_weights_to_dgrad_f16: too many (tap, channel-block) pairs");
+  weights_to_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(w), cout, cin, khw,
+                                                                                static_cast<__half*>(w_out));
+  MAUV_LAUNCH_CHECK("weights_to_dgrad_kernel");
+  return MAUV_OK;
 }
 
 int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
                        const void* y2, int G, long long M, int C, float* partial, unsigned int* amax, void* stream) {
   MAUV_CHECK_ARG(d1 && s1 && y && partial && amax && (!d2 || s2), "mauv_bn_bwd_reduce: null pointer");
   MAUV_CHECK_ARG(pow2_channels(C) && G >= 1 && M >= 1, "mauv_bn_bwd_reduce: C must be a power of two in [64, 2048] (got %d)", C);
-  const int nblk = mauv_bn_bwd_blocks(M);
+  const int nblk = mauv_bn_bwd_blocks(G, M, C);
   const long long rpb = (M + nblk - 1) / nblk;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MAUV_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned), st));
@@ -589,7 +711,7 @@ int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int whic
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MAUV_CUDA(cudaMemsetAsync(kmax, 0, sizeof(unsigned), st));
   dim3 grid((C + 31) / 32, G);
-  bn_bwd_coeffs_kernel<<<grid, 256, 0, st>>>(partial, mauv_bn_bwd_blocks(M), C, which, 1.0 / static_cast<double>(M),
+  bn_bwd_coeffs_kernel<<<grid, 256, 0, st>>>(partial, mauv_bn_bwd_blocks(G, M, C), C, which, 1.0 / static_cast<double>(M),
                                              reinterpret_cast<const float2*>(batch_stats), gamma, eps,
                                              reinterpret_cast<float4*>(coef), static_cast<double2*>(ws), kmax);
   MAUV_LAUNCH_CHECK("bn_bwd_coeffs_kernel");
@@ -615,7 +737,7 @@ int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const flo
   a.dy = static_cast<uint4*>(dy); a.dy2 = static_cast<uint4*>(dy2); a.dz = static_cast<uint4*>(dz);
   a.s_out = s_out; a.s_out2 = s_out2; a.M = M; a.C = C;
   const long long vecs = M * (C / 8);
-  long long bx = ceil_div_i64(vecs, 256 * 4);
+  long long bx = ceil_div_i64(vecs, 256 * 16);   // >= 16 vectors per thread: the 48-float coefficient prologue amortises
   const long long cap = static_cast<long long>(mauv_num_sms()) * 8;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
@@ -626,13 +748,21 @@ int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const flo
 }
 
 int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1, const void* d2, const float* s1,
-                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* dz, void* stream) {
-  MAUV_CHECK_ARG(y && scale_shift && d1 && s1 && dz && (!d2 || s2) && C % 8 == 0, "mauv_maxpool_bwd_f16: bad argument");
+                         const float* s2, int G, int imgs_per_sample, int H, int W, int C, void* idx_ws, void* dz, void* stream) {
+  MAUV_CHECK_ARG(y && scale_shift && d1 && s1 && dz && idx_ws && (!d2 || s2) && C % 8 == 0, "mauv_maxpool_bwd_f16: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(G) * imgs_per_sample * H * W * (C / 8);
-  maxpool_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift), make_up(d1, d2, s1, s2, nullptr),
-      imgs_per_sample, H, W, C, Ho, Wo, total, static_cast<uint4*>(dz));
+  const long long imgs = static_cast<long long>(G) * imgs_per_sample;
+  MAUV_CHECK_ARG(imgs <= 65535, "mauv_maxpool_bwd_f16: at most 65535 images per call (got %lld)", imgs);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int threads = Wo * (C / 8);
+  threads = threads > 128 ? 128 : ((threads + 31) / 32) * 32;
+  maxpool_argmax_kernel<<<dim3(Ho, static_cast<unsigned>(imgs)), threads, 0, st>>>(
+      static_cast<const uint4*>(y), reinterpret_cast<const float2*>(scale_shift), imgs_per_sample, H, W, C, Ho, Wo,
+      static_cast<uint2*>(idx_ws));
+  MAUV_LAUNCH_CHECK("maxpool_argmax_kernel");
+  const long long total = imgs * H * W * (C / 8);
+  maxpool_bwd_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, st>>>(
+      static_cast<const uint2*>(idx_ws), make_up(d1, d2, s1, s2, nullptr), H, W, C, Ho, Wo, total, static_cast<uint4*>(dz));
   MAUV_LAUNCH_CHECK("maxpool_bwd_kernel");
   return MAUV_OK;
 }
@@ -659,7 +789,7 @@ int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cou
                               void* stream) {
   MAUV_CHECK_ARG(dw_partial && scale && rho && grad_mu && grad_rho && G >= 1 && splits >= 1, "mauv_wgrad_finalize_group: bad argument");
   const long long n = static_cast<long long>(cout) * cin * kh * kw;
-  wgrad_finalize_group_kernel<<<static_cast<unsigned>(ceil_div_i64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  wgrad_finalize_group_kernel<<<static_cast<unsigned>(ceil_div_i64(ceil_div_i64(n, 4), 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
       sample0, stale_eps, grad_mu, grad_rho);
   MAUV_LAUNCH_CHECK("wgrad_finalize_group_kernel");

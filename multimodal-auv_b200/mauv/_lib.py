@@ -55,11 +55,12 @@ SIGNATURES = {
     "mauv_bn_act_x3_f16": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp]),
     "mauv_bn_relu_maxpool_x3_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "mauv_avgpool_x3_f16": (i32, [vp, i64, i32, i32, vp, vp]),
-    "mauv_bn_bwd_blocks": (i32, [i64]),
+    "mauv_bn_bwd_blocks": (i32, [i32, i64, i32]),
+    "mauv_weights_to_dgrad_f16": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "mauv_bn_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp]),
     "mauv_bn_bwd_coeffs": (i32, [vp, i32, i64, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp]),
     "mauv_bn_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i64, i32, vp, vp, vp, vp, vp, vp]),
-    "mauv_maxpool_bwd_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_maxpool_bwd_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mauv_avgpool_bwd_f16": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
     "mauv_wgrad_finalize_group": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, u64, u32, u32, i32, vp, vp, vp]),
     "mauv_sampled_linear_bwd_group_f32": (i32, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32,

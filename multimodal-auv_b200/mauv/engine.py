@@ -316,6 +316,10 @@ class MCEngine:
         G = min(group or self.max_group, S)
         if eps is None:
             eps = DEBUG_EPS
+        with ops.on_current_stream():
+            return self._forward_mc(inputs, S, G, sample0, eps, seed)
+
+    def _forward_mc(self, inputs, S, G, sample0, eps, seed) -> torch.Tensor:
         outs = []
         stems = self.stem_matrices(inputs) if (S > G and self.precision == "fp16") else None
         for s in range(0, S, G):

@@ -23,8 +23,29 @@ def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
     return t.data_ptr()
 
 
+_stream_override = None
+
+
 def _stream() -> int:
+    if _stream_override is not None:
+        return _stream_override
     return torch.cuda.current_stream().cuda_stream
+
+
+class on_current_stream:
+    """Resolve torch's current stream ONCE for a whole engine walk (torch.cuda.current_stream() costs ~10 us per call,
+    a walk makes ~2 000 calls). Do not switch streams inside the block."""
+
+    def __enter__(self):
+        global _stream_override
+        self._prev = _stream_override
+        _stream_override = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        global _stream_override
+        _stream_override = self._prev
+        return False
 
 
 
@@ -408,6 +429,16 @@ def sample_weights_dgrad_f16(mu, rho, G, *, eps=None, seed=0, layer_id=0, sample
     return out
 
 
+def weights_to_dgrad_f16(w: torch.Tensor, cin: int, kh: int, kw: int) -> torch.Tensor:
+    """forward sample [G, cout, kh*kw*cin] -> [G, cin, kh*kw*cout] (taps flipped) for the data-gradient conv"""
+    lib = _lib.require_device()
+    G, cout, K = w.shape
+    assert K == kh * kw * cin
+    out = torch.empty((G, cin, kh * kw * cout), dtype=F16, device=w.device)
+    _run("mauv_weights_to_dgrad_f16", lib.mauv_weights_to_dgrad_f16, _ptr(w, F16), G, cout, cin, kh, kw, _ptr(out), _stream())
+    return out
+
+
 def dilate_f16(x: torch.Tensor, Hd: int, Wd: int, stride: int) -> torch.Tensor:
     lib = _lib.require_device()
     N, Ho, Wo, Cc = x.shape
@@ -466,7 +497,7 @@ def sampled_linear_bwd_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, gra
 
 # ------------------------------------------------------------------ S-batched training backward
 GRAD_TARGET = 16.0   # amax the fp16 gradient tensors are renormalised to at every BatchNorm site
-KERNELS_PER_CALL.update({"mauv_avgpool_bwd_f16": 2, "mauv_sampled_linear_bwd_group_f32": 2, "mauv_bn_bwd_coeffs": 2})
+KERNELS_PER_CALL.update({"mauv_avgpool_bwd_f16": 2, "mauv_sampled_linear_bwd_group_f32": 2, "mauv_bn_bwd_coeffs": 2, "mauv_maxpool_bwd_f16": 2})
 
 
 class GradScratch:
@@ -496,7 +527,7 @@ def bn_bwd_site(gs: GradScratch, d1, s1, y, batch_stats, gamma, bn_eps, grad_gam
     lib = _lib.require_device()
     M = y.numel() // (G * C)
     dev = y.device
-    nblk = lib.mauv_bn_bwd_blocks(M)
+    nblk = lib.mauv_bn_bwd_blocks(G, M, C)
     partial = torch.empty((G, nblk, 3, C), dtype=F32, device=dev)
     amax = gs.slot()
     st = _stream()
@@ -528,8 +559,9 @@ def maxpool_bwd_f16(y, ss, d1, s1, G, *, d2=None, s2=None) -> torch.Tensor:
     lib = _lib.require_device()
     NB, H, W, Cc = y.shape
     dz = torch.empty_like(y)
+    idx = torch.empty(d1.shape, dtype=torch.uint8, device=y.device)
     _run("mauv_maxpool_bwd_f16", lib.mauv_maxpool_bwd_f16, _ptr(y, F16), _ptr(ss, F32), _ptr(d1, F16), _ptr(d2, F16), s1, s2, G,
-         NB // G, H, W, Cc, _ptr(dz), _stream())
+         NB // G, H, W, Cc, _ptr(idx), _ptr(dz), _stream())
     return dz
 
 

@@ -34,6 +34,16 @@ from .engine import MCEngine, _Block, _Conv, _Trunk
 F16, F32 = torch.float16, torch.float32
 
 
+def _group_splits(M: int, G: int, cout: int, kp: int) -> int:
+    """Split-K factor of the grouped weight-gradient GEMM: with G samples on the batch axis only as many pixel chunks as
+    needed to give every SM a couple of output tiles (the layer path, G = 1, needs up to 32)."""
+    tiles = G * ((cout + 127) // 128) * ((kp + 255) // 256)
+    s, cap = 1, _splits(M)
+    while s < cap and tiles * s < 2 * 148:
+        s *= 2
+    return s
+
+
 @dataclass
 class _ConvRec:
     c: _Conv
@@ -41,6 +51,7 @@ class _ConvRec:
     x: torch.Tensor        # conv input, NHWC fp16 [G*B, H, W, Cin] (None for the stem: explicit im2col matrix instead)
     y: torch.Tensor        # raw conv output, NHWC fp16
     bs: torch.Tensor       # batch statistics (mean, biased var) [G, Cout, 2]
+    w: Optional[torch.Tensor] = None   # the forward weight samples [G, Cout, K] fp16 (re-laid-out for the data gradient)
 
 
 @dataclass
@@ -84,7 +95,7 @@ class TrainEngine(MCEngine):
         else:
             y, st = ops.conv2d_im2col_f16(x, w, G, c.k, c.k, c.stride, c.pad, stats=True)
         ss, bs = self._bn_stats(st, y.numel() // (G * c.cout), bn)
-        return _ConvRec(c, bn, x, y, bs), ss
+        return _ConvRec(c, bn, x, y, bs, w), ss
 
     def _bn_stats(self, stats, count, bn: nn.BatchNorm2d):
         if bn.weight is None or bn.bias is None:
@@ -166,7 +177,7 @@ class TrainEngine(MCEngine):
         M = (NB // G) * Ho * Wo
         if M % 8 != 0:
             raise _lib.MauvError(f"conv backward needs B*Ho*Wo to be a multiple of 8 (got {M}) at {c.name}")
-        splits = _splits(M)
+        splits = _group_splits(M, G, Cout, c.k * c.k * Cin)
         a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits)                      # [G*splits, Cout, Mc]
         if c.k == 1 and c.stride == 1:
             b_t = ops.transpose_chunks_f16(r.x.view(G * M, Cin), G * splits)                  # [G*splits, Cin, Mc]
@@ -179,7 +190,10 @@ class TrainEngine(MCEngine):
                                  eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0, stale=stale)
         if not need_dx:
             return None
-        wd = ops.sample_weights_dgrad_f16(mu, rho, G, eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0)
+        if r.w is not None:
+            wd = ops.weights_to_dgrad_f16(r.w, Cin, c.k, c.k)
+        else:
+            wd = ops.sample_weights_dgrad_f16(mu, rho, G, eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0)
         Hd, Wd = H + 2 * c.pad - c.k + 1, W + 2 * c.pad - c.k + 1
         dyd = dy if c.stride == 1 else ops.dilate_f16(dy, Hd, Wd, c.stride)
         if c.k == 1:
@@ -193,8 +207,8 @@ class TrainEngine(MCEngine):
         layer = c.layer
         NB, Ho, Wo, Cout = dy.shape
         M = (NB // G) * Ho * Wo
-        splits = _splits(M)
         Kp = tr.a0.shape[1]
+        splits = _group_splits(M, 1, Cout, Kp)
         b_t = ops.transpose_chunks_f16(tr.a0, splits)                                         # [splits, Kp, Mc] (all samples)
         a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits).view(G, splits, Cout, M // splits)
         dw = torch.empty((G, splits, Cout, Kp), dtype=F16, device=dy.device)
@@ -375,6 +389,10 @@ class TrainEngine(MCEngine):
         if stale and G < S:
             raise _lib.MauvError("reference stale-eps mode needs all S samples in one group (raise max_group)")
         self._ensure_grads()
+        with ops.on_current_stream():
+            return self._step(xs, labels, S, G, kl_scale, sample0, eps, seed, stale)
+
+    def _step(self, xs, labels, S, G, kl_scale, sample0, eps, seed, stale) -> dict:
         tapes, logits = [], []
         for s in range(0, S, G):
             g = min(G, S - s)

@@ -640,7 +640,10 @@ def t_conv_bwd_group(G, B, H, W, Cin, Cout, k, stride, pad, stale=False):
     stub = types.SimpleNamespace(device=torch.device(dev))
     stub._eps_w = lambda e, name, s0, g: MCEngine._eps_w(stub, e, name, s0, g)
     c = _Conv("conv", layer, 7, Cin, Cout, k, stride, pad)
-    rec = _ConvRec(c, None, x.to(dev), None, None)
+    w_fwd = None
+    if G % 2 == 0:      # even G: data gradient from the re-laid-out forward samples (training engine); odd G: re-sampled
+        w_fwd = ops.sample_weights_f16(layer.mu_kernel.detach(), layer.rho_kernel.detach(), G, eps=eps.to(dev).contiguous())
+    rec = _ConvRec(c, None, x.to(dev), None, None, w_fwd)
     dx = TrainEngine._conv_backward(stub, rec, dyh.to(dev), gs.f.data_ptr(), G, 0, {"conv": {"w": eps, "b": None}}, 1, stale)
     tag = f"conv_bwd_group G={G} B={B} {H}x{W} {Cin}->{Cout} k{k}/{stride} stale={stale}"
     report(tag + " dx", dx.float() / sc, xr.grad.reshape(G * B, Cin, H, W).permute(0, 2, 3, 1), 3e-3)
