@@ -230,6 +230,12 @@ int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1
 /* backward of the global average pool: dfeat [N][C] fp32 -> out [N][HW][C] fp16 = dfeat/HW * r, *s_out = r (first scale). */
 int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
                          float* s_out, void* stream);
+/* Weight gradient of the grouped conv straight from the NHWC tensors (no transposed copies): dy [G*imgs][Ho][Wo][Cout],
+ * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] fp16 partial sums over pixel chunks (K order (r, s, c)). Both
+ * operands enter the tcgen05 MMA MN-major from [64 pixels][64 channels] TMA boxes (tiled for 1x1/stride 1, im2col mode
+ * otherwise). Cin % 64 == 0; pixels per chunk (imgs*Ho*Wo / splits) % 64 == 0. */
+int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
+                   int Cout, int kh, int kw, int stride, int pad, void* stream);
 /* dw_partial fp16 [G*splits][cout][k_pad] (value = dW_g * *scale / inv_alpha) -> grad_mu += sum_g dW_g,
  * grad_rho += sum_g dW_g * eps_g * sigmoid(rho); eps injected [G][n] or Philox(seed, layer_id, sample0+g).
  * stale_eps != 0 reproduces the reference's saved-eps-buffer behaviour (every pass sees the last pass's eps). */

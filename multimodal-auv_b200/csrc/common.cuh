@@ -231,10 +231,28 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile: the M (or N) dimension is contiguous in memory and the reduction index walks the rows - what a
+// TMA box [64 reduction rows][64 elements = 128 B] of a row-major [pixels][channels] tensor looks like in smem. Canonical
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 64 contiguous MN elements per 128 B row, 8 K rows per 1024 B
+// swizzle atom, SBO = 1024 B to the next 8 K rows, LBO = bytes to the next block of 64 MN elements (the next TMA box).
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: fp16 A/B (format 0), fp32 D (c_format 1),
 // both operands K-major, dense, no negate. n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// Same with both operands MN-major (a_major bit 15, b_major bit 16).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(uint32_t m, uint32_t n) {
+  return umma_idesc_f16(m, n) | (1u << 15) | (1u << 16);
 }
 
 // ----------------------------------------------------------------------------

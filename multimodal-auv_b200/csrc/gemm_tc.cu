@@ -54,6 +54,13 @@ struct GemmParams {
   int a_wrap_kb;         // tiled A: k-block count after which A's column coordinate wraps to 0 (0 = never)
   int a_cwrap;           // im2col A: channel-block period of A (0 = never)
   int split;             // epilogue writes (hi | lo) fp16 pairs: hi at column n, lo at column N + n
+  // weight-gradient mode (mauv_wgrad_f16): Y[batch][co][k] = sum_pixels dY[pixel][co] * Xcol[pixel][k]. Both operands are
+  // MN-major: TMA boxes of [64 pixels][64 channels] straight from the row-major dY and the NHWC activations (tiled for
+  // 1x1 / stride 1, im2col-mode for everything else); the batch index is (sample, pixel chunk), k_blocks = chunk / 64.
+  int mn;                // 1: weight-gradient mode
+  int b_im2col;          // mn: B boxes come from im2col-mode TMA (else tiled rows of [pixels][Cin])
+  int cin;               // mn: input channels (column -> (tap, channel block))
+  long long chunk;       // mn: pixels per batch entry
 };
 
 // Epilogue flavours: 0 = raw fp16 store + BN statistics, 1 = BN statistics only (no output: first pass of the
@@ -185,6 +192,40 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           iq = r2 - ip * p.Wo;
           in_ = g * p.imgs_per_sample + b;
         }
+        if (p.mn) {
+          // weight-gradient mode: 64-pixel k-blocks; A = 2 boxes of 64 output channels, B = BN/64 boxes of 64 columns
+          const int n0 = n_tile * BN;
+          int a_boxes = 0, b_boxes = 0;
+          for (int j = 0; j < 2; ++j) a_boxes += (m0 + 64 * j < p.M);
+          for (int j = 0; j < BN / 64; ++j) b_boxes += (n0 + 64 * j < p.N);
+          const int hw = p.Ho * p.Wo;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = tiles_base + stage * L::kStageBytes;
+            const uint32_t b_dst = a_dst + L::kABytes;
+            mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(a_boxes + b_boxes) * 8192u);
+            const long long pix0 = static_cast<long long>(g) * p.chunk + static_cast<long long>(kb) * 64;
+            for (int j = 0; j < a_boxes; ++j)
+              tma_load_3d(a_dst + j * 8192, &tmA, full_bar(stage), m0 + 64 * j, static_cast<int>(pix0), 0);
+            if (p.b_im2col) {
+              const int img = static_cast<int>(pix0 / hw);
+              const int r2 = static_cast<int>(pix0 - static_cast<long long>(img) * hw);
+              const int bp = r2 / p.Wo, bq = r2 - bp * p.Wo;
+              for (int j = 0; j < b_boxes; ++j) {
+                const int col = n0 + 64 * j;
+                const int tap = col / p.cin, c0 = col - tap * p.cin;
+                const int r = tap / p.kw, s2 = tap - r * p.kw;
+                tma_load_im2col_4d(b_dst + j * 8192, &tmB, full_bar(stage), c0, bq * p.stride - p.pad,
+                                   bp * p.stride - p.pad, img, static_cast<uint16_t>(s2), static_cast<uint16_t>(r));
+              }
+            } else {
+              for (int j = 0; j < b_boxes; ++j)
+                tma_load_3d(b_dst + j * 8192, &tmB, full_bar(stage), n0 + 64 * j, static_cast<int>(pix0), 0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = tiles_base + stage * L::kStageBytes;
@@ -226,12 +267,22 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t a_addr = tiles_base + stage * L::kStageBytes;
-          const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
+          if (p.mn) {
+            // MN-major boxes [64 pixels][64 channels]: one MMA consumes 16 pixel rows = 2048 bytes (+128 in the >>4 field)
+            constexpr uint32_t idesc_mn = umma_idesc_f16_mn(BM, BN);
+            const uint64_t a_desc = umma_smem_desc_mn_sw128(a_addr, 8192);
+            const uint64_t b_desc = umma_smem_desc_mn_sw128(a_addr + L::kABytes, 8192);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
-            umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16_ss(d_tmem, a_desc + 128u * k, b_desc + 128u * k, idesc_mn, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+              umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -626,7 +677,7 @@ int make_tiled_map(CUtensorMap* tm, const void* base, int64_t K, int64_t rows, i
 
 // NHWC fp16 activations seen as (C, W, H, N) in im2col mode: 64 channels x 128 output pixels.
 int make_im2col_map(CUtensorMap* tm, const void* base, int64_t C, int64_t W, int64_t H, int64_t N,
-                    int kh, int kw, int stride, int pad) {
+                    int kh, int kw, int stride, int pad, int pixel_box = BM) {
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
                         static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(C) * 2 * W,
@@ -635,7 +686,7 @@ int make_im2col_map(CUtensorMap* tm, const void* base, int64_t C, int64_t W, int
   int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
   cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
-                               strides, lower, upper, BK, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               strides, lower, upper, BK, pixel_box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -749,6 +800,62 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
   p.y = static_cast<__half*>(y);
   p.stats = stats_partial;
   p.bias = static_cast<const float*>(bias);
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- weight gradient of the grouped conv, straight from NHWC operands ---------------------------------------------
+// dw[(g, chunk)][co][(r, s, c)] = sum over the chunk's output pixels of dy[pixel][co] * x[pixel shifted by tap (r,s)][c]
+int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
+                   int Cout, int kh, int kw, int stride, int pad, void* stream) {
+  MAUV_CHECK_ARG(dy && x && dw && G >= 1 && splits >= 1, "mauv_wgrad_f16: bad argument");
+  MAUV_CHECK_ARG(Cin % 64 == 0 && Cout % 8 == 0, "mauv_wgrad_f16: Cin must be a multiple of 64 and Cout of 8 (Cin=%d Cout=%d)", Cin, Cout);
+  MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dw) & 15) == 0, "mauv_wgrad_f16: pointers must be 16-byte aligned");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  const long long Mg = static_cast<long long>(imgs_per_sample) * Ho * Wo;
+  MAUV_CHECK_ARG(Mg % splits == 0 && (Mg / splits) % 64 == 0,
+                 "mauv_wgrad_f16: pixels per chunk (%lld / %d) must be a multiple of 64", Mg, splits);
+  const long long rows = static_cast<long long>(G) * Mg;
+  MAUV_CHECK_ARG(rows < (1LL << 31), "mauv_wgrad_f16: too many pixels");
+  if (int rc = load_driver_entry_points()) return rc;
+  const bool plain = (kh == 1 && kw == 1 && stride == 1 && pad == 0);
+  const int K = kh * kw * Cin;
+  CUtensorMap tmA, tmB;
+  {   // row-major [pixels][channels] seen as (channels, pixels, 1), box 64 x 64
+    auto rowmajor = [&](CUtensorMap* tm, const void* base, int64_t cols) -> int {
+      cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), 1};
+      cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * static_cast<cuuint64_t>(rows)};
+      cuuint32_t box[3] = {64, 64, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return mauv_set_error(MAUV_ERR_DRIVER, "cuTensorMapEncodeTiled (wgrad operand) failed (%d)", (int)r);
+      return MAUV_OK;
+    };
+    if (int rc = rowmajor(&tmA, dy, Cout)) return rc;
+    if (plain) {
+      if (int rc = rowmajor(&tmB, x, Cin)) return rc;
+    } else {
+      if (int rc = make_im2col_map(&tmB, x, Cin, W, H, static_cast<int64_t>(G) * imgs_per_sample, kh, kw, stride, pad, 64)) return rc;
+    }
+  }
+  GemmParams p{};
+  p.stack = 1;
+  p.M = Cout;
+  p.N = K;
+  p.G = G * splits;
+  p.chunk = Mg / splits;
+  p.k_blocks = static_cast<int>(p.chunk / 64);
+  p.a_mode = 0;
+  p.a_batch_mul = 1;
+  p.mn = 1;
+  p.b_im2col = plain ? 0 : 1;
+  p.cin = Cin;
+  p.Wo = Wo; p.Ho = Ho; p.imgs_per_sample = imgs_per_sample; p.stride = stride; p.pad = pad; p.kw = kw;
+  p.y = static_cast<__half*>(dw);
+  p.stats = nullptr;
+  p.bias = nullptr;
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 

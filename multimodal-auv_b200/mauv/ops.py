@@ -575,6 +575,18 @@ def avgpool_bwd_f16(gs: GradScratch, dfeat: torch.Tensor, HW: int):
     return out, s_out
 
 
+def wgrad_f16(dy: torch.Tensor, x: torch.Tensor, G: int, splits: int, kh: int, kw: int, stride: int, pad: int) -> torch.Tensor:
+    """dy [G*B, Ho, Wo, Cout], x [G*B, H, W, Cin] NHWC fp16 -> dw partials [G*splits, Cout, kh*kw*Cin] fp16"""
+    lib = _lib.require_device()
+    NB, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw = torch.empty((G * splits, Cout, kh * kw * Cin), dtype=F16, device=x.device)
+    _run("mauv_wgrad_f16", lib.mauv_wgrad_f16, _ptr(dy, F16), _ptr(x, F16), _ptr(dw), G, splits, NB // G, H, W, Cin, Cout,
+         kh, kw, stride, pad, _stream(),
+         tag=f"G{G}x{splits} Cout{Cout} K{kh * kw * Cin} px{dy.numel() // (G * splits * Cout)}" if _prof is not None else None)
+    return dw
+
+
 def wgrad_finalize_group(dw_partial, G, mu_shape, inv_alpha, scale_addr, rho, grad_mu, grad_rho, *, eps=None, seed=0,
                          layer_id=0, sample0=0, stale=False) -> None:
     lib = _lib.require_device()

@@ -81,6 +81,7 @@ class TrainEngine(MCEngine):
 
     def __init__(self, model: nn.Module, max_group: int = 32):
         super().__init__(model, max_group=max_group, precision="fp16")
+        self.direct_wgrad = __import__("os").environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
         self._kl_plan = None
         self._bayes = [l for _, l in bayesian_layers(self.model)]
         self._sample_cursor = max([l._calls for l in self._bayes] + [0])
@@ -178,13 +179,17 @@ class TrainEngine(MCEngine):
         if M % 8 != 0:
             raise _lib.MauvError(f"conv backward needs B*Ho*Wo to be a multiple of 8 (got {M}) at {c.name}")
         splits = _group_splits(M, G, Cout, c.k * c.k * Cin)
-        a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits)                      # [G*splits, Cout, Mc]
-        if c.k == 1 and c.stride == 1:
-            b_t = ops.transpose_chunks_f16(r.x.view(G * M, Cin), G * splits)                  # [G*splits, Cin, Mc]
+        if (M // splits) % 64 == 0 and Cin % 64 == 0 and self.direct_wgrad:
+            # both operands MN-major straight from the NHWC tensors (TMA boxes of [64 pixels][64 channels])
+            dw = ops.wgrad_f16(dy, r.x, G, splits, c.k, c.k, c.stride, c.pad)                 # [G*splits, Cout, K]
         else:
-            b_t = ops.im2col_t_f16(r.x, c.k, c.k, c.stride, c.pad, G * splits)               # [G*splits, Kp, Mc]
-        dw, _ = ops.gemm_f16(a_t, b_t)                                                        # [G*splits, Cout, Kp]
-        del a_t, b_t
+            a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits)                  # [G*splits, Cout, Mc]
+            if c.k == 1 and c.stride == 1:
+                b_t = ops.transpose_chunks_f16(r.x.view(G * M, Cin), G * splits)              # [G*splits, Cin, Mc]
+            else:
+                b_t = ops.im2col_t_f16(r.x, c.k, c.k, c.stride, c.pad, G * splits)           # [G*splits, Kp, Mc]
+            dw, _ = ops.gemm_f16(a_t, b_t)                                                    # [G*splits, Cout, Kp]
+            del a_t, b_t
         ew = self._eps_w(eps, c.name, s0, G)
         ops.wgrad_finalize_group(dw, G, tuple(mu.shape), 1.0, s_dy, rho, layer.mu_kernel.grad, layer.rho_kernel.grad,
                                  eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0, stale=stale)

@@ -637,7 +637,7 @@ def t_conv_bwd_group(G, B, H, W, Cin, Cout, k, stride, pad, stale=False):
     gs = ops.GradScratch(dev)
     gs.f[0] = sc
     gs.used = 1
-    stub = types.SimpleNamespace(device=torch.device(dev))
+    stub = types.SimpleNamespace(device=torch.device(dev), direct_wgrad=True)
     stub._eps_w = lambda e, name, s0, g: MCEngine._eps_w(stub, e, name, s0, g)
     c = _Conv("conv", layer, 7, Cin, Cout, k, stride, pad)
     w_fwd = None
