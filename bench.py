@@ -369,6 +369,8 @@ def run_train(args):
             a = agg.get(n, (0, 0.0))
             agg[n] = (a[0] + c, a[1] + tms)
         detail = {k: {"calls": c, "ms": round(tms, 3)} for k, (c, tms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        for k, (c, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:60]:
+            print(f"{tms:9.3f} ms {c:4d} x {k}", file=sys.stderr)
     if rank != 0:
         torch.distributed.destroy_process_group()
         return 0

@@ -54,9 +54,38 @@ __device__ __forceinline__ void load_dz(const Upstream& u, long long idx, float 
   }
 }
 
+// Two-phase variant for software pipelining: issue every 16-byte load of a vector first, combine afterwards.
+struct RawVec { uint4 d1, d2, m, y, y2; };
+
+__device__ __forceinline__ void load_raw(const Upstream& u, const uint4* __restrict__ y, const uint4* __restrict__ y2,
+                                         long long idx, bool valid, RawVec& r) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  r.d1 = valid ? __ldg(u.d1 + idx) : z;
+  r.d2 = (valid && u.d2) ? __ldg(u.d2 + idx) : z;
+  r.m = (valid && u.mask) ? __ldg(u.mask + idx) : z;
+  r.y = valid ? __ldg(y + idx) : z;
+  r.y2 = (valid && y2) ? __ldg(y2 + idx) : z;
+}
+
+__device__ __forceinline__ void raw_dz(const Upstream& u, const RawVec& r, float ratio, float* dz) {
+  unpack8(r.d1, dz);
+  if (u.d2) {
+    float t[8];
+    unpack8(r.d2, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = fmaf(ratio, t[j], dz[j]);
+  }
+  if (u.mask) {
+    float m[8];
+    unpack8(r.m, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = m[j] > 0.f ? dz[j] : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------- BN backward, pass 1: per-(sample, channel) sums
 // partial [G][nblk][3][C] = (sum dz, sum dz*y, sum dz*y2); amax = max |dz| (float bits, atomicMax)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(Upstream u, const uint4* __restrict__ y, const uint4* __restrict__ y2, long long M, int C, int nblk,
                      long long rows_per_block, float* __restrict__ partial, unsigned* __restrict__ amax) {
   __shared__ float red[3 * 2048];
@@ -69,21 +98,29 @@ bn_bwd_reduce_kernel(Upstream u, const uint4* __restrict__ y, const uint4* __res
   float s0[8], s1[8], s2[8], mx = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
-  for (long long row = row0 + r; row < row1; row += rl) {
+  // two rows in flight per thread (up to 10 independent 16-byte loads): the pass is latency-bound otherwise
+  for (long long row = row0 + r; row < row1; row += 2 * rl) {
     const long long idx = (static_cast<long long>(g) * M + row) * lanes + cv;
-    float dz[8], yv[8];
-    load_dz(u, idx, ratio, dz);
-    unpack8(__ldg(y + idx), yv);
+    RawVec ra, rb;
+    load_raw(u, y, y2, idx, true, ra);
+    load_raw(u, y, y2, idx + static_cast<long long>(rl) * lanes, row + rl < row1, rb);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s0[j] += dz[j];
-      s1[j] = fmaf(dz[j], yv[j], s1[j]);
-      mx = fmaxf(mx, fabsf(dz[j]));
-    }
-    if (y2) {
-      unpack8(__ldg(y2 + idx), yv);
+    for (int h = 0; h < 2; ++h) {
+      const RawVec& rv = h ? rb : ra;
+      float dz[8], yv[8];
+      raw_dz(u, rv, ratio, dz);
+      unpack8(rv.y, yv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s2[j] = fmaf(dz[j], yv[j], s2[j]);
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += dz[j];
+        s1[j] = fmaf(dz[j], yv[j], s1[j]);
+        mx = fmaxf(mx, fabsf(dz[j]));
+      }
+      if (y2) {
+        unpack8(rv.y2, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2[j] = fmaf(dz[j], yv[j], s2[j]);
+      }
     }
   }
 #pragma unroll
@@ -189,6 +226,7 @@ struct ApplyArgs {
   long long M; int C;
 };
 
+template <bool HAS_Y2>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const ApplyArgs a) {
   const int lanes = a.C >> 3;
@@ -199,36 +237,47 @@ bn_bwd_apply_kernel(const ApplyArgs a) {
   const int cv = static_cast<int>(first % lanes);           // invariant: 256 % lanes == 0
   const float ratio = upstream_ratio(a.u);
   const float r1 = pow2_rescale(a.amax, a.kmax, a.target);
-  const float r2 = a.y2 ? pow2_rescale(a.amax, a.kmax2, a.target) : 1.f;
+  const float r2 = HAS_Y2 ? pow2_rescale(a.amax, a.kmax2, a.target) : 1.f;
   if (blockIdx.x == 0 && g == 0 && threadIdx.x == 0) {
     *a.s_out = (*a.u.s1) * r1;
-    if (a.y2) *a.s_out2 = (*a.u.s1) * r2;
+    if (HAS_Y2) *a.s_out2 = (*a.u.s1) * r2;
   }
-  float k0[8], k1[8], k2[8], q0[8], q1[8], q2[8];
+  float k0[8], k1[8], k2[8], q0[HAS_Y2 ? 8 : 1], q1[HAS_Y2 ? 8 : 1], q2[HAS_Y2 ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 k = a.coef[static_cast<long long>(g) * a.C + cv * 8 + j];
     k0[j] = k.x * r1; k1[j] = k.y * r1; k2[j] = k.z * r1;
-    if (a.y2) {
+    if (HAS_Y2) {
       const float4 q = a.coef2[static_cast<long long>(g) * a.C + cv * 8 + j];
       q0[j] = q.x * r2; q1[j] = q.y * r2; q2[j] = q.z * r2;
     }
   }
   const long long base = static_cast<long long>(g) * vecs;
-  for (long long i = first; i < vecs; i += step) {
-    float dz[8], yv[8], o[8];
-    load_dz(a.u, base + i, ratio, dz);
-    unpack8(__ldg(a.y + base + i), yv);
+  const uint4* y2p = HAS_Y2 ? a.y2 : nullptr;
+  for (long long i = first; i < vecs; i += 2 * step) {      // two vectors in flight per thread
+    RawVec ra, rb;
+    const bool vb = i + step < vecs;
+    load_raw(a.u, a.y, y2p, base + i, true, ra);
+    load_raw(a.u, a.y, y2p, base + i + step, vb, rb);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], dz[j], fmaf(k1[j], yv[j], k2[j]));
-    a.dy[base + i] = pack8(o);
-    if (a.y2) {
-      unpack8(__ldg(a.y2 + base + i), yv);
+    for (int h = 0; h < 2; ++h) {
+      if (h && !vb) break;
+      const RawVec& rv = h ? rb : ra;
+      const long long o_idx = base + i + (h ? step : 0);
+      float dz[8], yv[8], o[8];
+      raw_dz(a.u, rv, ratio, dz);
+      unpack8(rv.y, yv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(q0[j], dz[j], fmaf(q1[j], yv[j], q2[j]));
-      a.dy2[base + i] = pack8(o);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], dz[j], fmaf(k1[j], yv[j], k2[j]));
+      a.dy[o_idx] = pack8(o);
+      if (HAS_Y2) {
+        unpack8(rv.y2, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(q0[j], dz[j], fmaf(q1[j], yv[j], q2[j]));
+        a.dy2[o_idx] = pack8(o);
+      }
+      if (a.dz) a.dz[o_idx] = pack8(dz);
     }
-    if (a.dz) a.dz[base + i] = pack8(dz);
   }
 }
 
@@ -357,8 +406,8 @@ wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, in
   const long long quad = static_cast<long long>(blockIdx.x) * 32 + ql;
   const long long e0 = quad * 4;
   const int khw = kh * kw;
-  const long long per_out = static_cast<long long>(cin) * khw;
-  const long long n = per_out * cout;
+  const unsigned per_out = static_cast<unsigned>(cin) * khw;
+  const long long n = static_cast<long long>(per_out) * cout;       // < 2^31 (checked on the host): 32-bit index math
   const bool any = e0 < n;
   long long off[4];
   bool live[4];
@@ -366,11 +415,11 @@ wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, in
   for (int i = 0; i < 4; ++i) {
     const long long e = e0 + i;
     live[i] = e < n;
-    const long long ee = live[i] ? e : 0;
-    const long long co = ee / per_out;
-    const int rem = static_cast<int>(ee - co * per_out);
-    const int c = rem / khw, rs = rem - c * khw;
-    off[i] = co * Kp + static_cast<long long>(rs) * cin + c;
+    const unsigned ee = live[i] ? static_cast<unsigned>(e) : 0u;
+    const unsigned co = ee / per_out;
+    const unsigned rem = ee - co * per_out;
+    const unsigned c = rem / static_cast<unsigned>(khw), rs = rem - c * khw;
+    off[i] = static_cast<long long>(co) * Kp + static_cast<long long>(rs) * cin + c;
   }
   const bool vec = khw == 1 && live[3] && (cin % 4 == 0) && (Kp % 4 == 0);     // 4 consecutive k: one 8-byte load
   const long long gstride = static_cast<long long>(cout) * Kp;
@@ -742,7 +791,8 @@ int mauv_bn_bwd_apply(const void* d1, const void* d2, const float* s1, const flo
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(static_cast<unsigned>(bx), G);
-  bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (y2) bn_bwd_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else bn_bwd_apply_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MAUV_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return MAUV_OK;
 }
@@ -789,6 +839,7 @@ int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cou
                               void* stream) {
   MAUV_CHECK_ARG(dw_partial && scale && rho && grad_mu && grad_rho && G >= 1 && splits >= 1, "mauv_wgrad_finalize_group: bad argument");
   const long long n = static_cast<long long>(cout) * cin * kh * kw;
+  MAUV_CHECK_ARG(n < (1LL << 31), "mauv_wgrad_finalize_group: tensor too large");
   wgrad_finalize_group_kernel<<<static_cast<unsigned>(ceil_div_i64(ceil_div_i64(n, 4), 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
       sample0, stale_eps, grad_mu, grad_rho);

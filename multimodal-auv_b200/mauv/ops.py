@@ -532,7 +532,8 @@ def bn_bwd_site(gs: GradScratch, d1, s1, y, batch_stats, gamma, bn_eps, grad_gam
     amax = gs.slot()
     st = _stream()
     _run("mauv_bn_bwd_reduce", lib.mauv_bn_bwd_reduce, _ptr(d1, F16), _ptr(d2, F16), s1, s2, _ptr(relu_out, F16), _ptr(y, F16),
-         _ptr(y2, F16), G, M, C, _ptr(partial), amax, st)
+         _ptr(y2, F16), G, M, C, _ptr(partial), amax, st,
+         tag=f"G{G} M{M} C{C} d2{int(d2 is not None)} y2{int(y2 is not None)} nblk{nblk}" if _prof is not None else None)
     coef = torch.empty((G, C, 4), dtype=F32, device=dev)
     ws = torch.empty((G, C, 2), dtype=torch.float64, device=dev)
     kmax = gs.slot()
@@ -551,7 +552,8 @@ def bn_bwd_site(gs: GradScratch, d1, s1, y, batch_stats, gamma, bn_eps, grad_gam
     s_out = gs.slot()
     _run("mauv_bn_bwd_apply", lib.mauv_bn_bwd_apply, _ptr(d1, F16), _ptr(d2, F16), s1, s2, _ptr(relu_out, F16), _ptr(y, F16),
          _ptr(y2, F16), _ptr(coef), _ptr(coef2), amax, kmax, kmax2, GRAD_TARGET, G, M, C, _ptr(dy), _ptr(dy2), _ptr(dz), s_out,
-         s_out2, st)
+         s_out2, st,
+         tag=f"G{G} M{M} C{C} d2{int(d2 is not None)} y2{int(y2 is not None)} dz{int(want_dz)}" if _prof is not None else None)
     return dy, s_out, dy2, s_out2, dz
 
 
@@ -597,7 +599,8 @@ def wgrad_finalize_group(dw_partial, G, mu_shape, inv_alpha, scale_addr, rho, gr
         _, cin, kh, kw = mu_shape
     _run("mauv_wgrad_finalize_group", lib.mauv_wgrad_finalize_group, _ptr(dw_partial, F16), G, gsplits // G, cout, cin, kh, kw,
          k_pad, inv_alpha, scale_addr, _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0, int(stale), _ptr(grad_mu, F32),
-         _ptr(grad_rho, F32), _stream())
+         _ptr(grad_rho, F32), _stream(),
+         tag=f"G{G} sp{gsplits // G} cout{cout} cin{cin} k{kh}" if _prof is not None else None)
 
 
 def sampled_linear_bwd_group_f32(x, gy, mu_w, rho_w, rho_b, grad_mu_w, grad_rho_w, grad_mu_b, grad_rho_b, *, eps_w=None,

@@ -3,6 +3,8 @@
   python tests/gpu_microbench.py conv  G B H W Cin Cout k stride pad [iters]
   python tests/gpu_microbench.py bnact G M C [iters]
   python tests/gpu_microbench.py mcreduce S B C [iters]
+  python tests/gpu_microbench.py wgrad G B H W Cin Cout k stride pad [splits]
+  python tests/gpu_microbench.py bnbwd G M C
   python tests/gpu_microbench.py kl | sample
   python tests/gpu_microbench.py layers        (the ResNet-50 trunk shapes at B=256)
 """
@@ -114,6 +116,40 @@ def sample():
               f"({G * n / ms / 1e6:.1f} Gweights/s)", flush=True)
 
 
+def wgrad(G, B, H, W, Cin, Cout, k, stride, pad, splits=1, iters=5):
+    """weight gradient straight from the NHWC tensors (MN-major tcgen05 operands)"""
+    x = torch.randn(G * B, H, W, Cin, device=dev, dtype=torch.float16)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    dy = torch.randn(G * B, Ho, Wo, Cout, device=dev, dtype=torch.float16)
+    ms = timeit(lambda: ops.wgrad_f16(dy, x, G, splits, k, k, stride, pad), iters)
+    fl = 2.0 * G * B * Ho * Wo * Cout * k * k * Cin
+    by = (x.numel() + dy.numel() + G * splits * Cout * k * k * Cin) * 2
+    print(f"wgrad G={G} B={B} {H}x{W} {Cin}->{Cout} k{k}/{stride} splits={splits}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  "
+          f"{by / ms / 1e9:.2f} TB/s", flush=True)
+
+
+def bnbwd(G, M, C, iters=5):
+    """one BatchNorm-backward site of a bottleneck tail (two upstream tensors, ReLU mask, dz output)"""
+    y = torch.randn(G, M, C, device=dev, dtype=torch.float16)
+    out = torch.relu(torch.randn(G, M, C, device=dev, dtype=torch.float16))
+    d1 = torch.randn(G, M, C, device=dev, dtype=torch.float16)
+    d2 = torch.randn(G, M, C, device=dev, dtype=torch.float16)
+    bs = torch.stack([torch.zeros(G, C, device=dev), torch.ones(G, C, device=dev)], -1).contiguous()
+    gamma = torch.ones(C, device=dev)
+    gg, gb = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+
+    def run():
+        gs = ops.GradScratch(dev, 16)
+        gs.f[0], gs.f[1] = 1.0, 2.0
+        gs.used = 2
+        ops.bn_bwd_site(gs, d1, gs.f.data_ptr(), y, bs, gamma, 1e-5, gg, gb, G, C, d2=d2, s2=gs.f.data_ptr() + 4,
+                        relu_out=out, want_dz=True)
+    ms = timeit(run, iters)
+    n = y.numel() * 2
+    print(f"bn_bwd site G={G} M={M} C={C} (reduce + coeffs + apply): {ms:.3f} ms  {(4 * n + 6 * n) / ms / 1e9:.2f} TB/s "
+          f"(reduce reads 4 tensors; apply reads 4, writes 2)", flush=True)
+
+
 def hbm():
     """HBM read-only / write-only / copy bandwidth with plain torch ops (measurement aid for the roofline split)."""
     n = 1 << 31
@@ -143,4 +179,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)
