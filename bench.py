@@ -382,7 +382,8 @@ def run_train(args):
                                    f"path={args.train_path}, gradient all-reduce over {world} GPU(s)",
                        "triplet_samples_per_s": world * B * S / (ms / 1e3)},
             "model_tflops": flops / (ms / 1e3) / 1e12,
-            "gpu_launches": (ops.launch_count - l0), "loss": float(loss.detach())}
+            "gpu_launches": (ops.launch_count - l0), "loss": float(loss.detach()),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     if detail is not None:
         line["kernel_ms_per_step"] = detail
     print(json.dumps(line))

@@ -82,6 +82,11 @@ class TrainEngine(MCEngine):
     def __init__(self, model: nn.Module, max_group: int = 32):
         super().__init__(model, max_group=max_group, precision="fp16")
         self.direct_wgrad = __import__("os").environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
+        self._update_running = True
+        # activations kept per (triplet, MC sample) for the backward walk, bytes at 256x256 (raw conv outputs + activations of
+        # 53 convs per trunk in fp16, plus the transient gradient tensors); scaled with the input resolution
+        self.tape_bytes_256 = (230 if self.kind == "multimodal" else 80) * 2 ** 20
+        self.live_samples = int(__import__("os").environ.get("MAUV_TRAIN_LIVE_SAMPLES", "0")) or None
         self._kl_plan = None
         self._bayes = [l for _, l in bayesian_layers(self.model)]
         self._sample_cursor = max([l._calls for l in self._bayes] + [0])
@@ -102,7 +107,8 @@ class TrainEngine(MCEngine):
         if bn.weight is None or bn.bias is None:
             raise _lib.MauvError("TrainEngine needs affine BatchNorm (torchvision's default)")
         mom = 0.1 if bn.momentum is None else bn.momentum
-        track = bn.track_running_stats and bn.running_mean is not None
+        # the recompute pass of the two-phase step replays a forward whose running-statistics update already happened
+        track = bn.track_running_stats and bn.running_mean is not None and self._update_running
         return ops.bn_finalize(stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
                                bn.running_mean if track else None, bn.running_var if track else None,
                                want_batch_stats=True, num_batches_tracked=bn.num_batches_tracked if track else None)
@@ -390,12 +396,48 @@ class TrainEngine(MCEngine):
             eps = _engine.DEBUG_EPS               # test hook: injected eps instead of Philox (see engine.py)
         xs = [x.to(self.device, F32).contiguous() for x in inputs]
         labels = labels.to(self.device, torch.int64).contiguous()
+        B = xs[0].shape[0]
+        live = self.live_samples
+        if live is None:        # how many (triplet, sample) tapes fit in 70 % of the memory that is free right now
+            free = torch.cuda.mem_get_info(self.device)[0] + torch.cuda.memory_reserved(self.device) - \
+                torch.cuda.memory_allocated(self.device)
+            per = self.tape_bytes_256 * xs[0].shape[2] * xs[0].shape[3] / 65536.0
+            live = max(1, int(0.7 * free / per))
         G = min(self.max_group, S)
+        recompute = B * S > live
+        if recompute:
+            G = max(1, min(G, live // B))
         if stale and G < S:
-            raise _lib.MauvError("reference stale-eps mode needs all S samples in one group (raise max_group)")
+            raise _lib.MauvError("reference stale-eps mode needs all S samples in one group (raise max_group / free memory)")
         self._ensure_grads()
         with ops.on_current_stream():
+            if recompute:
+                return self._step_recompute(xs, labels, S, G, kl_scale, sample0, eps, seed, stale)
             return self._step(xs, labels, S, G, kl_scale, sample0, eps, seed, stale)
+
+    def _step_recompute(self, xs, labels, S, G, kl_scale, sample0, eps, seed, stale) -> dict:
+        """Memory-bounded variant: the tapes of all S samples do not fit, so phase 1 walks forward for the logits only and
+        phase 2 replays the forward of one sample group at a time (same Philox ids -> identical tensors; no second update
+        of the BN running statistics) right before that group's backward walk. Costs one extra forward (~+25 %)."""
+        logits = []
+        for s in range(0, S, G):
+            g = min(G, S - s)
+            lg, tape = self._forward_group(xs, g, sample0 + s, eps, seed)
+            del tape
+            logits.append(lg)
+        logits = logits[0] if len(logits) == 1 else torch.cat(logits, dim=0)
+        ce, mean_logit, dlogits = ops.ce_mean_fwd_bwd_f32(logits, labels)
+        self._update_running = False
+        try:
+            for s in range(0, S, G):
+                g = min(G, S - s)
+                _, tape = self._forward_group(xs, g, sample0 + s, eps, seed)
+                self._backward_group(tape, dlogits[s:s + g], g, sample0 + s, eps, seed, stale)
+                del tape
+        finally:
+            self._update_running = True
+        kl = self._kl(kl_scale)
+        return {"loss": ce + kl * kl_scale, "ce": ce, "kl": kl, "mean_logit": mean_logit, "logits": logits}
 
     def _step(self, xs, labels, S, G, kl_scale, sample0, eps, seed, stale) -> dict:
         tapes, logits = [], []
