@@ -257,6 +257,17 @@ def run_ours(args):
             sys.stderr.write("ms      kernel                 shape                                   calls TFLOP/s  TB/s(min traffic)\n")
             for t, b, tag, c, tf, tb in rows[:60]:
                 sys.stderr.write(f"{t:7.2f} {b:22s} {tag:40s} {c:4d} {tf:7.1f} {tb:7.2f}\n")
+        # per-launch roofline: ideal time of a launch = max(flops / tensor peak, minimum bytes / HBM peak)
+        ideal_ms = hbm_bound_ms = 0.0
+        for k, (c, t) in prof.items():
+            if "|" not in k or k.split("|")[0] not in tc:
+                continue
+            mdl = tc_launch_model(*k.split("|"))
+            if mdl is None:
+                continue
+            t_tc, t_hbm = mdl[0] / (tf_peak * 1e12) * 1e3, mdl[1] / (hbm_peak * 1e9) * 1e3
+            ideal_ms += c * max(t_tc, t_hbm)
+            hbm_bound_ms += t if t_hbm > t_tc else 0.0
         s_local = hi - lo
         conv_tflop = CONV_GFLOP_PER_TRIPLET_SAMPLE * B * s_local / 1e3
         achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
@@ -284,7 +295,13 @@ def run_ours(args):
                                  "summed launch durations; by shape the kernel runs at 0.89-0.94 of the tensor peak "
                                  "(K >= 2304) and at ~0.87 of the 3.9 TB/s HBM write-only peak on the wide-N 1x1 layers",
                          "launches_per_step": conv_calls, "avg_launch_ms": conv_ms / max(conv_calls, 1),
-                         "share_of_step": conv_ms / total_prof},
+                         "share_of_step": conv_ms / total_prof,
+                         # the kernel is tensor-bound on some shapes and HBM-bound on others: per launch,
+                         # ideal = max(flops / tensor peak, minimum bytes (inputs + weights + outputs once) / HBM peak)
+                         "per_launch": {"ideal_ms_per_step": ideal_ms, "measured_ms_per_step": conv_ms,
+                                        "frac": ideal_ms / conv_ms if conv_ms else None,
+                                        "hbm_bound_share_of_time": hbm_bound_ms / conv_ms if conv_ms else None,
+                                        "hbm_peak_gbs": hbm_peak}},
             "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu_base,
         }
@@ -292,6 +309,29 @@ def run_ours(args):
     if dist:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def tc_launch_model(base: str, tag: str):
+    """Algorithmic (flops, minimum HBM bytes) of ONE launch of gemm_f16_tc_kernel from its profiling tag."""
+    toks = {x[0]: int(x[1:]) for x in tag.split() if x[0] in "GMNK" and x[1:].isdigit()}
+    if not all(q in toks for q in "GMNK"):
+        return None
+    g, m, n, k = (toks[q] for q in "GMNK")
+    flops = 2.0 * g * m * n * k
+    w_bytes = g * n * k * 2
+    if base == "mauv_conv2d_im2col_f16":
+        geo = tag.split()[-1]                                   # "3x3/1"
+        kk, stride = geo.split("/")
+        taps = int(kk.split("x")[0]) * int(kk.split("x")[1])
+        a_bytes = g * m * int(stride) ** 2 * (k // taps) * 2    # the NHWC input is read once
+        y_bytes = g * m * n * 2
+    elif base == "mauv_gemm_bn_f16":
+        a_bytes = g * m * k * 2
+        y_bytes = 0 if tag.startswith("stats") else g * m * n * 2 * (2 if "res1" in tag else 1)
+    else:
+        a_bytes = (m if k % 64 else g * m) * k * 2              # K = 152 / 56: the stem's im2col matrix, shared by all samples
+        y_bytes = g * m * n * 2
+    return flops, a_bytes + w_bytes + y_bytes
 
 
 def run_train(args):

@@ -206,7 +206,9 @@ int mauv_bn_bwd_blocks(int G, long long M, int C);
 /* forward sample w [G][cout][kh*kw*cin] (mauv_sample_weights_f16) -> the data-gradient operand [G][cin][kh*kw*cout] with the
  * taps flipped (same layout as mauv_sample_weights_dgrad_f16, without replaying the noise). cout, cin % 8 == 0. */
 int mauv_weights_to_dgrad_f16(const void* w, int G, int cout, int cin, int kh, int kw, void* w_out, void* stream);
-/* pass 1: partial[g][blk][0..2][c] = sum dz, sum dz*y, sum dz*y2 (y2 nullable); *amax = max|dz| as float bits. */
+/* pass 1: partial[g][blk][0..2][c] = sum dz, sum dz*y, sum dz*y2 (y2 nullable); *amax = max(*amax, max|dz|) as float
+ * bits. The amax / kmax words of this family are atomicMax targets: the caller hands in ZEROED words (one memset of a
+ * scratch buffer per backward walk instead of one per site). */
 int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const float* s2, const void* relu_out, const void* y,
                        const void* y2, int G, long long M, int C, float* partial, unsigned int* amax, void* stream);
 /* pass 2: per-(sample, channel) coefficients of dy = k0*dz + k1*y + k2 for train-mode BN (batch_stats = (mean, biased var)

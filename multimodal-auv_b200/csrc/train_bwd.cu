@@ -744,7 +744,6 @@ int mauv_bn_bwd_reduce(const void* d1, const void* d2, const float* s1, const fl
   const int nblk = mauv_bn_bwd_blocks(G, M, C);
   const long long rpb = (M + nblk - 1) / nblk;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MAUV_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned), st));
   dim3 grid(nblk, G);
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(make_up(d1, d2, s1, s2, relu_out), static_cast<const uint4*>(y),
                                              static_cast<const uint4*>(y2), M, C, nblk, rpb, partial, amax);
@@ -758,7 +757,6 @@ int mauv_bn_bwd_coeffs(const float* partial, int G, long long M, int C, int whic
   MAUV_CHECK_ARG(partial && batch_stats && s_in && coef && kmax && ws && (which == 1 || which == 2), "mauv_bn_bwd_coeffs: bad argument");
   MAUV_CHECK_ARG(G >= 1 && G <= 65535, "mauv_bn_bwd_coeffs: G out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MAUV_CUDA(cudaMemsetAsync(kmax, 0, sizeof(unsigned), st));
   dim3 grid((C + 31) / 32, G);
   bn_bwd_coeffs_kernel<<<grid, 256, 0, st>>>(partial, mauv_bn_bwd_blocks(G, M, C), C, which, 1.0 / static_cast<double>(M),
                                              reinterpret_cast<const float2*>(batch_stats), gamma, eps,
@@ -821,7 +819,6 @@ int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float t
                          float* s_out, void* stream) {
   MAUV_CHECK_ARG(dfeat && amax_ws && out && s_out && N >= 1 && HW >= 1 && C >= 1, "mauv_avgpool_bwd_f16: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MAUV_CUDA(cudaMemsetAsync(amax_ws, 0, sizeof(unsigned), st));
   const long long nf = N * C;
   const int64_t ab = ceil_div_i64(nf, 256);
   amax_f32_kernel<<<static_cast<unsigned>(ab > 1024 ? 1024 : ab), 256, 0, st>>>(dfeat, nf, amax_ws);
