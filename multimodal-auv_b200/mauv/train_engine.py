@@ -30,6 +30,7 @@ from . import _lib, ops
 from .backward import _splits
 from .bayesian import bayesian_layers, current_seed, reference_stale_eps
 from .engine import MCEngine, _Block, _Conv, _Trunk
+from .flatgrad import FlatGrads
 
 F16, F32 = torch.float16, torch.float32
 
@@ -83,6 +84,7 @@ class TrainEngine(MCEngine):
         super().__init__(model, max_group=max_group, precision="fp16")
         self.direct_wgrad = __import__("os").environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
         self._update_running = True
+        self._flat: Optional[FlatGrads] = None
         # activations kept per (triplet, MC sample) for the backward walk, bytes at 256x256 (raw conv outputs + activations of
         # 53 convs per trunk in fp16, plus the transient gradient tensors); scaled with the input resolution
         self.tape_bytes_256 = (230 if self.kind == "multimodal" else 80) * 2 ** 20
@@ -306,28 +308,14 @@ class TrainEngine(MCEngine):
 
     # ------------------------------------------------------------------ public
     def flatten_grads(self) -> torch.Tensor:
-        """Re-home every `.grad` into ONE contiguous fp32 buffer: one memset per step, one NCCL all-reduce per step."""
-        params = [p for p in self.model.parameters() if p.requires_grad]
-        offs, tot = [], 0
-        for p in params:
-            offs.append(tot)
-            tot += (p.numel() + 31) // 32 * 32
-        flat = torch.zeros(tot, dtype=F32, device=self.device)
-        self._grad_views = []
-        for p, o in zip(params, offs):
-            v = flat[o:o + p.numel()].view_as(p)
-            if p.grad is not None:
-                v.copy_(p.grad)
-            p.grad = v
-            self._grad_views.append((p, v))
-        self._flat_grad = flat
-        return flat
+        """Re-home every `.grad` into ONE contiguous fp32 buffer (flatgrad.FlatGrads): one memset, one finite check and
+        (N > 1) one NCCL all-reduce per step."""
+        self._flat = FlatGrads(self.model.parameters(), self.device)
+        return self._flat.flat
 
     def zero_grad(self) -> None:
-        if getattr(self, "_flat_grad", None) is not None:
-            self._flat_grad.zero_()
-            for p, v in self._grad_views:
-                p.grad = v
+        if self._flat is not None:
+            self._flat.zero()
         else:
             for p in self.model.parameters():
                 if p.grad is not None:
@@ -335,28 +323,20 @@ class TrainEngine(MCEngine):
 
     def allreduce_grads(self, group=None) -> None:
         """Data-parallel exchange (minibatch split over ranks, all S samples on every rank): gradients are
-        averaged over the ranks, one NCCL all-reduce over the flat buffer."""
-        import torch.distributed as dist
-        if getattr(self, "_flat_grad", None) is None:
+        averaged over the ranks, one all-reduce over the flat buffer."""
+        if self._flat is None:
             self.flatten_grads()
-        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG, group=group)
+        self._flat.all_reduce_mean(group)
 
     def grads_finite(self) -> torch.Tensor:
         """0-d bool tensor (device): the reference's per-parameter NaN/Inf guard (train/multimodal.py:141-145) in one pass."""
-        if getattr(self, "_flat_grad", None) is not None:
-            return torch.isfinite(self._flat_grad).all()
+        if self._flat is not None:
+            return self._flat.finite()
         return torch.stack([torch.isfinite(p.grad).all() for p in self.model.parameters() if p.grad is not None]).all()
 
     def _ensure_grads(self):
-        flat = getattr(self, "_flat_grad", None)
-        if flat is not None:
-            missing = [(p, v) for p, v in self._grad_views if p.grad is None]
-            if len(missing) == len(self._grad_views):
-                flat.zero_()                       # optimizer.zero_grad(set_to_none=True) dropped the views
-            for p, v in missing:
-                if len(missing) != len(self._grad_views):
-                    v.zero_()
-                p.grad = v
+        if self._flat is not None:
+            self._flat.ensure_attached()
             return
         for p in self.model.parameters():
             if p.requires_grad and p.grad is None:

@@ -46,3 +46,86 @@ def test_gather_sample_blocks_world2_gloo(S):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------ training: flat gradient buffer + data-parallel mean
+def _small_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+
+
+def test_flat_grads_views_zero_and_reattach():
+    from mauv.flatgrad import FlatGrads
+    m = _small_model()
+    m(torch.randn(4, 5)).sum().backward()
+    before = [p.grad.clone() for p in m.parameters()]
+    fg = FlatGrads(m.parameters())
+    assert all(torch.equal(p.grad, b) for p, b in zip(m.parameters(), before))          # existing gradients are kept
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in m.parameters())
+    assert all((p.grad.data_ptr() - fg.flat.data_ptr()) % 128 == 0 for p in m.parameters())
+    m(torch.randn(4, 5)).sum().backward()                                               # autograd accumulates into the views
+    assert fg.flat.abs().sum() > 0 and bool(fg.finite())
+    torch.optim.SGD(m.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in m.parameters())
+    fg.ensure_attached()
+    assert all(p.grad is not None and float(p.grad.abs().sum()) == 0.0 for p in m.parameters())
+    next(m.parameters()).grad.fill_(float("nan"))
+    assert not bool(fg.finite())
+    fg.zero()
+    assert float(fg.flat.abs().sum()) == 0.0
+
+
+def test_group_splits_fill_the_gpu():
+    from mauv.train_engine import _group_splits
+    assert _group_splits(32768, 30, 256, 64) == 8            # layer1 conv3 at cfg3: 30 samples x 2 m-tiles x 1 n-tile = 60 tiles
+    assert _group_splits(32768, 30, 64, 576) == 4            # layer1 conv2
+    assert _group_splits(512, 30, 512, 4608) == 1            # layer4 conv2: already 2 160 tiles
+    assert _group_splits(8, 2, 64, 64) == 1                  # tiny test shapes never split below 2 048 pixels
+
+
+def test_train_engine_selection_rules():
+    """train_*_model take the S-batched engine only for plain mean CrossEntropyLoss; on a machine without the device the
+    selection returns None (the layer path then refuses CPU tensors loudly - there is no CPU fallback)."""
+    from mauv.train.multimodal import train_engine_for
+    m = _small_model()
+    assert train_engine_for(m, torch.nn.MSELoss()) is None
+    assert train_engine_for(m, torch.nn.CrossEntropyLoss(label_smoothing=0.1)) is None
+    assert train_engine_for(m, torch.nn.CrossEntropyLoss(reduction="sum")) is None
+    if not torch.cuda.is_available():
+        assert train_engine_for(m, torch.nn.CrossEntropyLoss()) is None
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from mauv.flatgrad import FlatGrads
+    m = _small_model()
+    fg = FlatGrads(m.parameters())
+    x = torch.arange(8 * 5, dtype=torch.float32).view(8, 5) / 10
+    y = torch.arange(8) % 3
+    shard = slice(rank * 4, rank * 4 + 4)
+    torch.nn.functional.cross_entropy(m(x[shard]), y[shard]).backward()                 # local shard gradient into the views
+    fg.all_reduce_mean()
+    ref = _small_model()
+    torch.nn.functional.cross_entropy(ref(x), y).backward()                              # global-minibatch gradient
+    ok = all(torch.allclose(p.grad, r.grad, atol=1e-6) for p, r in zip(m.parameters(), ref.parameters()))
+    q.put((rank, ok))
+    torch.distributed.destroy_process_group()
+
+
+def test_data_parallel_gradient_mean_world2_gloo():
+    """The N > 1 training exchange: shard gradients averaged by one all-reduce over the flat buffer == the gradient of the
+    global minibatch (equal shards)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
