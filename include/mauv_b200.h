@@ -232,6 +232,13 @@ int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1
 /* backward of the global average pool: dfeat [N][C] fp32 -> out [N][HW][C] fp16 = dfeat/HW * r, *s_out = r (first scale). */
 int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
                          float* s_out, void* stream);
+/* 3x3 / stride 1 / pad 1 conv with Cin = Cout = 64 (ResNet layer1 conv2: torchvision resnet.py Bottleneck.conv2) in
+ * "padded stream" mode: tiles are 128 consecutive positions of the zero-padded pixel stream, one TMA box per filter row,
+ * horizontal taps as shifted shared-memory descriptors, the sample's 9 weight blocks resident in shared memory. Same
+ * results as mauv_conv2d_im2col_f16; statistics partials are [G][mauv_conv3x3_c64_tiles()][64][2]. W <= 254. */
+int mauv_conv3x3_c64_tiles(int imgs_per_sample, int H, int W);
+int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, int G, int imgs_per_sample, int H,
+                         int W, void* stream);
 /* Weight gradient of the grouped conv straight from the NHWC tensors (no transposed copies): dy [G*imgs][Ho][Wo][Cout],
  * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] fp16 partial sums over pixel chunks (K order (r, s, c)). Both
  * operands enter the tcgen05 MMA MN-major from [64 pixels][64 channels] TMA boxes (tiled for 1x1/stride 1, im2col mode

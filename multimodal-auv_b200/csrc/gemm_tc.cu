@@ -21,6 +21,7 @@
 //               (the BatchNorm batch statistics of the reference's BN-train pass)
 // Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x) with the
 // n-tile fastest so that CTAs running concurrently share their A tile in L2.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -761,6 +762,232 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution with Cin = Cout = 64 (ResNet layer1 conv2, and its data gradient): "padded stream"
+// mode. The generic im2col path fetches the input once per filter tap (9 boxes of [128 px][64 ch] per tile): for N = 64
+// that is 9x the input through L2 per 128x64 outputs and the kernel is bound by L2->SM traffic (~7 TB/s), not by HBM or
+// the tensor cores. Here the tile is 128 consecutive positions of the zero-padded pixel stream (W+2 positions per image
+// row: an im2col-mode tensor map whose bounding box spans [-1, W] delivers exactly that stream, OOB zero-filled), so that
+// EVERY tap is a constant row shift of the same smem rows: one TMA box of 130 positions per filter row (3 per tile instead
+// of 9) and the three horizontal taps are the same box read through smem descriptors that start 0, 1, 2 rows (128 B)
+// later. The 9 x [64][64] weight blocks of a sample (72 KB) stay resident in shared memory across all of that sample's
+// tiles. 2 of every W+2 output positions are padding and are dropped by the epilogue (97 % useful at W = 64).
+// Epilogue: two sets of 4 warps, one per TMEM accumulator stage (even / odd tiles), so two tiles drain concurrently.
+struct StreamParams {
+  int G, imgs_per_sample, H, W, Wp;       // Wp = W + 2
+  long long Mv;                            // padded positions per sample = imgs * H * Wp
+  int m_tiles;                             // ceil(Mv / 128)
+  long long total_tiles;
+  int base_offset_mode;                    // 1: descriptor base_offset = start row mod 8
+  __half* y;                               // [G*imgs][H][W][64]
+  float* stats;                            // [G][m_tiles][64][2] or nullptr
+};
+
+constexpr int kStreamBox = 130;                       // positions per TMA box (128 + 2 for the horizontal taps)
+constexpr int kStreamRegion = 17408;                  // 130 * 128 B rounded up to 1024
+constexpr int kStreamBBytes = 9 * 8192;
+constexpr int kStreamABytes = 3 * kStreamRegion;      // per stage
+constexpr int kStreamStages = 2;
+constexpr int kStreamOutBytes = 8 * 4096;             // per epilogue warp: 32 rows x 128 B staging (for the statistics)
+constexpr int kStreamStatBytes = 2 * 4 * 64 * 2 * 4;
+constexpr int kStreamSmem = 1024 + kStreamBBytes + kStreamStages * kStreamABytes + kStreamOutBytes + kStreamStatBytes + 256;
+
+__global__ void __launch_bounds__(384, 1)
+conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const StreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_base = smem_base;
+  const uint32_t a_base = b_base + kStreamBBytes;
+  const uint32_t out_base = a_base + kStreamStages * kStreamABytes;
+  float* stat_smem = reinterpret_cast<float*>(smem_gen + kStreamBBytes + kStreamStages * kStreamABytes + kStreamOutBytes);
+  const uint32_t bar_base = out_base + kStreamOutBytes + kStreamStatBytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  const uint32_t b_full = bar_base + 8u * 4, b_empty = bar_base + 8u * 5;
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (6 + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (8 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 10;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + kStreamBBytes + kStreamStages * kStreamABytes + kStreamOutBytes + kStreamStatBytes + 8 * 10);
+
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStreamStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<128>(tmem_ptr_addr);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const long long hwp = static_cast<long long>(p.H) * p.Wp;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, cur_g = -1;
+      uint32_t phase = 0, b_loads = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int g = static_cast<int>(tile / p.m_tiles);
+        const int m_tile = static_cast<int>(tile - static_cast<long long>(g) * p.m_tiles);
+        if (g != cur_g) {       // new sample: its 9 weight blocks replace the resident ones once the MMAs reading them retired
+          if (b_loads > 0) mbar_wait(b_empty, (b_loads - 1) & 1u);
+          mbar_expect_tx(b_full, kStreamBBytes);
+          for (int tap = 0; tap < 9; ++tap) tma_load_3d(b_base + tap * 8192, &tmB, b_full, tap * 64, 0, g);
+          ++b_loads;
+          cur_g = g;
+        }
+        const long long v0 = static_cast<long long>(m_tile) * 128;
+        const int img = static_cast<int>(v0 / hwp);
+        const int rem = static_cast<int>(v0 - img * hwp);
+        const int pr = rem / p.Wp, j0 = rem - pr * p.Wp;
+        mbar_wait(a_empty(stage), phase ^ 1u);
+        mbar_expect_tx(a_full(stage), 3u * kStreamBox * 128u);
+        for (int r = 0; r < 3; ++r)
+          tma_load_im2col_4d(a_base + stage * kStreamABytes + r * kStreamRegion, &tmA, a_full(stage), 0, j0 - 1, pr - 1,
+                             g * p.imgs_per_sample + img, 0, static_cast<uint16_t>(r));
+        if (++stage == kStreamStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, 64);
+      int stage = 0, cur_g = -1;
+      uint32_t phase = 0, it = 0, b_uses = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int g = static_cast<int>(tile / p.m_tiles);
+        if (g != cur_g) {
+          if (cur_g >= 0) umma_commit(b_empty);        // arrives when every MMA issued so far (old weights) has completed
+          mbar_wait(b_full, b_uses & 1u);
+          ++b_uses;
+          cur_g = g;
+        }
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(a_full(stage), phase);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, sx = tap - r * 3;
+          const uint32_t a_addr = a_base + stage * kStreamABytes + r * kStreamRegion + sx * 128;
+          uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+          if (p.base_offset_mode) a_desc |= static_cast<uint64_t>(sx) << 49;    // start row within the 8-row swizzle atom
+          const uint64_t b_desc = umma_smem_desc_sw128(b_base + tap * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (tap | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(a_empty(stage));
+        umma_commit(tmem_full_bar(acc));
+        if (++stage == kStreamStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int set = (warp - 4) >> 2;          // which accumulator stage (= tile parity) this warp drains
+    const int ew = warp & 3;                  // TMEM lane quarter
+    const uint32_t lane = lane_id();
+    const uint32_t my_out = out_base + (warp - 4) * 4096;
+    float* stat_buf = stat_smem + set * (4 * 64 * 2);
+    const int et = threadIdx.x - 128 - set * 128;   // 0..127 inside the set
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (static_cast<int>(it & 1u) != set) continue;
+      const int g = static_cast<int>(tile / p.m_tiles);
+      const int m_tile = static_cast<int>(tile - static_cast<long long>(g) * p.m_tiles);
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tmem_full_bar(set), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + set * 64 + (static_cast<uint32_t>(ew * 32) << 16);
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(taddr, ra);
+      tmem_ld_32x32b_x32(taddr + 32, rb);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(set));
+      // this lane's position in the padded stream -> dense output pixel (or padding / past the end)
+      const long long v = static_cast<long long>(m_tile) * 128 + ew * 32 + lane;
+      bool valid = v < p.Mv;
+      long long dense = 0;
+      if (valid) {
+        const int img = static_cast<int>(v / hwp);
+        const int rem = static_cast<int>(v - img * hwp);
+        const int pr = rem / p.Wp, u = rem - pr * p.Wp;
+        valid = u < p.W;
+        dense = ((static_cast<long long>(g) * p.imgs_per_sample + img) * p.H + pr) * p.W + u;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(p.y + dense * 64);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t* src = (q < 4) ? &ra[q * 8] : &rb[(q - 4) * 8];
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]), __uint_as_float(src[1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]), __uint_as_float(src[3]));
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]), __uint_as_float(src[5]));
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]), __uint_as_float(src[7]));
+          o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          dst[q] = o;                                                    // 128 contiguous bytes per lane
+        }
+        if (p.stats) {
+          const uint32_t off = lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_out + off), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+      }
+      if (p.stats) {
+        __syncwarp();
+        // lane j owns channels 2j, 2j+1: sums over the warp's 32 rows of the staged fp16 values (padding rows are zero)
+        unsigned long long sa = 0ull, qa = 0ull;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          uint32_t w0;
+          const uint32_t off = ((((lane >> 2) ^ (static_cast<uint32_t>(r) & 7u)) << 4) + ((lane & 3u) << 2)) + r * 128u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(my_out + off));
+          const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w0));
+          const unsigned long long f2 = *reinterpret_cast<const unsigned long long*>(&f);
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(f2));
+          asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qa) : "l"(f2));
+        }
+        const float2 sf = *reinterpret_cast<float2*>(&sa), qf = *reinterpret_cast<float2*>(&qa);
+        *reinterpret_cast<float4*>(stat_buf + (ew * 64 + 2 * lane) * 2) = make_float4(sf.x, qf.x, sf.y, qf.y);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+        if (et < 64) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            a += stat_buf[(w * 64 + et) * 2 + 0];
+            b += stat_buf[(w * 64 + et) * 2 + 1];
+          }
+          reinterpret_cast<float2*>(p.stats)[(static_cast<long long>(g) * p.m_tiles + m_tile) * 64 + et] = make_float2(a, b);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -801,6 +1028,54 @@ int mauv_gemm_f16(const void* a, long long a_sample_stride, const void* w, const
   p.stats = stats_partial;
   p.bias = static_cast<const float*>(bias);
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// 3x3 / stride 1 / pad 1, Cin = Cout = 64: padded-stream kernel (see conv3x3_c64_stream_kernel). stats_partial:
+// [G][mauv_conv3x3_c64_tiles(...)][64][2].
+int mauv_conv3x3_c64_tiles(int imgs_per_sample, int H, int W) {
+  return static_cast<int>(ceil_div_i64(static_cast<long long>(imgs_per_sample) * H * (W + 2), 128));
+}
+
+int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, int G, int imgs_per_sample, int H,
+                         int W, void* stream) {
+  MAUV_CHECK_ARG(x && w && y && G >= 1 && imgs_per_sample >= 1 && H >= 1 && W >= 1 && W <= 254, "mauv_conv3x3_c64_f16: bad argument");
+  MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0, "mauv_conv3x3_c64_f16: pointers must be 16-byte aligned");
+  if (int rc = load_driver_entry_points()) return rc;
+  const long long N = static_cast<long long>(G) * imgs_per_sample;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(128) * W, static_cast<cuuint64_t>(128) * W * H};
+    int lower[2] = {-1, -1};
+    int upper[2] = {1, -1};          // W: positions -1 .. W (the zero-padded row); H: the usual 3-row filter window
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+                                 64, kStreamBox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return mauv_set_error(MAUV_ERR_DRIVER, "cuTensorMapEncodeIm2col (padded stream) failed (%d) W=%d H=%d N=%lld", (int)r, W, H, N);
+  }
+  if (int rc = make_tiled_map(&tmB, w, 576, 64, G, 64 * 576, 64)) return rc;
+  StreamParams p{};
+  p.G = G; p.imgs_per_sample = imgs_per_sample; p.H = H; p.W = W; p.Wp = W + 2;
+  p.Mv = static_cast<long long>(imgs_per_sample) * H * p.Wp;
+  p.m_tiles = mauv_conv3x3_c64_tiles(imgs_per_sample, H, W);
+  p.total_tiles = static_cast<long long>(p.m_tiles) * G;
+  // measured on B200: the 128B swizzle is a function of the absolute shared-memory address, so a descriptor may start on any
+  // 128-byte row of a TMA-written tile with base_offset = 0 (base_offset = start row mod 8 gives wrong results)
+  p.base_offset_mode = 0;
+  p.y = static_cast<__half*>(y);
+  p.stats = stats_partial;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MAUV_CUDA(cudaFuncSetAttribute(conv3x3_c64_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    attr_set = true;
+  }
+  const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
+  conv3x3_c64_stream_kernel<<<static_cast<unsigned>(grid), 384, kStreamSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  MAUV_LAUNCH_CHECK("conv3x3_c64_stream_kernel");
+  return MAUV_OK;
 }
 
 // ---- weight gradient of the grouped conv, straight from NHWC operands ---------------------------------------------

@@ -13,6 +13,7 @@ Activations are NHWC fp16, statistics and the fusion head fp32. All compute is l
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -103,7 +104,7 @@ class MCEngine:
         # recompute-fusion of conv3 + bn3 + residual + ReLU (removes the y3 write and re-read) for bottlenecks whose
         # conv3 has K <= fuse_conv3_max_k (layer1/layer2: HBM-write bound; deeper ones are tensor bound)
         self.fuse_conv3 = True
-        self.fuse_conv3_max_k = int(__import__('os').environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
+        self.fuse_conv3_max_k = int(os.environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
 
     # ------------------------------------------------------------------ planning
     def _conv(self, layer: nn.Module, name: str) -> _Conv:

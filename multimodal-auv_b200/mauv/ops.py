@@ -195,6 +195,9 @@ def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int
     B = NB // G
     Cout = w.shape[1]
     assert w.shape[0] == G and w.shape[2] == kh * kw * Cin
+    if (STREAM_CONV and Cin == 64 and Cout == 64 and kh == 3 and kw == 3 and stride == 1 and pad == 1 and W <= 254
+            and out is None and stats_out is None):
+        return conv3x3_c64_f16(x, w, G, stats=stats)          # ResNet layer1 conv2: padded-stream kernel
     Ho = (H + 2 * pad - kh) // stride + 1
     Wo = (W + 2 * pad - kw) // stride + 1
     if out is None:
@@ -206,6 +209,22 @@ def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int
                                           kh, kw, stride, pad, _stream(),
          tag=f"G{G} M{B * Ho * Wo} N{Cout} K{kh * kw * Cin} {kh}x{kw}/{stride}" if _prof is not None else None)
     return out, (stats_out if stats else None)
+
+
+STREAM_CONV = __import__("os").environ.get("MAUV_STREAM_CONV", "1") != "0"
+
+
+def conv3x3_c64_f16(x: torch.Tensor, w: torch.Tensor, G: int, *, stats: bool = False):
+    """3x3 / stride 1 / pad 1, 64 -> 64 channels (padded-stream kernel). x [G*B, H, W, 64], w [G, 64, 576]."""
+    lib = _lib.require_device()
+    NB, H, W, Cin = x.shape
+    assert Cin == 64 and tuple(w.shape) == (G, 64, 576) and NB % G == 0
+    B = NB // G
+    out = torch.empty((NB, H, W, 64), dtype=F16, device=x.device)
+    st = torch.empty((G, lib.mauv_conv3x3_c64_tiles(B, H, W), 64, 2), dtype=F32, device=x.device) if stats else None
+    _run("mauv_conv3x3_c64_f16", lib.mauv_conv3x3_c64_f16, _ptr(x, F16), _ptr(w, F16), _ptr(out), _ptr(st), G, B, H, W, _stream(),
+         tag=f"G{G} M{B * H * W} N64 K576 stream" if _prof is not None else None)
+    return out, st
 
 
 # ------------------------------------------------------------------ BN / pooling

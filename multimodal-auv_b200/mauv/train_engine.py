@@ -20,6 +20,7 @@ in the step. Parameter gradients land in fp32 `.grad` (accumulated, like autogra
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -82,13 +83,13 @@ class TrainEngine(MCEngine):
 
     def __init__(self, model: nn.Module, max_group: int = 32):
         super().__init__(model, max_group=max_group, precision="fp16")
-        self.direct_wgrad = __import__("os").environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
+        self.direct_wgrad = os.environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
         self._update_running = True
         self._flat: Optional[FlatGrads] = None
         # activations kept per (triplet, MC sample) for the backward walk, bytes at 256x256 (raw conv outputs + activations of
         # 53 convs per trunk in fp16, plus the transient gradient tensors); scaled with the input resolution
         self.tape_bytes_256 = (230 if self.kind == "multimodal" else 80) * 2 ** 20
-        self.live_samples = int(__import__("os").environ.get("MAUV_TRAIN_LIVE_SAMPLES", "0")) or None
+        self.live_samples = int(os.environ.get("MAUV_TRAIN_LIVE_SAMPLES", "0")) or None
         self._kl_plan = None
         self._bayes = [l for _, l in bayesian_layers(self.model)]
         self._sample_cursor = max([l._calls for l in self._bayes] + [0])

@@ -68,6 +68,9 @@ def conv(G, B, H, W, Cin, Cout, k, stride, pad, iters=5):
     y = torch.empty(G * B, Ho, Wo, Cout, device=dev, dtype=torch.float16)
     st = torch.empty(G, ops.gemm_m_tiles(B * Ho * Wo), Cout, 2, device=dev)
     ms = timeit(lambda: ops.conv2d_im2col_f16(x, w, G, k, k, stride, pad, stats=True, out=y, stats_out=st), iters)
+    if Cin == 64 and Cout == 64 and k == 3 and stride == 1:
+        ms2 = timeit(lambda: ops.conv3x3_c64_f16(x, w, G, stats=True), iters)
+        print(f"   padded-stream kernel: {ms2:.3f} ms ({ms / ms2:.2f}x the im2col path)", flush=True)
     fl = 2.0 * G * B * Ho * Wo * Cout * k * k * Cin
     by = (x.numel() + y.numel() + w.numel()) * 2 + st.numel() * 4
     print(f"conv G={G} B={B} {H}x{W} {Cin}->{Cout} k{k}/{stride}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e9:.2f} TB/s", flush=True)
