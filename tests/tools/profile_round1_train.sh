@@ -9,3 +9,4 @@ KREGEX=gemm_f16_tc P wgrad_1x1_64_256 wgrad 30 8 64 64 64 256 1 1 0 4 3
 KREGEX=bn_bwd_apply SKIP=2 P bn_bwd_apply bnbwd 30 32768 256 3
 KREGEX=bn_bwd_reduce SKIP=2 P bn_bwd_reduce bnbwd 30 32768 256 3
 ls -la gpurun_out | tail -12
+KREGEX=conv3x3_c64_stream SKIP=2 P conv3x3_c64_stream conv 10 256 64 64 64 64 3 1 1 3
