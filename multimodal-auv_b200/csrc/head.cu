@@ -9,7 +9,7 @@
 namespace {
 
 constexpr int TO = 16;   // outputs per CTA
-constexpr int TB = 64;   // batch rows per CTA
+constexpr int TB = 32;   // batch rows per CTA: small tiles -> several CTAs per SM hide the global-load latency of the k loop
 constexpr int TK = 32;   // k chunk
 
 struct LinearParams {
@@ -31,7 +31,10 @@ sampled_linear_kernel(const LinearParams p) {
   const int tx = threadIdx.x % TO;
   const int ty = threadIdx.x / TO;  // 0..15
   const float* xg = p.x + static_cast<long long>(g) * p.x_gs;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[TB / 16];
+#pragma unroll
+  for (int j = 0; j < TB / 16; ++j) acc[j] = 0.f;
+  const bool quads = (p.in % 4 == 0);     // 4 consecutive k share one Philox4x32 block
 
   for (int k0 = 0; k0 < p.in; k0 += TK) {
     // activations: 64 x 32 tile, coalesced along k
@@ -41,24 +44,45 @@ sampled_linear_kernel(const LinearParams p) {
       xs[r][k] = (b < p.B && kk < p.in) ? xg[static_cast<long long>(b) * p.ldx + kk] : 0.f;
     }
     // weights: sample the 16 x 32 tile in place
-    for (int i = threadIdx.x; i < TO * TK; i += 256) {
-      const int r = i / TK, k = i % TK;
-      const int o = o0 + r, kk = k0 + k;
-      float w = 0.f;
-      if (o < p.out && kk < p.in) {
-        const long long e = static_cast<long long>(o) * p.in + kk;
-        const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e]
-                                : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
-        w = fmaf(softplus_ref(p.rho_w[e]), z, p.mu_w[e]);
+    if (quads && !p.eps_w) {
+      if (threadIdx.x < TO * TK / 4) {
+        const int r = threadIdx.x / (TK / 4), k = (threadIdx.x % (TK / 4)) * 4;
+        const int o = o0 + r, kk = k0 + k;
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (o < p.out && kk < p.in) {            // in % 4 == 0: the whole quad is in range
+          const long long e = static_cast<long long>(o) * p.in + kk;
+          float z[4];
+          philox_normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e >> 2), z);
+          const float4 m4 = *reinterpret_cast<const float4*>(p.mu_w + e);
+          const float4 r4 = *reinterpret_cast<const float4*>(p.rho_w + e);
+          w[0] = fmaf(softplus_ref(r4.x), z[0], m4.x);
+          w[1] = fmaf(softplus_ref(r4.y), z[1], m4.y);
+          w[2] = fmaf(softplus_ref(r4.z), z[2], m4.z);
+          w[3] = fmaf(softplus_ref(r4.w), z[3], m4.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ws[r][k + j] = w[j];
       }
-      ws[r][k] = w;
+    } else {
+      for (int i = threadIdx.x; i < TO * TK; i += 256) {
+        const int r = i / TK, k = i % TK;
+        const int o = o0 + r, kk = k0 + k;
+        float w = 0.f;
+        if (o < p.out && kk < p.in) {
+          const long long e = static_cast<long long>(o) * p.in + kk;
+          const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e]
+                                  : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
+          w = fmaf(softplus_ref(p.rho_w[e]), z, p.mu_w[e]);
+        }
+        ws[r][k] = w;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
       const float w = ws[tx][k];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xs[ty + 16 * j][k], w, acc[j]);
+      for (int j = 0; j < TB / 16; ++j) acc[j] = fmaf(xs[ty + 16 * j][k], w, acc[j]);
     }
     __syncthreads();
   }
@@ -73,7 +97,7 @@ sampled_linear_kernel(const LinearParams p) {
   }
   float* yg = p.y + static_cast<long long>(g) * p.y_gs;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < TB / 16; ++j) {
     const int b = b0 + ty + 16 * j;
     if (b < p.B) yg[static_cast<long long>(b) * p.ldy + o] = acc[j] + bias;
   }
