@@ -232,6 +232,18 @@ int mauv_maxpool_bwd_f16(const void* y, const float* scale_shift, const void* d1
 /* backward of the global average pool: dfeat [N][C] fp32 -> out [N][HW][C] fp16 = dfeat/HW * r, *s_out = r (first scale). */
 int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float target, unsigned int* amax_ws, void* out,
                          float* s_out, void* stream);
+/* Fused tail of a bottleneck with a downsample branch (torchvision resnet.py Bottleneck.forward: out = relu(bn3(conv3(.)) +
+ * downsample(x))): ONE contraction over K-concatenated operands [a1 | a2] * [s3*W3 | sd*Wd]^T + (t3 + td). The BN scales are
+ * folded into the sampled weights (mauv_sample_weights_scaled_f16), the shifts into the epilogue constants
+ * (mauv_bn_shift_sum); the statistics come from two mauv_gemm_bn_f16 mode-1 passes. a1 [G][M][K1], a2 [G][M][K2] (a strided
+ * downsample input is made dense with mauv_subsample_f16), w_cat [G][N][K1+K2], scale_shift [G][N][2] = (1, shift). */
+int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
+                         int relu, int G, long long M, int N, void* stream);
+int mauv_sample_weights_scaled_f16(const float* mu, const float* rho, const float* eps, uint64_t seed, uint32_t layer_id,
+                                   uint32_t sample0, int G, int cout, int cin, const float* scale_shift, int row_pitch,
+                                   int col0, void* w_out, void* stream);
+int mauv_bn_shift_sum(const float* scale_shift_a, const float* scale_shift_b, long long n, float* out, void* stream);
+int mauv_subsample_f16(const void* x, long long N, int H, int W, int C, int stride, void* out, void* stream);
 /* 3x3 / stride 1 / pad 1 conv with Cin = Cout = 64 (ResNet layer1 conv2: torchvision resnet.py Bottleneck.conv2) in
  * "padded stream" mode: tiles are 128 consecutive positions of the zero-padded pixel stream, one TMA box per filter row,
  * horizontal taps as shifted shared-memory descriptors, the sample's 9 weight blocks resident in shared memory. Same

@@ -320,6 +320,30 @@ nhwc_to_nchw_f32_kernel(const __half* __restrict__ x, int C, int HW, long long t
   out[i] = __half2float(x[(n * HW + hw) * C + c]);
 }
 
+
+// (scale, shift) pairs of two BatchNorms that are summed after normalisation -> (1, shift_a + shift_b): the epilogue
+// constants of the fused bottleneck tail whose scales were folded into the weights (mauv_gemm_bn_cat_f16).
+__global__ void __launch_bounds__(256)
+bn_shift_sum_kernel(const float2* __restrict__ a, const float2* __restrict__ b, long long n, float2* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2(1.f, a[i].y + b[i].y);
+}
+
+// x [N][H][W][C] -> out [N][Ho][Wo][C], out(p, q) = x(p*stride, q*stride): the input of a strided 1x1 conv (downsample
+// branch) as a dense matrix, so that the statistics pass and the fused pass can read it with tiled TMA.
+__global__ void __launch_bounds__(256)
+subsample_kernel(const uint4* __restrict__ x, int H, int W, int cvec, int Ho, int Wo, int stride, long long total,
+                 uint4* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % cvec);
+  long long t = i / cvec;
+  const int q = static_cast<int>(t % Wo); t /= Wo;
+  const int p = static_cast<int>(t % Ho);
+  const long long n = t / Ho;
+  out[i] = __ldg(x + ((n * H + static_cast<long long>(p) * stride) * W + static_cast<long long>(q) * stride) * cvec + cv);
+}
+
 }  // namespace
 
 extern "C" {
@@ -436,6 +460,25 @@ int mauv_nhwc_f16_to_nchw_f32(const void* x, long long N, int C, int HW, float* 
   nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), C, HW, total, out);
   MAUV_LAUNCH_CHECK("nhwc_to_nchw_f32_kernel");
+  return MAUV_OK;
+}
+
+int mauv_bn_shift_sum(const float* scale_shift_a, const float* scale_shift_b, long long n, float* out, void* stream) {
+  MAUV_CHECK_ARG(scale_shift_a && scale_shift_b && out && n >= 1, "mauv_bn_shift_sum: bad argument");
+  bn_shift_sum_kernel<<<static_cast<unsigned>(ceil_div_i64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(scale_shift_a), reinterpret_cast<const float2*>(scale_shift_b), n,
+      reinterpret_cast<float2*>(out));
+  MAUV_LAUNCH_CHECK("bn_shift_sum_kernel");
+  return MAUV_OK;
+}
+
+int mauv_subsample_f16(const void* x, long long N, int H, int W, int C, int stride, void* out, void* stream) {
+  MAUV_CHECK_ARG(x && out && C % 8 == 0 && stride >= 1, "mauv_subsample_f16: bad argument");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = N * Ho * Wo * (C / 8);
+  subsample_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), H, W, C / 8, Ho, Wo, stride, total, static_cast<uint4*>(out));
+  MAUV_LAUNCH_CHECK("subsample_kernel");
   return MAUV_OK;
 }
 

@@ -58,6 +58,8 @@ struct GemmParams {
   // weight-gradient mode (mauv_wgrad_f16): Y[batch][co][k] = sum_pixels dY[pixel][co] * Xcol[pixel][k]. Both operands are
   // MN-major: TMA boxes of [64 pixels][64 channels] straight from the row-major dY and the NHWC activations (tiled for
   // 1x1 / stride 1, im2col-mode for everything else); the batch index is (sample, pixel chunk), k_blocks = chunk / 64.
+  int a2_kb;             // > 0: tiled A is K-concatenated from two tensors: k-blocks >= a2_kb come from the map in the tmR
+                         //      slot (fused bottleneck tail with a downsample branch: [a2 | x] * [s3*W3 | sd*Wd]^T)
   int mn;                // 1: weight-gradient mode
   int b_im2col;          // mn: B boxes come from im2col-mode TMA (else tiled rows of [pixels][Cin])
   int cin;               // mn: input channels (column -> (tap, channel block))
@@ -233,8 +235,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t b_dst = a_dst + L::kABytes;
           mbar_expect_tx(full_bar(stage), L::kStageBytes);
           if (p.a_mode == 0) {
-            const int akb = p.a_wrap_kb ? kb % p.a_wrap_kb : kb;
-            tma_load_3d(a_dst, &tmA, full_bar(stage), akb * BK, m0, g * p.a_batch_mul);
+            if (p.a2_kb && kb >= p.a2_kb) {
+              tma_load_3d(a_dst, &tmR, full_bar(stage), (kb - p.a2_kb) * BK, m0, g);
+            } else {
+              const int akb = p.a_wrap_kb ? kb % p.a_wrap_kb : kb;
+              tma_load_3d(a_dst, &tmA, full_bar(stage), akb * BK, m0, g * p.a_batch_mul);
+            }
           } else {
             const int tap = kb / p.c_blocks;
             int cb = kb - tap * p.c_blocks;
@@ -721,7 +727,7 @@ int pick_bn(int N) {
 }
 
 int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream, int epi = 0,
-             const void* residual = nullptr) {
+             const void* residual = nullptr, const CUtensorMap* tmA2 = nullptr) {
   const int bn = (p.stack > 1 || epi == EPI_STATS_T) ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
@@ -740,6 +746,7 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
   if (epi == EPI_FUSED_BN && residual) {
     if (int rc = make_tiled_map(&tmR, residual, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
   }
+  if (tmA2) tmR = *tmA2;      // K-concatenated A (no residual in that mode): the spare map slot carries the second tensor
   if (epi == EPI_STATS_ONLY) {
     switch (bn) {
       case 64: return launch_gemm<64, 1>(tmA, tmB, tmY, tmR, p, stream);
@@ -1250,6 +1257,37 @@ int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial
     // the Y map describes [G][M][N]; with y aliased to A it is never written (EPI 1 issues no store)
   }
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream), mode, residual);
+}
+
+// Fused tail of a bottleneck WITH a downsample branch: out = relu(bn3(a1 * W3^T) + bnd(a2 * Wd^T)) as ONE contraction over
+// the K-concatenated operands [a1 | a2] * [s3*W3 | sd*Wd]^T + (t3 + td): the BatchNorm scales are folded into the sampled
+// weights (mauv_sample_weights_scaled_f16), the shifts into the epilogue (scale_shift = (1, t3 + td)). Neither raw conv
+// output ever reaches HBM. a1 [G][M][K1], a2 [G][M][K2], w_cat [G][N][K1+K2], K1 % 64 == 0.
+int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
+                         int relu, int G, long long M, int N, void* stream) {
+  MAUV_CHECK_ARG(a1 && a2 && w_cat && y && scale_shift, "mauv_gemm_bn_cat_f16: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 64 && N % 64 == 0 && N % pick_bn(N) == 0, "mauv_gemm_bn_cat_f16: N must be 64, 128 or a multiple of 256 (got %d)", N);
+  MAUV_CHECK_ARG(K1 >= 64 && K1 % 64 == 0 && K2 >= 8 && K2 % 8 == 0, "mauv_gemm_bn_cat_f16: K1 must be a multiple of 64, K2 of 8 (K1=%d K2=%d)", K1, K2);
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmA2, tmB;
+  if (int rc = make_tiled_map(&tmA, a1, K1, M, G, M * K1, BM)) return rc;
+  if (int rc = make_tiled_map(&tmA2, a2, K2, M, G, M * K2, BM)) return rc;
+  const int K = K1 + K2;
+  if (int rc = make_tiled_map(&tmB, w_cat, K, N, G, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  GemmParams p{};
+  p.stack = 1;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.a2_kb = K1 / BK;
+  p.k_blocks = p.a2_kb + static_cast<int>(ceil_div_i64(K2, BK));
+  p.G = G;
+  p.a_mode = 0;
+  p.a_batch_mul = 1;
+  p.y = static_cast<__half*>(y);
+  p.ss = reinterpret_cast<const float2*>(scale_shift);
+  p.has_res = 0;
+  p.relu = relu;
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream), EPI_FUSED_BN, nullptr, &tmA2);
 }
 
 int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,

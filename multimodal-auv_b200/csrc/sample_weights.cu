@@ -25,6 +25,8 @@ struct SampleParams {
   long long n;        // cout*cin*kh*kw
   __half* w;          // [G][cout][k_pad]   (dgrad: [G][cin][kh*kw*cout], taps flipped)
   int dgrad;          // 1: write the transposed + spatially flipped layout the data-gradient conv consumes
+  const float2* row_scale;   // optional [G][cout] (scale, shift): w *= scale (a BatchNorm scale folded into the weights)
+  long long g_stride; // elements between consecutive samples in w (0 = dense default)
 };
 
 __device__ __forceinline__ void normals4(uint64_t seed, uint32_t layer, uint32_t sample,
@@ -87,7 +89,8 @@ sample_weights_kernel(const SampleParams p, int G) {
                        : co * p.k_pad + static_cast<long long>(rs) * p.cin + c;
     }
   }
-  const long long w_stride = p.dgrad ? static_cast<long long>(p.cin) * p.k_pad : static_cast<long long>(p.cout) * p.k_pad;
+  const long long w_stride = p.g_stride ? p.g_stride
+                             : (p.dgrad ? static_cast<long long>(p.cin) * p.k_pad : static_cast<long long>(p.cout) * p.k_pad);
   for (int g = 0; g < G; ++g) {
     float z[4];
     if (p.eps) {
@@ -100,6 +103,13 @@ sample_weights_kernel(const SampleParams p, int G) {
     float w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[i] = fmaf(sg[i], z[i], mu[i]);
+    if (p.row_scale) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long co = (e0 + i) / per_out;
+        if (co < p.cout) w[i] *= p.row_scale[static_cast<long long>(g) * p.cout + co].x;
+      }
+    }
     __half* wg = p.w + static_cast<long long>(g) * w_stride;
     if (direct) {
       __half2 h0 = __floats2half2_rn(w[0], w[1]);
@@ -165,9 +175,34 @@ int mauv_sample_weights_f16(const float* mu, const float* rho, const float* eps,
   p.n = static_cast<long long>(cout) * K;
   p.w = static_cast<__half*>(w_out);
   p.dgrad = 0;
+  p.row_scale = nullptr;
+  p.g_stride = 0;
   const long long quads = ceil_div_i64(p.n, 4);
   sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, st>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel");
+  return MAUV_OK;
+}
+
+// 1x1 conv / linear weights sampled into a column block of a wider (K-concatenated) operand, each output row multiplied by
+// a per-(sample, row) BatchNorm scale: w_out[g][co][col0 + c] = scale[g][co] * (mu + log1p(exp(rho)) * eps)[co][c].
+// row_pitch = total columns of the concatenated operand; scale_shift [G][cout][2] as written by mauv_bn_finalize.
+int mauv_sample_weights_scaled_f16(const float* mu, const float* rho, const float* eps, uint64_t seed, uint32_t layer_id,
+                                   uint32_t sample0, int G, int cout, int cin, const float* scale_shift, int row_pitch,
+                                   int col0, void* w_out, void* stream) {
+  MAUV_CHECK_ARG(mu && rho && w_out && scale_shift, "mauv_sample_weights_scaled_f16: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && cout >= 1 && cin >= 1 && cin % 4 == 0 && row_pitch % 8 == 0 && col0 % 8 == 0 && col0 + cin <= row_pitch,
+                 "mauv_sample_weights_scaled_f16: bad layout (cin=%d row_pitch=%d col0=%d)", cin, row_pitch, col0);
+  SampleParams p;
+  p.mu = mu; p.rho = rho; p.eps = eps; p.seed = seed; p.layer_id = layer_id; p.sample0 = sample0;
+  p.cout = cout; p.cin = cin; p.kh = 1; p.kw = 1; p.k_pad = row_pitch;
+  p.n = static_cast<long long>(cout) * cin;
+  p.w = static_cast<__half*>(w_out) + col0;
+  p.dgrad = 0;
+  p.row_scale = reinterpret_cast<const float2*>(scale_shift);
+  p.g_stride = static_cast<long long>(cout) * row_pitch;
+  const long long quads = ceil_div_i64(p.n, 4);
+  sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
+  MAUV_LAUNCH_CHECK("sample_weights_kernel(scaled)");
   return MAUV_OK;
 }
 
@@ -185,6 +220,8 @@ int mauv_sample_weights_dgrad_f16(const float* mu, const float* rho, const float
   p.n = static_cast<long long>(cout) * cin * kh * kw;
   p.w = static_cast<__half*>(w_out);
   p.dgrad = 1;
+  p.row_scale = nullptr;
+  p.g_stride = 0;
   const long long quads = ceil_div_i64(p.n, 4);
   sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel(dgrad)");

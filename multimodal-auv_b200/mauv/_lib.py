@@ -62,6 +62,10 @@ SIGNATURES = {
     "mauv_bn_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, i64, i32, vp, vp, vp, vp, vp, vp]),
     "mauv_maxpool_bwd_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mauv_avgpool_bwd_f16": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
+    "mauv_gemm_bn_cat_f16": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, i32, i64, i32, vp]),
+    "mauv_sample_weights_scaled_f16": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "mauv_bn_shift_sum": (i32, [vp, vp, i64, vp, vp]),
+    "mauv_subsample_f16": (i32, [vp, i64, i32, i32, i32, i32, vp, vp]),
     "mauv_conv3x3_c64_tiles": (i32, [i32, i32, i32]),
     "mauv_conv3x3_c64_f16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "mauv_wgrad_f16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -250,6 +250,10 @@ class MCEngine:
                 x = ops.gemm_bn_act_f16(a2v, w3, ss3, residual=x.view(G, B * H * W, c3.cout), relu=True).view(NB, H, W, c3.cout)
                 self.launches += 2
                 continue
+            if (blk.down is not None and self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k
+                    and blk.down.cin <= self.fuse_conv3_max_k and blk.down.k == 1 and blk.down.pad == 0):
+                x = self._fused_downsample_tail(blk, a2, x, G, B, s0, eps, seed)
+                continue
             y3, ss3 = self._conv_bn(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
             if blk.down is not None:
                 yd, ssd = self._conv_bn(blk.down, blk.down_bn, x, G, B, s0, eps, seed)
@@ -260,6 +264,30 @@ class MCEngine:
         feat = ops.avgpool_f16(x)                                                 # [G*B, 2048] fp32
         self.launches += 1
         return feat.view(G, B, -1)
+
+    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed):
+        """relu(bn3(conv3(a2)) + bn_d(conv_d(x))) without either raw conv output in HBM: two statistics passes (recompute
+        scheme), then ONE contraction over K-concatenated operands [a2 | x'] * [s3*W3 | sd*Wd]^T + (t3 + td) - the BN scales
+        folded into freshly sampled weights, the shifts into the epilogue. x' = x for stride 1, else x subsampled."""
+        c3, cd = blk.conv3, blk.down
+        NB, H, W, Cm = a2.shape
+        M = B * H * W
+        a2v = a2.view(G, M, Cm)
+        xs = x if cd.stride == 1 else ops.subsample_f16(x, cd.stride)
+        assert xs.shape[1] == H and xs.shape[2] == W
+        xv = xs.view(G, M, cd.cin)
+        w3 = self._sample(c3, G, s0, eps, seed)
+        wd = self._sample(cd, G, s0, eps, seed)
+        ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), M, blk.bn3, G)
+        ssd = self._bn(ops.gemm_stats_f16(xv, wd), M, blk.down_bn, G)
+        wcat = torch.empty((G, c3.cout, Cm + cd.cin), dtype=F16, device=self.device)
+        ops.sample_weights_scaled_f16(c3.layer.mu_kernel.detach(), c3.layer.rho_kernel.detach(), G, ss3, wcat, 0,
+                                      eps=self._eps_w(eps, c3.name, s0, G), seed=seed, layer_id=c3.layer_id, sample0=s0)
+        ops.sample_weights_scaled_f16(cd.layer.mu_kernel.detach(), cd.layer.rho_kernel.detach(), G, ssd, wcat, Cm,
+                                      eps=self._eps_w(eps, cd.name, s0, G), seed=seed, layer_id=cd.layer_id, sample0=s0)
+        out = ops.gemm_bn_cat_f16(a2v, xv, wcat, ops.bn_shift_sum(ss3, ssd), relu=True)
+        self.launches += 9 + (cd.stride != 1)
+        return out.view(NB, H, W, c3.cout)
 
     # ------------------------------------------------------------------ head
     def _linear(self, layer, name, x, G, s0, eps, seed, out=None, out_col=0):

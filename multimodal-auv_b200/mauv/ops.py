@@ -211,6 +211,44 @@ def conv2d_im2col_f16(x: torch.Tensor, w: torch.Tensor, G: int, kh: int, kw: int
     return out, (stats_out if stats else None)
 
 
+def sample_weights_scaled_f16(mu, rho, G, ss, out, col0, *, eps=None, seed=0, layer_id=0, sample0=0) -> None:
+    """1x1 weights [cout, cin(,1,1)] sampled into columns [col0, col0+cin) of out [G, cout, Ktot], rows scaled by ss[g, co, 0]"""
+    lib = _lib.require_device()
+    cout, cin = mu.shape[0], mu.shape[1]
+    assert mu.numel() == cout * cin and out.shape[0] == G and out.shape[1] == cout
+    _run("mauv_sample_weights_scaled_f16", lib.mauv_sample_weights_scaled_f16, _ptr(mu, F32), _ptr(rho, F32), _ptr(eps, F32), seed,
+         layer_id, sample0, G, cout, cin, _ptr(ss, F32), out.shape[2], col0, _ptr(out, F16), _stream())
+
+
+def bn_shift_sum(ss_a: torch.Tensor, ss_b: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    out = torch.empty_like(ss_a)
+    _run("mauv_bn_shift_sum", lib.mauv_bn_shift_sum, _ptr(ss_a, F32), _ptr(ss_b, F32), ss_a.numel() // 2, _ptr(out), _stream())
+    return out
+
+
+def subsample_f16(x: torch.Tensor, stride: int) -> torch.Tensor:
+    lib = _lib.require_device()
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, (H - 1) // stride + 1, (W - 1) // stride + 1, Cc), dtype=F16, device=x.device)
+    _run("mauv_subsample_f16", lib.mauv_subsample_f16, _ptr(x, F16), N, H, W, Cc, stride, _ptr(out), _stream())
+    return out
+
+
+def gemm_bn_cat_f16(a1: torch.Tensor, a2: torch.Tensor, w_cat: torch.Tensor, shift: torch.Tensor, *, relu: bool = True) -> torch.Tensor:
+    """relu?([a1 | a2] * w_cat^T + shift): a1 [G, M, K1], a2 [G, M, K2], w_cat [G, N, K1+K2], shift [G, N, 2] -> [G, M, N]"""
+    lib = _lib.require_device()
+    G, M, K1 = a1.shape
+    K2 = a2.shape[2]
+    N = w_cat.shape[1]
+    assert w_cat.shape[2] == K1 + K2 and a2.shape[:2] == a1.shape[:2]
+    out = torch.empty((G, M, N), dtype=F16, device=a1.device)
+    _run("mauv_gemm_bn_cat_f16", lib.mauv_gemm_bn_cat_f16, _ptr(a1, F16), K1, _ptr(a2, F16), K2, _ptr(w_cat, F16), _ptr(out),
+         _ptr(shift, F32), int(relu), G, M, N, _stream(),
+         tag=f"fused G{G} M{M} N{N} K{K1 + K2} cat" if _prof is not None else None)
+    return out
+
+
 STREAM_CONV = __import__("os").environ.get("MAUV_STREAM_CONV", "1") != "0"
 
 

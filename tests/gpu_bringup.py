@@ -279,6 +279,32 @@ def t_gemm_bn(G, M, N, K, res=True):
               " bad rows:", torch.unique(bad[:, 1])[:12].tolist(), " bad cols:", torch.unique(bad[:, 2])[:12].tolist())
 
 
+def t_gemm_bn_cat(G, M, N, K1, K2):
+    """Fused downsample tail: relu(s3*(a1 W3^T) + t3 + sd*(a2 Wd^T) + td) as one K-concatenated contraction with the BN
+    scales folded into the sampled weights (injected eps) and the shifts summed into the epilogue."""
+    torch.manual_seed(51)
+    a1 = (torch.randn(G, M, K1) * 0.5).half()
+    a2 = (torch.randn(G, M, K2) * 0.5).half()
+    mu3, mud = torch.randn(N, K1, 1, 1) * 0.05, torch.randn(N, K2, 1, 1) * 0.05
+    rho3, rhod = torch.randn(N, K1, 1, 1) - 3, torch.randn(N, K2, 1, 1) - 3
+    e3, ed = torch.randn(G, N, K1, 1, 1), torch.randn(G, N, K2, 1, 1)
+    ss3 = torch.stack([torch.rand(G, N) + 0.5, torch.randn(G, N) * 0.2], -1).contiguous()
+    ssd = torch.stack([torch.rand(G, N) * 2 + 0.2, torch.randn(G, N) * 0.2], -1).contiguous()
+    w3 = (mu3 + torch.log1p(torch.exp(rho3)) * e3).view(G, N, K1)
+    wd = (mud + torch.log1p(torch.exp(rhod)) * ed).view(G, N, K2)
+    ref = torch.relu(torch.einsum("gmk,gnk->gmn", a1.float(), w3) * ss3[:, None, :, 0] + ss3[:, None, :, 1]
+                     + torch.einsum("gmk,gnk->gmn", a2.float(), wd) * ssd[:, None, :, 0] + ssd[:, None, :, 1])
+    wcat = torch.empty(G, N, K1 + K2, dtype=torch.float16, device=dev)
+    ops.sample_weights_scaled_f16(mu3.to(dev), rho3.to(dev), G, ss3.to(dev), wcat, 0, eps=e3.to(dev).contiguous())
+    ops.sample_weights_scaled_f16(mud.to(dev), rhod.to(dev), G, ssd.to(dev), wcat, K1, eps=ed.to(dev).contiguous())
+    wref = torch.cat([w3 * ss3[..., 0:1], wd * ssd[..., 0:1]], -1)
+    report(f"scaled concat weights G={G} N={N} K={K1}+{K2}", wcat, wref, 1e-3)
+    out = ops.gemm_bn_cat_f16(a1.to(dev), a2.to(dev), wcat, ops.bn_shift_sum(ss3.to(dev), ssd.to(dev)))
+    report(f"gemm_bn_cat G={G} M={M} N={N} K={K1}+{K2}", out, ref, 3e-3)
+    x = torch.randn(3, 9, 10, 64).half()
+    report("subsample /2", ops.subsample_f16(x.to(dev), 2), x[:, ::2, ::2, :], 0.0)
+
+
 def t_conv(G, B, H, W, Cin, Cout, k, stride, pad):
     torch.manual_seed(8)
     x = (torch.randn(G * B, H, W, Cin, device=dev) * 0.5).half()
@@ -745,6 +771,8 @@ GROUPS = {
     "gemm_bn": lambda: [run_case(t_gemm_bn, *a) for a in [
         (2, 1000, 256, 64), (3, 4096, 512, 128), (1, 40, 64, 64), (2, 20000, 256, 64), (1, 300, 128, 128, False),
         (4, 65536, 256, 64)]],
+    "gemm_bn_cat": lambda: [run_case(t_gemm_bn_cat, *a) for a in [(2, 1000, 256, 64, 64), (3, 4096, 512, 128, 256),
+                                                                  (1, 300, 256, 64, 64), (2, 20000, 256, 64, 64)]],
     "conv": lambda: [run_case(t_conv, *a) for a in [
         (1, 2, 8, 8, 64, 64, 1, 1, 0), (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1),
         (1, 1, 16, 16, 256, 512, 1, 2, 0), (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1),

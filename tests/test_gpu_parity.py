@@ -103,6 +103,13 @@ def test_tcgen05_gemm_fused_batchnorm_residual_epilogue(bu, shape):
     _run(bu, bu.t_gemm_bn, *shape)
 
 
+@pytest.mark.parametrize("shape", [(2, 1000, 256, 64, 64), (3, 4096, 512, 128, 256), (1, 300, 256, 64, 64), (2, 20000, 256, 64, 64)])
+def test_fused_downsample_tail_k_concatenated(bu, shape):
+    """relu(bn3(conv3(a)) + bn_d(conv_d(x))) as ONE tcgen05 contraction over K-concatenated operands, BN scales folded into
+    the sampled weights, shifts in the epilogue: vs the fp32 composition of the same terms, 3e-3 of max."""
+    _run(bu, bu.t_gemm_bn_cat, *shape)
+
+
 @pytest.mark.parametrize("shape", [
     (1, 2, 8, 8, 64, 64, 3, 1, 1), (2, 2, 16, 16, 128, 128, 3, 2, 1), (1, 1, 16, 16, 256, 512, 1, 2, 0),
     (2, 4, 16, 16, 64, 256, 3, 1, 1), (2, 3, 10, 12, 64, 64, 3, 1, 1), (1, 2, 4, 4, 512, 512, 3, 1, 1),
