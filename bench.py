@@ -234,7 +234,7 @@ def run_ours(args):
             fc, ft = fam.get(b, (0, 0.0))
             fam[b] = (fc + c, ft + t)
         # all launches of the tcgen05 kernels (gemm_f16_tc_kernel and its padded-stream sibling for layer1's 3x3 conv)
-        tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16")
+        tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16")
         conv_calls = sum(fam.get(k, (0, 0.0))[0] for k in tc)
         conv_ms = sum(fam.get(k, (0, 0.0))[1] for k in tc)
         if args.detail:
