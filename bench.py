@@ -290,9 +290,9 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tc_kernel + conv3x3_c64_stream_kernel (tcgen05 implicit-GEMM conv, all 159 convs)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_source": peak_src,
-                         # mean DRAM read+write bytes per launch of this kernel over the 586 launches of
-                         # profiles/r1_bench_launch_list.csv.gz (ncu dram__bytes_read.sum + dram__bytes_write.sum)
-                         "traffic": 2.674e9,
+                         # mean DRAM read+write bytes per launch of these kernels over their 587 launches in one step,
+                         # profiles/r1b_bench_launch_list.csv.gz (ncu dram__bytes_read.sum + dram__bytes_write.sum)
+                         "traffic": 2.586e9,
                          "note": "algorithmic FLOPs (31.824 GFLOP per triplet-sample, recompute passes not counted) / "
                                  "summed launch durations; by shape the kernel runs at 0.89-0.94 of the tensor peak "
                                  "(K >= 2304) and at ~0.87 of the 3.9 TB/s HBM write-only peak on the wide-N 1x1 layers",
