@@ -87,15 +87,22 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- model
+MODEL_KIND = "multimodal"      # --model: cfg4 benches one unimodal ResNet50Custom branch ("image" | "bathy" | "sss")
+GFLOP_PER_SAMPLE = {"multimodal": CONV_GFLOP_PER_TRIPLET_SAMPLE, "image": 10.677, "bathy": 10.677, "sss": 10.471}
+
+
 def build_model_cpu(seed: int = 1234):
     """Random-init (torchvision default init) + MOPED(delta=0.1) multimodal BNN, as BASELINE.md §4."""
     from mauv.bayesian import dnn_to_bnn
-    from mauv.models.base_models import MultiModalModel
+    from mauv.models.base_models import MultiModalModel, ResNet50Custom
     from mauv.models.model_utils import load_pretrained_resnet_as_feature_extractor as feat
     import logging
     logging.disable(logging.WARNING)
     torch.manual_seed(seed)
-    m = MultiModalModel(feat(), feat(), feat(input_channels=1), C_CLASSES)
+    if MODEL_KIND == "multimodal":
+        m = MultiModalModel(feat(), feat(), feat(input_channels=1), C_CLASSES)
+    else:
+        m = ResNet50Custom(1 if MODEL_KIND == "sss" else 3, C_CLASSES)
     prior = {"prior_mu": 0.0, "prior_sigma": 1.0, "posterior_mu_init": 0.0, "posterior_rho_init": -3.0,
              "type": "Reparameterization", "moped_enable": True, "moped_delta": 0.1}
     dnn_to_bnn(m, prior)
@@ -107,6 +114,8 @@ def synthetic_inputs(B: int, seed: int = 1234, pin: bool = False):
     g = torch.Generator().manual_seed(seed)
     xs = [torch.randn((B, 3, SIZE, SIZE), generator=g), torch.rand((B, 3, SIZE, SIZE), generator=g),
           torch.rand((B, 1, SIZE, SIZE), generator=g)]
+    if MODEL_KIND != "multimodal":
+        xs = [xs[("image", "bathy", "sss").index(MODEL_KIND)]]
     return [x.pin_memory() for x in xs] if pin else xs
 
 
@@ -216,7 +225,7 @@ def run_ours(args):
     prof = ops.stop_profile()
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and MODEL_KIND == "multimodal":   # the CPU arm is the headline config
         cores = os.cpu_count() or 1
         t = cpu_reference_pass(cores, 4, 3, autocast=True)[1:]
         per_pass = sum(t) / len(t)
@@ -271,15 +280,18 @@ def run_ours(args):
             ideal_ms += c * max(t_tc, t_hbm)
             hbm_bound_ms += t if t_hbm > t_tc else 0.0
         s_local = hi - lo
-        conv_tflop = CONV_GFLOP_PER_TRIPLET_SAMPLE * B * s_local / 1e3
+        conv_tflop = GFLOP_PER_SAMPLE[MODEL_KIND] * B * s_local / 1e3
         achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
         total_prof = sum(v[1] for v in fam.values()) or 1.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if MODEL_KIND == "multimodal" else f"MC-sampled patches/sec (S={S}, unimodal {MODEL_KIND} branch)",
+            "value": value, "unit": UNIT if MODEL_KIND == "multimodal" else "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate+statistics (reference predictor: autocast fp16 on CUDA)",
             "data": "synthetic",
-            "config": {"workload": f"cfg2 multimodal BNN inference B={B} S={S} 256x256 C={C_CLASSES}, MC samples sharded over "
+            "config": {"workload": f"{'cfg2 multimodal' if MODEL_KIND == 'multimodal' else 'cfg4 unimodal ' + MODEL_KIND} BNN inference "
+                                   f"B={B} S={S} 256x256 C={C_CLASSES}, MC samples sharded over "
                                    f"{world} GPU(s), group={group}",
                        "l2": "no flush: per-step inputs (470 MB) and activations (GBs) exceed the 126 MB L2",
                        "triplet_samples_per_s": value * S},
@@ -419,11 +431,13 @@ def run_train(args):
     if rank != 0:
         torch.distributed.destroy_process_group()
         return 0
-    flops = 94.77e9 * world * B * S      # forward + dgrad + wgrad per triplet-sample
+    # forward + dgrad + wgrad per triplet-sample (a unimodal branch: ~1/3 of it)
+    flops = 94.77e9 * (GFLOP_PER_SAMPLE[MODEL_KIND] / CONV_GFLOP_PER_TRIPLET_SAMPLE) * world * B * S
     line = {"metric": "ELBO training triplets/sec", "value": world * B / (ms / 1e3), "unit": UNIT,
             "n_gpus": world, "scaling": "weak", "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients",
-            "config": {"workload": f"cfg3 multimodal ELBO step, {B} triplets per GPU, S={S}, 256x256, C=7, Adam, "
+            "config": {"workload": f"{'cfg3 multimodal' if MODEL_KIND == 'multimodal' else 'cfg4 unimodal ' + MODEL_KIND} ELBO step, "
+                                   f"{B} triplets per GPU, S={S}, 256x256, C=7, Adam, "
                                    f"path={args.train_path}, gradient all-reduce over {world} GPU(s)",
                        "triplet_samples_per_s": world * B * S / (ms / 1e3)},
             "model_tflops": flops / (ms / 1e3) / 1e12,
@@ -450,9 +464,13 @@ def main():
     ap.add_argument("--detail", action="store_true", help="per-shape kernel table on stderr")
     ap.add_argument("--train-path", default="engine", choices=["engine", "layers"],
                     help="--workload train: S-batched TrainEngine (default) or the drop-in layer path")
+    ap.add_argument("--model", default="multimodal", choices=["multimodal", "image", "bathy", "sss"],
+                    help="multimodal (cfg2 / cfg3, the headline) or one unimodal ResNet50Custom branch (cfg4)")
     ap.add_argument("--workload", default="inference", choices=["inference", "train"],
                     help="inference = BASELINE cfg2 (headline); train = cfg3-style ELBO step (secondary)")
     args = ap.parse_args()
+    global MODEL_KIND
+    MODEL_KIND = args.model
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.workload == "train" and args.impl == "ours":
