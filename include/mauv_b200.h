@@ -249,8 +249,10 @@ int mauv_subsample_f16(const void* x, long long N, int H, int W, int C, int stri
  * horizontal taps as shifted shared-memory descriptors, the sample's 9 weight blocks resident in shared memory. Same
  * results as mauv_conv2d_im2col_f16; statistics partials are [G][mauv_conv3x3_c64_tiles()][64][2]. W <= 254. */
 int mauv_conv3x3_c64_tiles(int imgs_per_sample, int H, int W);
-int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, int G, int imgs_per_sample, int H,
-                         int W, void* stream);
+/* in_scale_shift (nullable) [G][64][2]: x is the RAW output of the previous conv and relu(x*scale + shift) - that layer's
+ * BatchNorm + ReLU - is applied to each tile in shared memory before the MMAs (the activated tensor never exists in HBM). */
+int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, const float* in_scale_shift, int G,
+                         int imgs_per_sample, int H, int W, void* stream);
 /* Weight gradient of the grouped conv straight from the NHWC tensors (no transposed copies): dy [G*imgs][Ho][Wo][Cout],
  * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] fp16 partial sums over pixel chunks (K order (r, s, c)). Both
  * operands enter the tcgen05 MMA MN-major from [64 pixels][64 channels] TMA boxes (tiled for 1x1/stride 1, im2col mode

@@ -789,6 +789,10 @@ struct StreamParams {
   int base_offset_mode;                    // 1: descriptor base_offset = start row mod 8
   __half* y;                               // [G*imgs][H][W][64]
   float* stats;                            // [G][m_tiles][64][2] or nullptr
+  // optional input transform: the kernel is handed the RAW output of the previous conv and applies that layer's
+  // BatchNorm + ReLU to the tile in shared memory (in_ss [G][64] (scale, shift)); padding positions stay zero. The
+  // activated tensor is then never written to / re-read from HBM.
+  const float2* in_ss;
 };
 
 constexpr int kStreamBox = 130;                       // positions per TMA box (128 + 2 for the horizontal taps)
@@ -797,10 +801,10 @@ constexpr int kStreamBBytes = 9 * 8192;
 constexpr int kStreamABytes = 3 * kStreamRegion;      // per stage
 constexpr int kStreamStages = 2;
 constexpr int kStreamOutBytes = 8 * 4096;             // per epilogue warp: 32 rows x 128 B staging (for the statistics)
-constexpr int kStreamStatBytes = 2 * 4 * 64 * 2 * 4;
+constexpr int kStreamStatBytes = 2 * 4 * 64 * 2 * 4 + 512;   // + 512: padding flags of the input transform
 constexpr int kStreamSmem = 1024 + kStreamBBytes + kStreamStages * kStreamABytes + kStreamOutBytes + kStreamStatBytes + 256;
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -817,6 +821,7 @@ conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (6 + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (8 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * 10;
+  auto a_ready = [&](int s) { return bar_base + 8u * (12 + s); };     // input transform done (4 warps arrive)
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + kStreamBBytes + kStreamStages * kStreamABytes + kStreamOutBytes + kStreamStatBytes + 8 * 10);
 
@@ -835,6 +840,7 @@ conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), 4);
+      mbar_init(a_ready(a), 4);
     }
     mbar_fence_init();
   }
@@ -886,7 +892,7 @@ conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
-        mbar_wait(a_full(stage), phase);
+        mbar_wait(p.in_ss ? a_ready(stage) : a_full(stage), phase);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64;
 #pragma unroll
@@ -901,6 +907,65 @@ conv3x3_c64_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         umma_commit(a_empty(stage));
         umma_commit(tmem_full_bar(acc));
+        if (++stage == kStreamStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 12) {
+    // ===================== input transform (optional): a = relu(y * scale + shift) in place, padding stays zero ==========
+    // 128 threads. Thread t owns the LOGICAL 16-byte chunk lc = t & 7 (channels 8*lc .. 8*lc+7: its 8 (scale, shift) pairs
+    // live in registers) of the rows (t >> 3) + 16*i of the 3 x 130-row boxes; the physical chunk is lc ^ (row & 7)
+    // (128B swizzle). Which rows are conv padding is worked out once per tile (3 rows per thread) into shared memory.
+    if (p.in_ss) {
+      const int t = threadIdx.x - 384;          // 0..127
+      const int lc = t & 7;
+      uint8_t* inside_flag = reinterpret_cast<uint8_t*>(stat_smem) + kStreamStatBytes - 512;   // 3*130 flags (spare tail)
+      float sc[8], sh[8];
+      int stage = 0, cur_g = -1;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int g = static_cast<int>(tile / p.m_tiles);
+        const int m_tile = static_cast<int>(tile - static_cast<long long>(g) * p.m_tiles);
+        if (g != cur_g) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 v2 = p.in_ss[static_cast<long long>(g) * 64 + lc * 8 + q];
+            sc[q] = v2.x; sh[q] = v2.y;
+          }
+          cur_g = g;
+        }
+        const int v0 = m_tile * 128;
+        const int hwp_i = static_cast<int>(hwp);
+        for (int i = t; i < 3 * kStreamBox; i += 128) {
+          const int r = i / kStreamBox, row = i - r * kStreamBox;
+          const int v = v0 + row;
+          const int img = v / hwp_i;
+          const int r2 = v - img * hwp_i;
+          const int pr = r2 / p.Wp, j = r2 - pr * p.Wp;
+          const int h = pr + r - 1;
+          inside_flag[i] = (j >= 1 && j <= p.W && h >= 0 && h < p.H) ? 1 : 0;       // else: zero-filled conv padding
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        mbar_wait(a_full(stage), phase);
+        for (int i = t >> 3; i < 3 * kStreamBox; i += 16) {
+          const int r = i / kStreamBox, row = i - r * kStreamBox;
+          const uint32_t addr = a_base + stage * kStreamABytes + r * kStreamRegion + row * 128 + ((lc ^ (row & 7)) << 4);
+          uint32_t wv[4];
+          if (inside_flag[i]) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(addr));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(*reinterpret_cast<__half2*>(&wv[q]));
+              __half2 o = __floats2half2_rn(fmaxf(fmaf(f.x, sc[2 * q], sh[2 * q]), 0.f),
+                                            fmaxf(fmaf(f.y, sc[2 * q + 1], sh[2 * q + 1]), 0.f));
+              wv[q] = *reinterpret_cast<uint32_t*>(&o);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+          }       // padding rows were zero-filled by TMA and stay zero
+        }
+        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(a_ready(stage));
+        asm volatile("bar.sync 3, 128;" ::: "memory");      // flags are rewritten for the next tile
         if (++stage == kStreamStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -1043,8 +1108,8 @@ int mauv_conv3x3_c64_tiles(int imgs_per_sample, int H, int W) {
   return static_cast<int>(ceil_div_i64(static_cast<long long>(imgs_per_sample) * H * (W + 2), 128));
 }
 
-int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, int G, int imgs_per_sample, int H,
-                         int W, void* stream) {
+int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, const float* in_scale_shift, int G,
+                         int imgs_per_sample, int H, int W, void* stream) {
   MAUV_CHECK_ARG(x && w && y && G >= 1 && imgs_per_sample >= 1 && H >= 1 && W >= 1 && W <= 254, "mauv_conv3x3_c64_f16: bad argument");
   MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(y) & 15) == 0, "mauv_conv3x3_c64_f16: pointers must be 16-byte aligned");
@@ -1074,13 +1139,14 @@ int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_par
   p.base_offset_mode = 0;
   p.y = static_cast<__half*>(y);
   p.stats = stats_partial;
+  p.in_ss = reinterpret_cast<const float2*>(in_scale_shift);
   static bool attr_set = false;
   if (!attr_set) {
     MAUV_CUDA(cudaFuncSetAttribute(conv3x3_c64_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  conv3x3_c64_stream_kernel<<<static_cast<unsigned>(grid), 384, kStreamSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  conv3x3_c64_stream_kernel<<<static_cast<unsigned>(grid), 512, kStreamSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   MAUV_LAUNCH_CHECK("conv3x3_c64_stream_kernel");
   return MAUV_OK;
 }

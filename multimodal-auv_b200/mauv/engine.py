@@ -104,6 +104,7 @@ class MCEngine:
         # recompute-fusion of conv3 + bn3 + residual + ReLU (removes the y3 write and re-read) for bottlenecks whose
         # conv3 has K <= fuse_conv3_max_k (layer1/layer2: HBM-write bound; deeper ones are tensor bound)
         self.fuse_conv3 = True
+        self.fuse_input_bn = os.environ.get("MAUV_FUSE_INPUT_BN", "0") == "1"
         self.fuse_conv3_max_k = int(os.environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
 
     # ------------------------------------------------------------------ planning
@@ -236,8 +237,19 @@ class MCEngine:
         del y
         for blk in t.blocks:
             y1, ss1 = self._conv_bn(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
-            a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
-            y2, ss2 = self._conv_bn(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
+            c2 = blk.conv2
+            if (self.fuse_input_bn and ops.STREAM_CONV and c2.cin == 64 and c2.cout == 64 and c2.k == 3 and c2.stride == 1
+                    and c2.pad == 1 and y1.shape[2] <= 254):
+                # layer1: bn1 + ReLU applied to conv2's input tiles in shared memory (padded-stream kernel), a1 never reaches
+                # HBM. Correct (tested) but OFF by default: with 4 transform warps the in-smem pass costs 1.75 ms per launch
+                # at cfg2 against the 0.44 ms bn_act pass it replaces (measured: 79 vs 31.6 + 12 ms per step).
+                w2 = self._sample(c2, G, s0, eps, seed)
+                y2, st2 = ops.conv3x3_c64_f16(y1, w2, G, stats=True, in_ss=ss1)
+                ss2 = self._bn(st2, y2.numel() // (G * c2.cout), blk.bn2, G)
+                self.launches += 1
+            else:
+                a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
+                y2, ss2 = self._conv_bn(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
             a2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True)
             if blk.down is None and self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k:
                 # HBM-write-bound tail of the bottleneck: recompute scheme. Pass 1 = statistics of conv3 only,

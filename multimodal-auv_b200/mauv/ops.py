@@ -252,16 +252,17 @@ def gemm_bn_cat_f16(a1: torch.Tensor, a2: torch.Tensor, w_cat: torch.Tensor, shi
 STREAM_CONV = __import__("os").environ.get("MAUV_STREAM_CONV", "1") != "0"
 
 
-def conv3x3_c64_f16(x: torch.Tensor, w: torch.Tensor, G: int, *, stats: bool = False):
-    """3x3 / stride 1 / pad 1, 64 -> 64 channels (padded-stream kernel). x [G*B, H, W, 64], w [G, 64, 576]."""
+def conv3x3_c64_f16(x: torch.Tensor, w: torch.Tensor, G: int, *, stats: bool = False, in_ss: Optional[torch.Tensor] = None):
+    """3x3 / stride 1 / pad 1, 64 -> 64 channels (padded-stream kernel). x [G*B, H, W, 64], w [G, 64, 576].
+    in_ss [G, 64, 2]: x is a raw conv output; relu(x * scale + shift) is applied to the tiles in shared memory."""
     lib = _lib.require_device()
     NB, H, W, Cin = x.shape
     assert Cin == 64 and tuple(w.shape) == (G, 64, 576) and NB % G == 0
     B = NB // G
     out = torch.empty((NB, H, W, 64), dtype=F16, device=x.device)
     st = torch.empty((G, lib.mauv_conv3x3_c64_tiles(B, H, W), 64, 2), dtype=F32, device=x.device) if stats else None
-    _run("mauv_conv3x3_c64_f16", lib.mauv_conv3x3_c64_f16, _ptr(x, F16), _ptr(w, F16), _ptr(out), _ptr(st), G, B, H, W, _stream(),
-         tag=f"G{G} M{B * H * W} N64 K576 stream" if _prof is not None else None)
+    _run("mauv_conv3x3_c64_f16", lib.mauv_conv3x3_c64_f16, _ptr(x, F16), _ptr(w, F16), _ptr(out), _ptr(st), _ptr(in_ss, F32), G, B, H,
+         W, _stream(), tag=f"G{G} M{B * H * W} N64 K576 stream{'+bn' if in_ss is not None else ''}" if _prof is not None else None)
     return out, st
 
 

@@ -305,6 +305,24 @@ def t_gemm_bn_cat(G, M, N, K1, K2):
     report("subsample /2", ops.subsample_f16(x.to(dev), 2), x[:, ::2, ::2, :], 0.0)
 
 
+def t_conv_stream_bn(G, B, H, W):
+    """padded-stream 3x3 64->64 conv with the previous layer's BatchNorm + ReLU applied to the input tiles in shared
+    memory: == conv(relu(y * scale + shift)) with exact zero padding."""
+    torch.manual_seed(61)
+    y = (torch.randn(G * B, H, W, 64, device=dev) * 0.7).half()
+    ss = torch.stack([torch.rand(G, 64, device=dev) + 0.5, torch.randn(G, 64, device=dev) * 0.5], -1).contiguous()
+    w = (torch.randn(G, 64, 3, 3, 64, device=dev) * 0.1).half()
+    out, st = ops.conv3x3_c64_f16(y, w.view(G, 64, -1), G, stats=True, in_ss=ss)
+    torch.cuda.synchronize()
+    a = torch.relu(y.float().view(G, B, H, W, 64) * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]).half().float()
+    refs = []
+    for g in range(G):
+        refs.append(F.conv2d(a[g].permute(0, 3, 1, 2), w[g].float().permute(0, 3, 1, 2), None, 1, 1).permute(0, 2, 3, 1))
+    ref = torch.cat(refs)
+    report(f"stream conv + input BN/ReLU G={G} B={B} {H}x{W}", out, ref, 3e-3)
+    report("   stats sum", st[..., 0].sum(1), ref.view(G, -1, 64).sum(1), 2e-3)
+
+
 def t_conv(G, B, H, W, Cin, Cout, k, stride, pad):
     torch.manual_seed(8)
     x = (torch.randn(G * B, H, W, Cin, device=dev) * 0.5).half()
@@ -771,6 +789,7 @@ GROUPS = {
     "gemm_bn": lambda: [run_case(t_gemm_bn, *a) for a in [
         (2, 1000, 256, 64), (3, 4096, 512, 128), (1, 40, 64, 64), (2, 20000, 256, 64), (1, 300, 128, 128, False),
         (4, 65536, 256, 64)]],
+    "stream_bn": lambda: [run_case(t_conv_stream_bn, *a) for a in [(1, 2, 8, 8), (2, 3, 10, 12), (2, 8, 64, 64), (3, 1, 5, 7)]],
     "gemm_bn_cat": lambda: [run_case(t_gemm_bn_cat, *a) for a in [(2, 1000, 256, 64, 64), (3, 4096, 512, 128, 256),
                                                                   (1, 300, 256, 64, 64), (2, 20000, 256, 64, 64)]],
     "conv": lambda: [run_case(t_conv, *a) for a in [

@@ -103,6 +103,13 @@ def test_tcgen05_gemm_fused_batchnorm_residual_epilogue(bu, shape):
     _run(bu, bu.t_gemm_bn, *shape)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 8, 8), (2, 3, 10, 12), (2, 8, 64, 64), (3, 1, 5, 7)])
+def test_padded_stream_conv_with_input_batchnorm_relu(bu, shape):
+    """layer1 conv2 fed with the RAW conv1 output: bn1 + ReLU applied to the TMA-loaded tiles in shared memory, padding kept
+    at exact zero (tiles straddle image rows, images and samples)."""
+    _run(bu, bu.t_conv_stream_bn, *shape)
+
+
 @pytest.mark.parametrize("shape", [(2, 1000, 256, 64, 64), (3, 4096, 512, 128, 256), (1, 300, 256, 64, 64), (2, 20000, 256, 64, 64)])
 def test_fused_downsample_tail_k_concatenated(bu, shape):
     """relu(bn3(conv3(a)) + bn_d(conv_d(x))) as ONE tcgen05 contraction over K-concatenated operands, BN scales folded into
