@@ -1,16 +1,17 @@
 // K2: the fusion head. 15 Bayesian Linear layers per MC pass (AdditiveAttention x3:
 // models/base_models.py:35-52, then fc/fc1/fc2: models/base_models.py:60-65,86-89) with
 // M = batch rows only, so here the weight sampling w = mu + log1p(exp(rho))*eps really is
-// fused into operand staging: each CTA samples its [16 x 32] weight tile straight into
+// fused into operand staging: each CTA samples its [32 x 32] weight tile straight into
 // shared memory (Philox or injected eps) and contracts it in fp32; no sampled weight
 // ever reaches HBM. (bayesian-torch linear_variational.py forward; weight AND bias sampled.)
 #include "common.cuh"
 
 namespace {
 
-constexpr int TO = 16;   // outputs per CTA
-constexpr int TB = 32;   // batch rows per CTA: small tiles -> several CTAs per SM hide the global-load latency of the k loop
-constexpr int TK = 32;   // k chunk
+constexpr int TO = 32;        // outputs per CTA
+constexpr int TB = 32;        // batch rows per CTA (every row tile re-samples its weight tile: Philox is cheap, latency is not)
+constexpr int TK = 32;        // k chunk
+constexpr int PITCH = TK + 4; // 16-byte aligned rows, float4 reads in the inner product
 
 struct LinearParams {
   const float* x; long long x_gs; int ldx;      // [G][B][in], sample stride, row stride
@@ -21,36 +22,46 @@ struct LinearParams {
   float* y; long long y_gs; int ldy;            // [G][B][out]
 };
 
+// 256 threads = 16 x 16; each thread owns a 2 x 2 block of the 32 x 32 output tile (rows ty, ty+16; outputs tx, tx+16) and
+// walks k four at a time with 16-byte shared-memory reads (4 FMAs per LDS.128). Per k-step the CTA stages a 32 x 32
+// activation tile (one float4 per thread) and SAMPLES its 32 x 32 weight tile in place (one Philox4x32 block per thread).
 __global__ void __launch_bounds__(256)
 sampled_linear_kernel(const LinearParams p) {
-  __shared__ float xs[TB][TK + 1];
-  __shared__ float ws[TO][TK + 1];
+  __shared__ __align__(16) float xs[TB][PITCH];
+  __shared__ __align__(16) float ws[TO][PITCH];
   const int g = blockIdx.z;
   const int o0 = blockIdx.x * TO;
   const int b0 = blockIdx.y * TB;
-  const int tx = threadIdx.x % TO;
-  const int ty = threadIdx.x / TO;  // 0..15
+  const int tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 4;  // 0..15
   const float* xg = p.x + static_cast<long long>(g) * p.x_gs;
-  float acc[TB / 16];
-#pragma unroll
-  for (int j = 0; j < TB / 16; ++j) acc[j] = 0.f;
-  const bool quads = (p.in % 4 == 0);     // 4 consecutive k share one Philox4x32 block
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const bool quads = (p.in % 4 == 0);     // 4 consecutive k share one Philox4x32 block / one 16-byte load
+  const bool x_vec = quads && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) && (p.ldx % 4 == 0);
+  const int sr = threadIdx.x >> 3, sc = (threadIdx.x & 7) * 4;      // staging role: row sr, columns sc .. sc+3
 
   for (int k0 = 0; k0 < p.in; k0 += TK) {
-    // activations: 64 x 32 tile, coalesced along k
-    for (int i = threadIdx.x; i < TB * TK; i += 256) {
-      const int r = i / TK, k = i % TK;
-      const int b = b0 + r, kk = k0 + k;
-      xs[r][k] = (b < p.B && kk < p.in) ? xg[static_cast<long long>(b) * p.ldx + kk] : 0.f;
+    {   // activations
+      const int b = b0 + sr, kk = k0 + sc;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < p.B) {
+        const float* src = xg + static_cast<long long>(b) * p.ldx + kk;
+        if (x_vec && kk < p.in) v = *reinterpret_cast<const float4*>(src);
+        else {
+          if (kk < p.in) v.x = src[0];
+          if (kk + 1 < p.in) v.y = src[1];
+          if (kk + 2 < p.in) v.z = src[2];
+          if (kk + 3 < p.in) v.w = src[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&xs[sr][sc]) = v;
     }
-    // weights: sample the 16 x 32 tile in place
-    if (quads && !p.eps_w) {
-      if (threadIdx.x < TO * TK / 4) {
-        const int r = threadIdx.x / (TK / 4), k = (threadIdx.x % (TK / 4)) * 4;
-        const int o = o0 + r, kk = k0 + k;
-        float w[4] = {0.f, 0.f, 0.f, 0.f};
-        if (o < p.out && kk < p.in) {            // in % 4 == 0: the whole quad is in range
-          const long long e = static_cast<long long>(o) * p.in + kk;
+    {   // weights: sample the tile in place
+      const int o = o0 + sr, kk = k0 + sc;
+      float w[4] = {0.f, 0.f, 0.f, 0.f};
+      if (o < p.out && kk < p.in) {
+        const long long e = static_cast<long long>(o) * p.in + kk;
+        if (quads && !p.eps_w) {           // in % 4 == 0: the whole quad is in range and 16-byte aligned
           float z[4];
           philox_normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e >> 2), z);
           const float4 m4 = *reinterpret_cast<const float4*>(p.mu_w + e);
@@ -59,47 +70,51 @@ sampled_linear_kernel(const LinearParams p) {
           w[1] = fmaf(softplus_ref(r4.y), z[1], m4.y);
           w[2] = fmaf(softplus_ref(r4.z), z[2], m4.z);
           w[3] = fmaf(softplus_ref(r4.w), z[3], m4.w);
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ws[r][k + j] = w[j];
-      }
-    } else {
-      for (int i = threadIdx.x; i < TO * TK; i += 256) {
-        const int r = i / TK, k = i % TK;
-        const int o = o0 + r, kk = k0 + k;
-        float w = 0.f;
-        if (o < p.out && kk < p.in) {
-          const long long e = static_cast<long long>(o) * p.in + kk;
-          const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e]
-                                  : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
-          w = fmaf(softplus_ref(p.rho_w[e]), z, p.mu_w[e]);
+          for (int j = 0; j < 4; ++j) {
+            if (kk + j < p.in) {
+              const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e + j]
+                                      : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e + j));
+              w[j] = fmaf(softplus_ref(p.rho_w[e + j]), z, p.mu_w[e + j]);
+            }
+          }
         }
-        ws[r][k] = w;
       }
+      *reinterpret_cast<float4*>(&ws[sr][sc]) = make_float4(w[0], w[1], w[2], w[3]);
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      const float w = ws[tx][k];
-#pragma unroll
-      for (int j = 0; j < TB / 16; ++j) acc[j] = fmaf(xs[ty + 16 * j][k], w, acc[j]);
+    for (int k4 = 0; k4 < TK; k4 += 4) {
+      const float4 wa = *reinterpret_cast<const float4*>(&ws[tx][k4]);
+      const float4 wb = *reinterpret_cast<const float4*>(&ws[tx + 16][k4]);
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[ty][k4]);
+      const float4 xb = *reinterpret_cast<const float4*>(&xs[ty + 16][k4]);
+      // k order inside the chunk is fixed (x, y, z, w): deterministic accumulation
+      acc[0][0] = fmaf(xa.w, wa.w, fmaf(xa.z, wa.z, fmaf(xa.y, wa.y, fmaf(xa.x, wa.x, acc[0][0]))));
+      acc[0][1] = fmaf(xa.w, wb.w, fmaf(xa.z, wb.z, fmaf(xa.y, wb.y, fmaf(xa.x, wb.x, acc[0][1]))));
+      acc[1][0] = fmaf(xb.w, wa.w, fmaf(xb.z, wa.z, fmaf(xb.y, wa.y, fmaf(xb.x, wa.x, acc[1][0]))));
+      acc[1][1] = fmaf(xb.w, wb.w, fmaf(xb.z, wb.z, fmaf(xb.y, wb.y, fmaf(xb.x, wb.x, acc[1][1]))));
     }
     __syncthreads();
-  }
-  const int o = o0 + tx;
-  if (o >= p.out) return;
-  float bias = 0.f;
-  if (p.mu_b) {
-    // bias eps uses layer_id | 0x80000000 so its Philox stream is disjoint from the weight's
-    const float z = p.eps_b ? p.eps_b[static_cast<long long>(g) * p.out + o]
-                            : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + g, static_cast<uint64_t>(o));
-    bias = fmaf(softplus_ref(p.rho_b[o]), z, p.mu_b[o]);
   }
   float* yg = p.y + static_cast<long long>(g) * p.y_gs;
 #pragma unroll
-  for (int j = 0; j < TB / 16; ++j) {
-    const int b = b0 + ty + 16 * j;
-    if (b < p.B) yg[static_cast<long long>(b) * p.ldy + o] = acc[j] + bias;
+  for (int jo = 0; jo < 2; ++jo) {
+    const int o = o0 + tx + 16 * jo;
+    if (o >= p.out) continue;
+    float bias = 0.f;
+    if (p.mu_b) {
+      // bias eps uses layer_id | 0x80000000 so its Philox stream is disjoint from the weight's
+      const float z = p.eps_b ? p.eps_b[static_cast<long long>(g) * p.out + o]
+                              : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + g, static_cast<uint64_t>(o));
+      bias = fmaf(softplus_ref(p.rho_b[o]), z, p.mu_b[o]);
+    }
+#pragma unroll
+    for (int jb = 0; jb < 2; ++jb) {
+      const int b = b0 + ty + 16 * jb;
+      if (b < p.B) yg[static_cast<long long>(b) * p.ldy + o] = acc[jb][jo] + bias;
+    }
   }
 }
 
