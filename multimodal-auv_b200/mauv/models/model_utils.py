@@ -40,3 +40,38 @@ def define_models(device: torch.device, num_classes: int,
     except Exception as e:
         logging.error(f"Error defining models: {e}", exc_info=True)
         raise
+
+
+_BRANCHES = ("image_model_feat", "bathy_model_feat", "sss_model_feat")
+
+
+def load_reference_weights(multimodal_model: nn.Module, weights, num_classes: int = 7, map_location="cpu"):
+    """Load a checkpoint written by the reference into the mauv multimodal model: a `.pth` from
+    train/checkpointing.py:40 (`torch.save(model.state_dict())`, possibly with the `module.` prefix of DataParallel) or
+    the published `pytorch_model.bin`, whose trunks are stored one level deeper (`image_model_feat.model.conv1...`).
+    Same key normalisation as Examples/Example_Inference_model.py:82-112: strip `module.`, drop the `.model.` level of the
+    three trunks, and leave the output layer (`fc2.*`) at its fresh initialisation when num_classes differs from the 7
+    classes the published weights were trained on. The Bayesian layers carry the same parameter names as
+    bayesian-torch's (mu_kernel / rho_kernel / mu_weight / rho_weight / mu_bias / rho_bias), so nothing else is remapped.
+    -> (missing_keys, unexpected_keys) as `load_state_dict(strict=False)` reports them."""
+    state = torch.load(weights, map_location=map_location) if isinstance(weights, (str, bytes)) or hasattr(weights, "read") \
+        else weights
+    fixed = {}
+    for key, value in state.items():
+        if key.startswith("module."):
+            key = key[len("module."):]
+        for branch in _BRANCHES:
+            deep = branch + ".model."
+            if key.startswith(deep):
+                key = branch + "." + key[len(deep):]
+                break
+        if num_classes != 7 and key.startswith("fc2."):
+            logging.info(f"load_reference_weights: skipping '{key}' (checkpoint has 7 classes, model has {num_classes})")
+            continue
+        fixed[key] = value
+    result = multimodal_model.load_state_dict(fixed, strict=False)
+    for key in result.missing_keys:
+        logging.warning(f"load_reference_weights: missing in the checkpoint: {key}")
+    for key in result.unexpected_keys:
+        logging.warning(f"load_reference_weights: not used by the model: {key}")
+    return list(result.missing_keys), list(result.unexpected_keys)

@@ -129,3 +129,33 @@ def test_data_parallel_gradient_mean_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_load_reference_weights_key_normalisation(tmp_path):
+    """Checkpoints as the reference writes / publishes them (DataParallel `module.` prefix, trunks one `.model.` level deeper,
+    7-class output layer) load into the mauv multimodal model: Examples/Example_Inference_model.py:82-112."""
+    import bnn_oracle as O
+    from mauv.models.model_utils import define_models, load_reference_weights
+    torch.manual_seed(3)
+    src = define_models(torch.device("cpu"), 7, O.DEFAULT_PRIOR)["multimodal_model"]
+    published = {}
+    for k, v in src.state_dict().items():
+        for b in ("image_model_feat", "bathy_model_feat", "sss_model_feat"):
+            if k.startswith(b + "."):
+                k = b + ".model." + k[len(b) + 1:]
+                break
+        published["module." + k] = v.clone()
+    path = tmp_path / "pytorch_model.bin"
+    torch.save(published, path)
+    torch.manual_seed(4)
+    dst = define_models(torch.device("cpu"), 7, O.DEFAULT_PRIOR)["multimodal_model"]
+    missing, unexpected = load_reference_weights(dst, str(path))
+    assert missing == [] and unexpected == []
+    assert all(torch.equal(v, dst.state_dict()[k]) for k, v in src.state_dict().items())
+    # 5-class head: fc2 keeps its fresh initialisation, everything else is loaded
+    dst5 = define_models(torch.device("cpu"), 5, O.DEFAULT_PRIOR)["multimodal_model"]
+    fc2_before = dst5.fc2.mu_weight.detach().clone()
+    missing, unexpected = load_reference_weights(dst5, published, num_classes=5)
+    assert sorted(missing) == sorted(k for k in dst5.state_dict() if k.startswith("fc2.")) and unexpected == []
+    assert torch.equal(dst5.fc2.mu_weight, fc2_before)
+    assert torch.equal(dst5.fc1.mu_weight, src.fc1.mu_weight)
