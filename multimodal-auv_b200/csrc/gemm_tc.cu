@@ -21,6 +21,14 @@
 //               (the BatchNorm batch statistics of the reference's BN-train pass)
 // Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x) with the
 // n-tile fastest so that CTAs running concurrently share their A tile in L2.
+//
+// Further modes of the same kernel (selected through GemmParams):
+//   * EPI 1/3 statistics-only passes and EPI 2 fused BatchNorm(+residual)(+ReLU) epilogue: the recompute scheme of the
+//     bottleneck tails; a2_kb > 0 K-concatenates A from two tensors (tail of a block with a downsample branch);
+//   * mn = 1: weight gradient dW = dY^T X with BOTH operands MN-major, read where they lie ([64 px][64 ch] TMA boxes of
+//     the row-major dY and of the NHWC activations; im2col-mode TMA on the B side for 3x3 / strided layers);
+//   * split / a_wrap_kb / a_cwrap: the fp16x3 validation arithmetic (K-concatenated hi/lo operands).
+// conv3x3_c64_stream_kernel (below) is the padded-stream sibling for layer1's 3x3 64->64 convs.
 #include <cstdlib>
 #include "common.cuh"
 
