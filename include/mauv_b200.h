@@ -253,6 +253,9 @@ int mauv_conv3x3_c64_tiles(int imgs_per_sample, int H, int W);
  * BatchNorm + ReLU - is applied to each tile in shared memory before the MMAs (the activated tensor never exists in HBM). */
 int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_partial, const float* in_scale_shift, int G,
                          int imgs_per_sample, int H, int W, void* stream);
+/* mauv_gemm_f16 whose [N][K] operand is shared by groups of batches: y[g] = a[g] * w[g % w_batches]^T (the stem's weight
+ * gradient: per-sample dY^T chunks against the chunks of the one im2col matrix all samples share). */
+int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int G, long long M, int N, int K, void* stream);
 /* Weight gradient of the grouped conv straight from the NHWC tensors (no transposed copies): dy [G*imgs][Ho][Wo][Cout],
  * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] fp16 partial sums over pixel chunks (K order (r, s, c)). Both
  * operands enter the tcgen05 MMA MN-major from [64 pixels][64 channels] TMA boxes (tiled for 1x1/stride 1, im2col mode

@@ -68,6 +68,8 @@ struct GemmParams {
   // 1x1 / stride 1, im2col-mode for everything else); the batch index is (sample, pixel chunk), k_blocks = chunk / 64.
   int a2_kb;             // > 0: tiled A is K-concatenated from two tensors: k-blocks >= a2_kb come from the map in the tmR
                          //      slot (fused bottleneck tail with a downsample branch: [a2 | x] * [s3*W3 | sd*Wd]^T)
+  int b_mod;             // > 0: B (the [N][K] operand) has only b_mod batch entries, entry = g % b_mod (an operand shared by
+                         //      groups of batches: the stem's im2col matrix in the weight gradient)
   int mn;                // 1: weight-gradient mode
   int b_im2col;          // mn: B boxes come from im2col-mode TMA (else tiled rows of [pixels][Cin])
   int cin;               // mn: input channels (column -> (tap, channel block))
@@ -260,7 +262,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                static_cast<uint16_t>(r));
           }
           if (p.stack > 1) tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, g * p.N, 0);   // flattened [G*N][K]
-          else tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, g);
+          else tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, p.b_mod ? g % p.b_mod : g);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -1157,6 +1159,30 @@ int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_par
   conv3x3_c64_stream_kernel<<<static_cast<unsigned>(grid), 512, kStreamSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   MAUV_LAUNCH_CHECK("conv3x3_c64_stream_kernel");
   return MAUV_OK;
+}
+
+// mauv_gemm_f16 whose [N][K] operand is shared by groups of batches: y[g] = a[g] * w[g % w_batches]^T. Used by the stem's
+// weight gradient (dY_s^T chunks against the chunks of the ONE im2col matrix all samples share): one launch for all samples.
+int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int G, long long M, int N, int K, void* stream) {
+  MAUV_CHECK_ARG(a && w && y && w_batches >= 1 && G >= 1 && M >= 1, "mauv_gemm_wmod_f16: bad argument");
+  MAUV_CHECK_ARG(N >= 8 && K >= 8 && K % 8 == 0 && N % 8 == 0, "mauv_gemm_wmod_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0, "mauv_gemm_wmod_f16: pointers must be 16-byte aligned");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tiled_map(&tmA, a, K, M, G, M * K, BM)) return rc;
+  if (int rc = make_tiled_map(&tmB, w, K, N, w_batches, static_cast<int64_t>(N) * K, pick_bn(N))) return rc;
+  GemmParams p{};
+  p.stack = 1;
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.k_blocks = static_cast<int>(ceil_div_i64(K, BK));
+  p.G = G;
+  p.a_mode = 0;
+  p.a_batch_mul = 1;
+  p.b_mod = w_batches;
+  p.y = static_cast<__half*>(y);
+  return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
 // ---- weight gradient of the grouped conv, straight from NHWC operands ---------------------------------------------

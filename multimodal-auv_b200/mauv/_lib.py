@@ -68,6 +68,7 @@ SIGNATURES = {
     "mauv_subsample_f16": (i32, [vp, i64, i32, i32, i32, i32, vp, vp]),
     "mauv_conv3x3_c64_tiles": (i32, [i32, i32, i32]),
     "mauv_conv3x3_c64_f16": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "mauv_gemm_wmod_f16": (i32, [vp, vp, i32, vp, i32, i64, i32, i32, vp]),
     "mauv_wgrad_f16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mauv_wgrad_finalize_group": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, u64, u32, u32, i32, vp, vp, vp]),
     "mauv_sampled_linear_bwd_group_f32": (i32, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32,

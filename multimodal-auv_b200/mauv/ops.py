@@ -159,6 +159,18 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] =
     return out, (stats_out if stats else None)
 
 
+def gemm_wmod_f16(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """a [G, M, K], w [Gw, N, K] with G % Gw == 0 -> y [G, M, N] = a[g] @ w[g % Gw]^T"""
+    lib = _lib.require_device()
+    G, M, K = a.shape
+    Gw, N, _ = w.shape
+    assert w.shape[2] == K and G % Gw == 0
+    out = torch.empty((G, M, N), dtype=F16, device=a.device)
+    _run("mauv_gemm_wmod_f16", lib.mauv_gemm_wmod_f16, _ptr(a, F16), _ptr(w, F16), Gw, _ptr(out), G, M, N, K, _stream(),
+         tag=f"G{G} M{M} N{N} K{K} wmod{Gw}" if _prof is not None else None)
+    return out
+
+
 def gemm_stats_f16(a: torch.Tensor, w: torch.Tensor, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """First pass of the recompute scheme: BN partial statistics of A*W^T without storing it. a [G,M,K], w [G,N,K]."""
     lib = _lib.require_device()

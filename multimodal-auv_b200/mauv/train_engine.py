@@ -222,12 +222,10 @@ class TrainEngine(MCEngine):
         NB, Ho, Wo, Cout = dy.shape
         M = (NB // G) * Ho * Wo
         Kp = tr.a0.shape[1]
-        splits = _group_splits(M, 1, Cout, Kp)
+        splits = _group_splits(M, G, Cout, Kp)
         b_t = ops.transpose_chunks_f16(tr.a0, splits)                                         # [splits, Kp, Mc] (all samples)
-        a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits).view(G, splits, Cout, M // splits)
-        dw = torch.empty((G, splits, Cout, Kp), dtype=F16, device=dy.device)
-        for g in range(G):
-            ops.gemm_f16(a_t[g], b_t, out=dw[g])
+        a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits)                      # [G*splits, Cout, Mc]
+        dw = ops.gemm_wmod_f16(a_t, b_t)                                                      # batch (g, sp) uses b_t[sp]
         ops.wgrad_finalize_group(dw.view(G * splits, Cout, Kp), G, tuple(layer.mu_kernel.shape), 1.0, s_dy,
                                  layer.rho_kernel.detach(), layer.mu_kernel.grad, layer.rho_kernel.grad,
                                  eps=self._eps_w(eps, c.name, s0, G), seed=seed, layer_id=c.layer_id, sample0=s0, stale=stale)
