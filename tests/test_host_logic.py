@@ -159,3 +159,27 @@ def test_load_reference_weights_key_normalisation(tmp_path):
     assert sorted(missing) == sorted(k for k in dst5.state_dict() if k.startswith("fc2.")) and unexpected == []
     assert torch.equal(dst5.fc2.mu_weight, fc2_before)
     assert torch.equal(dst5.fc1.mu_weight, src.fc1.mu_weight)
+
+
+def test_bench_roofline_launch_model():
+    """bench.py's per-launch roofline model: algorithmic flops and minimum HBM bytes parsed from the profiling tags."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f, b = bench.tc_launch_model("mauv_gemm_f16", "G10 M1048576 N256 K64")
+    assert f == 2.0 * 10 * 1048576 * 256 * 64
+    assert b == 10 * 1048576 * 64 * 2 + 10 * 256 * 64 * 2 + 10 * 1048576 * 256 * 2          # A + W + Y
+    f, b = bench.tc_launch_model("mauv_conv2d_im2col_f16", "G10 M262144 N128 K1152 3x3/2")
+    assert f == 2.0 * 10 * 262144 * 128 * 1152
+    assert b == 10 * 262144 * 4 * 128 * 2 + 10 * 128 * 1152 * 2 + 10 * 262144 * 128 * 2       # stride 2: 4x the input pixels
+    f, b = bench.tc_launch_model("mauv_gemm_bn_f16", "stats G10 M65536 N1024 K256")
+    assert b == 10 * 65536 * 256 * 2 + 10 * 1024 * 256 * 2                                     # statistics pass: no output
+    f, b = bench.tc_launch_model("mauv_gemm_bn_f16", "fused G10 M65536 N1024 K256 res1")
+    assert b == 10 * 65536 * 256 * 2 + 10 * 1024 * 256 * 2 + 2 * 10 * 65536 * 1024 * 2         # + residual read + output
+    f, b = bench.tc_launch_model("mauv_gemm_f16", "G10 M4194304 N64 K152")
+    assert b == 4194304 * 152 * 2 + 10 * 64 * 152 * 2 + 10 * 4194304 * 64 * 2                  # stem: A shared by all samples
+    f, b = bench.tc_launch_model("mauv_conv3x3_c64_f16", "G10 M1048576 N64 K576 stream")
+    assert b == 10 * 1048576 * 64 * 2 * 2 + 10 * 64 * 576 * 2
+    assert bench.tc_launch_model("mauv_bn_act_f16", "G10 M100 C64 res0 dual0") is None
