@@ -40,6 +40,13 @@ int mauv_version(void);
 const char* mauv_last_error(void);
 int mauv_device_check(void);
 int mauv_num_sms_c(void);
+/* Device-resident Philox sample-id base for the CALLING THREAD's subsequent launches of the forward sampling entry
+ * points (mauv_sample_weights_f16, _scaled_f16, _dgrad_f16, _x3_f16, mauv_sampled_linear_f32); NULL = none. Those kernels
+ * add *sample_base to their sample ids when they RUN, so a CUDA graph captured with a base set draws fresh eps on every
+ * replay once the caller bumps the word - the reference draws fresh eps on every pass of every batch
+ * (inference/predictors.py:54-66; bayesian-torch `eps.data.normal_()`). The pointer must stay valid while such work
+ * (or a graph holding it) can run. */
+int mauv_set_sample_base(const unsigned int* sample_base);
 
 /* ---- K1 operand staging: w = mu + log1p(exp(rho)) * eps ---------------------------------
  * Replaces bayesian-torch 0.5.0 Conv2dReparameterization.forward / LinearReparameterization
@@ -281,7 +288,9 @@ int mauv_sampled_linear_bwd_group_f32(const float* x, long long x_sg, int x_sb, 
 int mauv_tanh_bwd_f32(const float* t, const float* dt, long long n, float* out, void* stream);
 int mauv_softmax_gate_bwd_f32(const float* score, const float* v, const float* dout, int ld_dout, long long rows, int n,
                               float* dscore, float* dv, void* stream);
-/* loss = cross_entropy(mean_s logits, labels) (train/multimodal.py:118-121); dlogits [S][B][C] = d loss / d logits. */
+/* loss = cross_entropy(mean_s logits, labels) (train/multimodal.py:118-121); dlogits [S][B][C] = d loss / d logits.
+ * Labels as torch's cross_entropy: -100 rows are ignored (not in the mean, zero gradient); any other label outside
+ * [0, C) makes the loss NaN (torch: device assert) and leaves that row's gradient zero - never read out of bounds. */
 int mauv_ce_mean_fwd_bwd_f32(const float* logits, const long long* labels, int S, int B, int C, float* mean_logit,
                              float* dlogits, float* loss, void* stream);
 

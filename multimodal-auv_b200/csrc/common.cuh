@@ -47,6 +47,9 @@ int mauv_set_error(int code, const char* fmt, ...);
                             cudaGetErrorString(_e));                           \
   } while (0)
 
+// Device word added to the Philox sample ids by the sampling kernels (thread-local, see mauv_set_sample_base); may be null.
+const unsigned int* mauv_sample_base();
+
 // Number of SMs of the current device (cached).
 int mauv_num_sms();
 

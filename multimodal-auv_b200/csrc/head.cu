@@ -20,6 +20,7 @@ struct LinearParams {
   uint64_t seed; uint32_t layer_id, sample0;
   int G, B, in, out;
   float* y; long long y_gs; int ldy;            // [G][B][out]
+  const unsigned int* sample_base;              // optional device word added to the sample ids (mauv_set_sample_base)
 };
 
 // 256 threads = 16 x 16; each thread owns a 2 x 2 block of the 32 x 32 output tile (rows ty, ty+16; outputs tx, tx+16) and
@@ -27,6 +28,7 @@ struct LinearParams {
 // activation tile (one float4 per thread) and SAMPLES its 32 x 32 weight tile in place (one Philox4x32 block per thread).
 __global__ void __launch_bounds__(256)
 sampled_linear_kernel(const LinearParams p) {
+  const uint32_t sample0 = p.sample0 + (p.sample_base ? *p.sample_base : 0u);
   __shared__ __align__(16) float xs[TB][PITCH];
   __shared__ __align__(16) float ws[TO][PITCH];
   const int g = blockIdx.z;
@@ -63,7 +65,7 @@ sampled_linear_kernel(const LinearParams p) {
         const long long e = static_cast<long long>(o) * p.in + kk;
         if (quads && !p.eps_w) {           // in % 4 == 0: the whole quad is in range and 16-byte aligned
           float z[4];
-          philox_normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e >> 2), z);
+          philox_normals4(p.seed, p.layer_id, sample0 + g, static_cast<uint64_t>(e >> 2), z);
           const float4 m4 = *reinterpret_cast<const float4*>(p.mu_w + e);
           const float4 r4 = *reinterpret_cast<const float4*>(p.rho_w + e);
           w[0] = fmaf(softplus_ref(r4.x), z[0], m4.x);
@@ -75,7 +77,7 @@ sampled_linear_kernel(const LinearParams p) {
           for (int j = 0; j < 4; ++j) {
             if (kk + j < p.in) {
               const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e + j]
-                                      : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e + j));
+                                      : philox_normal(p.seed, p.layer_id, sample0 + g, static_cast<uint64_t>(e + j));
               w[j] = fmaf(softplus_ref(p.rho_w[e + j]), z, p.mu_w[e + j]);
             }
           }
@@ -107,7 +109,7 @@ sampled_linear_kernel(const LinearParams p) {
     if (p.mu_b) {
       // bias eps uses layer_id | 0x80000000 so its Philox stream is disjoint from the weight's
       const float z = p.eps_b ? p.eps_b[static_cast<long long>(g) * p.out + o]
-                              : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + g, static_cast<uint64_t>(o));
+                              : philox_normal(p.seed, p.layer_id | 0x80000000u, sample0 + g, static_cast<uint64_t>(o));
       bias = fmaf(softplus_ref(p.rho_b[o]), z, p.mu_b[o]);
     }
 #pragma unroll
@@ -161,6 +163,7 @@ int mauv_sampled_linear_f32(const float* x, long long x_sample_stride, int ldx, 
   p.mu_w = mu_w; p.rho_w = rho_w; p.eps_w = eps_w;
   p.mu_b = mu_b; p.rho_b = rho_b; p.eps_b = eps_b;
   p.seed = seed; p.layer_id = layer_id; p.sample0 = sample0;
+  p.sample_base = mauv_sample_base();
   p.G = G; p.B = B; p.in = in_features; p.out = out_features;
   p.y = y; p.y_gs = y_sample_stride; p.ldy = ldy;
   dim3 grid((out_features + TO - 1) / TO, (B + TB - 1) / TB, G);

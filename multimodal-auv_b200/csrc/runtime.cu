@@ -15,6 +15,9 @@ int mauv_set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static thread_local const unsigned int* g_sample_base = nullptr;
+const unsigned int* mauv_sample_base() { return g_sample_base; }
+
 int mauv_num_sms() {
   static int sms[64] = {0};
   int dev = 0;
@@ -47,5 +50,14 @@ int mauv_device_check(void) {
 }
 
 int mauv_num_sms_c(void) { return mauv_num_sms(); }
+
+// Device-resident Philox sample-id base for the calling thread's subsequent sampling launches (NULL = none): every
+// kernel that draws eps adds *sample_base to its sample ids when it RUNS. A CUDA graph captured with a base pointer set
+// therefore replays with whatever value the word holds at replay time - fresh Monte-Carlo draws for every batch from one
+// recorded graph (the reference draws fresh eps on every pass, inference/predictors.py:54-66).
+int mauv_set_sample_base(const unsigned int* sample_base) {
+  g_sample_base = sample_base;
+  return MAUV_OK;
+}
 
 }  // extern "C"

@@ -27,6 +27,7 @@ struct SampleParams {
   int dgrad;          // 1: write the transposed + spatially flipped layout the data-gradient conv consumes
   const float2* row_scale;   // optional [G][cout] (scale, shift): w *= scale (a BatchNorm scale folded into the weights)
   long long g_stride; // elements between consecutive samples in w (0 = dense default)
+  const unsigned int* sample_base;   // optional device word added to the sample ids at run time (mauv_set_sample_base)
 };
 
 __device__ __forceinline__ void normals4(uint64_t seed, uint32_t layer, uint32_t sample,
@@ -89,6 +90,7 @@ sample_weights_kernel(const SampleParams p, int G) {
                        : co * p.k_pad + static_cast<long long>(rs) * p.cin + c;
     }
   }
+  const uint32_t sample0 = p.sample0 + (p.sample_base ? *p.sample_base : 0u);
   const long long w_stride = p.g_stride ? p.g_stride
                              : (p.dgrad ? static_cast<long long>(p.cin) * p.k_pad : static_cast<long long>(p.cout) * p.k_pad);
   for (int g = 0; g < G; ++g) {
@@ -98,7 +100,7 @@ sample_weights_kernel(const SampleParams p, int G) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) z[i] = (e0 + i < p.n) ? ep[i] : 0.f;
     } else {
-      normals4(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(quad), z);
+      normals4(p.seed, p.layer_id, sample0 + g, static_cast<uint64_t>(quad), z);
     }
     float w[4];
 #pragma unroll
@@ -177,6 +179,7 @@ int mauv_sample_weights_f16(const float* mu, const float* rho, const float* eps,
   p.dgrad = 0;
   p.row_scale = nullptr;
   p.g_stride = 0;
+  p.sample_base = mauv_sample_base();
   const long long quads = ceil_div_i64(p.n, 4);
   sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, st>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel");
@@ -200,6 +203,7 @@ int mauv_sample_weights_scaled_f16(const float* mu, const float* rho, const floa
   p.dgrad = 0;
   p.row_scale = reinterpret_cast<const float2*>(scale_shift);
   p.g_stride = static_cast<long long>(cout) * row_pitch;
+  p.sample_base = mauv_sample_base();
   const long long quads = ceil_div_i64(p.n, 4);
   sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel(scaled)");
@@ -222,6 +226,7 @@ int mauv_sample_weights_dgrad_f16(const float* mu, const float* rho, const float
   p.dgrad = 1;
   p.row_scale = nullptr;
   p.g_stride = 0;
+  p.sample_base = mauv_sample_base();
   const long long quads = ceil_div_i64(p.n, 4);
   sample_weights_kernel<<<static_cast<unsigned>(ceil_div_i64(quads, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
   MAUV_LAUNCH_CHECK("sample_weights_kernel(dgrad)");

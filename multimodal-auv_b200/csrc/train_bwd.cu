@@ -667,11 +667,37 @@ softmax_gate_bwd_kernel(const float* __restrict__ score, const float* __restrict
   }
 }
 
-// loss = mean_b CE(mean_s logits[s,b,:], label_b) ; dlogits[s,b,c] = (softmax(mean)[c] - [c == label]) / (B*S)
+// loss = mean over the valid rows b of CE(mean_s logits[s,b,:], label_b); dlogits[s,b,c] = (softmax(mean)[c] - [c == label]) / (n_valid*S).
+// Labels follow torch.nn.functional.cross_entropy: -100 (ignore_index) rows are skipped - no loss term, zero gradient, not
+// counted in the mean; any other label outside [0, C) is an error that torch reports with a device assert: here the loss
+// becomes NaN (the drivers' finite-loss guard skips the batch) and the row gets a zero gradient - never an out-of-bounds read.
 __global__ void __launch_bounds__(256)
 ce_mean_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int S, int B, int C,
                float* __restrict__ mean_logit, float* __restrict__ dlogits, float* __restrict__ loss) {
   __shared__ float warp_sum[8];
+  __shared__ int warp_cnt[8], warp_bad[8];
+  __shared__ int n_valid_s, n_bad_s;
+  int cnt = 0, bad = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const long long lab = labels[b];
+    if (lab >= 0 && lab < C) ++cnt;
+    else if (lab != -100) ++bad;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) { warp_cnt[threadIdx.x >> 5] = cnt; warp_bad[threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0, d = 0;
+    for (int wi = 0; wi < (blockDim.x >> 5); ++wi) { c += warp_cnt[wi]; d += warp_bad[wi]; }
+    n_valid_s = c; n_bad_s = d;
+  }
+  __syncthreads();
+  const int n_valid = n_valid_s;
+  const float w = n_valid > 0 ? 1.f / (static_cast<float>(n_valid) * static_cast<float>(S)) : 0.f;
   float local = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     float mx = -INFINITY;
@@ -682,14 +708,15 @@ ce_mean_kernel(const float* __restrict__ logits, const long long* __restrict__ l
       mean_logit[b * C + c] = m;
       mx = fmaxf(mx, m);
     }
+    const long long lab64 = labels[b];
+    const bool valid = lab64 >= 0 && lab64 < C;
+    const int lab = valid ? static_cast<int>(lab64) : -1;
     float den = 0.f;
     for (int c = 0; c < C; ++c) den += expf(mean_logit[b * C + c] - mx);
     const float lse = mx + logf(den);
-    const int lab = static_cast<int>(labels[b]);
-    local += lse - mean_logit[b * C + lab];
-    const float w = 1.f / (static_cast<float>(B) * static_cast<float>(S));
+    if (valid) local += lse - mean_logit[b * C + lab];
     for (int c = 0; c < C; ++c) {
-      const float gr = (expf(mean_logit[b * C + c] - lse) - (c == lab ? 1.f : 0.f)) * w;
+      const float gr = valid ? (expf(mean_logit[b * C + c] - lse) - (c == lab ? 1.f : 0.f)) * w : 0.f;
       for (int s = 0; s < S; ++s) dlogits[(static_cast<long long>(s) * B + b) * C + c] = gr;
     }
   }
@@ -700,7 +727,8 @@ ce_mean_kernel(const float* __restrict__ logits, const long long* __restrict__ l
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int wi = 0; wi < (blockDim.x >> 5); ++wi) t += warp_sum[wi];
-    *loss = t / static_cast<float>(B);
+    // all rows ignored: torch returns NaN (0 / 0) as well
+    *loss = (n_bad_s > 0 || n_valid == 0) ? __int_as_float(0x7fc00000) : t / static_cast<float>(n_valid);
   }
 }
 

@@ -17,8 +17,9 @@ __device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
 __global__ void __launch_bounds__(256)
 sample_x3_kernel(const float* __restrict__ mu, const float* __restrict__ rho, const float* __restrict__ eps,
                  uint64_t seed, uint32_t layer_id, uint32_t sample0, int cout, int cin, int kh, int kw, int kp,
-                 int per_tap, float scale, long long n, __half* __restrict__ out) {
+                 int per_tap, float scale, long long n, __half* __restrict__ out, const unsigned int* __restrict__ sample_base) {
   const int g = blockIdx.y;
+  if (sample_base) sample0 += *sample_base;
   const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const int khw = kh * kw;
@@ -147,7 +148,7 @@ int mauv_sample_weights_x3_f16(const float* mu, const float* rho, const float* e
   MAUV_CUDA(cudaMemsetAsync(w_out, 0, static_cast<size_t>(G) * cout * row * sizeof(__half), st));
   dim3 grid(static_cast<unsigned>(ceil_div_i64(n, 256)), G);
   sample_x3_kernel<<<grid, 256, 0, st>>>(mu, rho, eps, seed, layer_id, sample0, cout, cin, kh, kw, kp, per_tap, scale, n,
-                                         static_cast<__half*>(w_out));
+                                         static_cast<__half*>(w_out), mauv_sample_base());
   MAUV_LAUNCH_CHECK("sample_x3_kernel");
   return MAUV_OK;
 }

@@ -20,6 +20,7 @@ SIGNATURES = {
     "mauv_last_error": (C.c_char_p, []),
     "mauv_device_check": (i32, []),
     "mauv_num_sms_c": (i32, []),
+    "mauv_set_sample_base": (i32, [vp]),
     "mauv_sample_weights_f16": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mauv_sample_vector_f32": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, vp, vp]),
     "mauv_philox_normal_f32": (i32, [u64, u32, u32, i64, vp, vp]),

@@ -107,6 +107,24 @@ class MCEngine:
         self.fuse_input_bn = os.environ.get("MAUV_FUSE_INPUT_BN", "0") == "1"
         self.fuse_conv3_max_k = int(os.environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
 
+    # Philox sample-id cursor, shared by every engine built on the same model (it lives on the model object): each
+    # forward_mc / TrainEngine.step / predictor batch that is not given explicit sample ids takes the next S ids, so
+    # every batch, epoch and call sees fresh Monte-Carlo draws like the reference (eps.data.normal_() per pass) instead of
+    # replaying ids [0, S).
+    @property
+    def _sample_cursor(self) -> int:
+        return self.model.__dict__.get("_mauv_sample_cursor", 0)
+
+    @_sample_cursor.setter
+    def _sample_cursor(self, v: int) -> None:
+        self.model.__dict__["_mauv_sample_cursor"] = int(v) & 0xFFFFFFFF
+
+    def take_samples(self, S: int) -> int:
+        """-> first id of a fresh block of S sample ids (advances the model's cursor)"""
+        s0 = self._sample_cursor
+        self._sample_cursor = s0 + S
+        return s0
+
     # ------------------------------------------------------------------ planning
     def _conv(self, layer: nn.Module, name: str) -> _Conv:
         if not hasattr(layer, "mu_kernel"):
@@ -351,12 +369,15 @@ class MCEngine:
         return self._linear(m.fc2, "fc2", h, G, sample0, eps, seed)
 
     @torch.no_grad()
-    def forward_mc(self, inputs: Sequence[torch.Tensor], S: int, sample0: int = 0, eps: Optional[dict] = None,
+    def forward_mc(self, inputs: Sequence[torch.Tensor], S: int, sample0: Optional[int] = None, eps: Optional[dict] = None,
                    seed: Optional[int] = None, group: Optional[int] = None) -> torch.Tensor:
-        """logits [S, B, C] for MC samples sample0 .. sample0+S-1 (eps indexed from 0 when injected)."""
+        """logits [S, B, C] for MC samples sample0 .. sample0+S-1. sample0=None: a fresh block of ids from the model's
+        cursor (production); with injected eps (validation) the ids index the eps tensors and default to 0."""
         G = min(group or self.max_group, S)
         if eps is None:
             eps = DEBUG_EPS
+        if sample0 is None:
+            sample0 = 0 if eps is not None else self.take_samples(S)
         with ops.on_current_stream():
             return self._forward_mc(inputs, S, G, sample0, eps, seed)
 

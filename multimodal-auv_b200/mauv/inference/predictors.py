@@ -67,15 +67,21 @@ class MCPredictor:
 
     @torch.no_grad()
     def mc_logits(self, inputs: Sequence[torch.Tensor], eps: Optional[dict] = None,
-                  seed: Optional[int] = None) -> torch.Tensor:
-        """[S, B, C] logits; under torch.distributed each rank computes its block and all ranks gather."""
+                  seed: Optional[int] = None, sample0: Optional[int] = None) -> torch.Tensor:
+        """[S, B, C] logits; under torch.distributed each rank computes its block and all ranks gather.
+        sample0: first Philox sample id of this batch's S draws. None (production) takes a fresh block of S ids from the
+        model's cursor on every call - identical on all ranks, which advance in lockstep - so every batch is evaluated
+        with its own Monte-Carlo draws, as in the reference; with injected eps the ids index the eps tensors (base 0)."""
+        from .. import engine as _engine
+        if sample0 is None:
+            sample0 = 0 if (eps is not None or _engine.DEBUG_EPS is not None) else self.engine.take_samples(self.S)
         lo, hi = shard_samples(self.S, self.world, self.rank)
         if hi <= lo:
             local = None
         elif eps is None and self._want_graph(inputs[0].shape[0], hi - lo):
-            local = self._forward_graphed(inputs, lo, hi, seed)
+            local = self._forward_graphed(inputs, sample0, lo, hi, seed)
         else:
-            local = self.engine.forward_mc(inputs, hi - lo, sample0=lo, eps=eps, seed=seed)
+            local = self.engine.forward_mc(inputs, hi - lo, sample0=sample0 + lo, eps=eps, seed=seed)
         if self.world == 1:
             return local
         C = local.shape[-1] if local is not None else self._num_classes()
@@ -87,29 +93,33 @@ class MCPredictor:
             return 0.036 * G * B < 60.0          # measured: 93 us GPU time per launch at G=10, B=256; 57 us to enqueue
         return bool(self.use_graph)
 
-    def _forward_graphed(self, inputs, lo, hi, seed):
+    def _forward_graphed(self, inputs, sample0, lo, hi, seed):
         from .. import engine as _engine
         from ..bayesian import current_seed
         if _engine.DEBUG_EPS is not None:
-            return self.engine.forward_mc(inputs, hi - lo, sample0=lo, seed=seed)
+            return self.engine.forward_mc(inputs, hi - lo, sample0=sample0 + lo, seed=seed)
         seed = current_seed() if seed is None else seed
+        # the graph is recorded for sample ids lo .. hi-1 PLUS a device-resident base word (ops.sample_base): the batch's
+        # sample0 is written into that word before every replay, so one graph serves every batch with fresh draws
         key = (tuple(tuple(x.shape) for x in inputs), lo, hi, seed, self.engine.precision)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = [torch.empty(x.shape, dtype=torch.float32, device=self.device) for x in inputs]
             for d, x in zip(static_in, inputs):
                 d.copy_(x)
+            base = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.engine.forward_mc(static_in, hi - lo, sample0=lo, seed=seed)       # eager warm-up (lazy inits)
             torch.cuda.synchronize(self.device)
             n0 = ops.launch_count
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), ops.sample_base(base):
                 static_out = self.engine.forward_mc(static_in, hi - lo, sample0=lo, seed=seed)
-            entry = (graph, static_in, static_out, ops.launch_count - n0)
+            entry = (graph, static_in, static_out, ops.launch_count - n0, base)
             self._graphs[key] = entry
-        graph, static_in, static_out, n_launch = entry
+        graph, static_in, static_out, n_launch, base = entry
         for d, x in zip(static_in, inputs):
             d.copy_(x, non_blocking=True)
+        base.fill_(((sample0 & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000)      # uint32 bit pattern in an int32 word
         graph.replay()
         ops.launch_count += n_launch
         return static_out.clone()      # 4*S*B*C bytes; the static buffer is overwritten by the next replay
@@ -120,18 +130,18 @@ class MCPredictor:
 
     @torch.no_grad()
     def predict_device(self, inputs: Sequence[torch.Tensor], eps: Optional[dict] = None,
-                       seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
-        logits = self.mc_logits(inputs, eps, seed)
+                       seed: Optional[int] = None, sample0: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        logits = self.mc_logits(inputs, eps, seed, sample0)
         out = ops.mc_reduce(logits, self.eps_entropy)
         out["logits"] = logits
         return out
 
     @torch.no_grad()
     def predict_batch(self, host_inputs: Sequence[torch.Tensor], eps: Optional[dict] = None,
-                      seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                      seed: Optional[int] = None, sample0: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Host tensors in, host results out: (class [B] int64, predictive unc. [B], aleatoric [B], MI [B])."""
         dev_in = [x.to(self.device, non_blocking=True) for x in host_inputs]
-        o = self.predict_device(dev_in, eps, seed)
+        o = self.predict_device(dev_in, eps, seed, sample0)
         return _unpack_results(_pack_results(o).cpu())                       # one [B, 5] D2H
 
 

@@ -1,7 +1,8 @@
 """models/model_utils.py of the reference (define_models :10-45, load_pretrained_resnet_as_feature_extractor
 :52-64) over mauv.bayesian instead of bayesian_torch."""
 import logging
-from typing import Any, Dict
+import os
+from typing import Any, Dict, Tuple
 
 import torch
 import torch.nn as nn
@@ -42,6 +43,31 @@ def define_models(device: torch.device, num_classes: int,
         raise
 
 
+def load_models(model_paths: Dict[str, str], device: torch.device,
+                num_classes: int) -> Tuple[nn.Module, nn.Module, nn.Module]:
+    """models/model_utils.py:66-101 of the reference: the three (deterministic) ResNet-50 feature extractors, each filled
+    from `model_paths[key]` (keys "image", "channels", "sss") when that file exists. A missing path is a warning and a
+    failing load an error log, never an exception - the reference's behaviour; only a failure to build the trunks raises."""
+    try:
+        loaded = {"image": load_pretrained_resnet_as_feature_extractor(),
+                  "channels": load_pretrained_resnet_as_feature_extractor(),
+                  "sss": load_pretrained_resnet_as_feature_extractor(input_channels=1)}
+        for key, model in loaded.items():
+            path = model_paths.get(key)
+            try:
+                if path and os.path.exists(path):
+                    model.load_state_dict(torch.load(path, map_location=device))
+                    logging.info(f"{key.capitalize()} model loaded successfully from {path}.")
+                else:
+                    logging.warning(f"Path not found for model: {key} -> {path}")
+            except Exception as inner_e:
+                logging.error(f"Failed to load {key} model from {path}: {inner_e}", exc_info=True)
+        return loaded["image"], loaded["channels"], loaded["sss"]
+    except Exception as e:
+        logging.error(f"Error loading models: {e}", exc_info=True)
+        raise
+
+
 _BRANCHES = ("image_model_feat", "bathy_model_feat", "sss_model_feat")
 
 
@@ -54,8 +80,12 @@ def load_reference_weights(multimodal_model: nn.Module, weights, num_classes: in
     classes the published weights were trained on. The Bayesian layers carry the same parameter names as
     bayesian-torch's (mu_kernel / rho_kernel / mu_weight / rho_weight / mu_bias / rho_bias), so nothing else is remapped.
     -> (missing_keys, unexpected_keys) as `load_state_dict(strict=False)` reports them."""
-    state = torch.load(weights, map_location=map_location) if isinstance(weights, (str, bytes)) or hasattr(weights, "read") \
-        else weights
+    if isinstance(weights, (str, bytes, os.PathLike)) or hasattr(weights, "read"):
+        state = torch.load(weights, map_location=map_location)
+    else:
+        state = weights
+    if not hasattr(state, "items"):
+        raise TypeError(f"load_reference_weights: expected a path, a file object or a state_dict, got {type(weights).__name__}")
     fixed = {}
     for key, value in state.items():
         if key.startswith("module."):

@@ -49,6 +49,25 @@ class on_current_stream:
 
 
 
+class sample_base:
+    """While active, the forward sampling kernels launched by this thread add the uint32 word `word` (a 1-element int32 /
+    uint32 CUDA tensor) to their Philox sample ids when they run (mauv_set_sample_base): a CUDA graph captured inside the
+    block draws fresh eps on every replay after `word` is bumped."""
+
+    def __init__(self, word: Optional[torch.Tensor]):
+        if word is not None and (not word.is_cuda or word.numel() != 1 or word.element_size() != 4):
+            raise _lib.MauvError("sample_base: a 1-element 32-bit CUDA tensor is required")
+        self.word = word
+
+    def __enter__(self):
+        _lib.check(_lib.require_device().mauv_set_sample_base(self.word.data_ptr() if self.word is not None else None))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.check(_lib.require_device().mauv_set_sample_base(None))
+        return False
+
+
 # ------------------------------------------------------------------ launch accounting / profiling
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 KERNELS_PER_CALL = {"mauv_kl_fwd_bwd": 2, "mauv_bn_finalize": 2, "mauv_sampled_linear_bwd_f32": 2}

@@ -73,12 +73,18 @@ def train_multimodal_model(multimodal_model: nn.Module, dataloader, criterion: n
             module = multimodal_model.module if isinstance(
                 multimodal_model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else multimodal_model
             engine = train_engine_for(module, criterion)
+            sync_group = ddp_sync_group(multimodal_model, engine)
             for i, batch in enumerate(dataloader):
                 logging.info(f"Train batch {i+1}/{len(dataloader)} - Model: {model_type}")
                 inputs, labels, bathy_patch, sss_patch = _select_patches(batch, device, bathy_patch_type, sss_patch_type)
                 if engine is not None:
                     # S-batched step (train_engine.py): one grouped forward + one grouped backward for all num_mc passes
                     res = engine.step((inputs, bathy_patch, sss_patch), labels, num_mc, kl_weight / dataloader.batch_size)
+                    if sync_group is not False:
+                        # the engine writes `.grad` directly, so DistributedDataParallel's reducer never sees these
+                        # gradients: average them over the ranks here (one all-reduce of the flat buffer), BEFORE the
+                        # finite check and the optimizer step, as DDP's backward hooks would have
+                        engine.allreduce_grads(sync_group)
                     output, cross_entropy_loss, loss = res["mean_logit"], res["ce"], res["loss"]
                     scaled_kl = res["kl"] / dataloader.batch_size * kl_weight
                     if not bool(torch.isfinite(loss)):
@@ -128,6 +134,22 @@ def train_multimodal_model(multimodal_model: nn.Module, dataloader, criterion: n
         logging.error(f"Error at epoch {epoch}", exc_info=True)
         train_loss, train_accuracy = 0.0, 0.0
     return train_loss, train_accuracy
+
+
+def ddp_sync_group(model: nn.Module, engine):
+    """The process group over which the S-batched engine's gradients must be averaged, or False when no exchange is
+    needed. The reference's loops rely on the wrapper (`model(x)` through DistributedDataParallel synchronises gradients
+    in backward); TrainEngine bypasses the wrapper's forward, so the drop-in loops do the exchange themselves whenever the
+    model they were handed is DDP-wrapped and torch.distributed runs with more than one rank. nn.DataParallel (what
+    reference utils/device.py:19 uses) is single-process: the engine runs the whole minibatch on the module's device."""
+    if engine is None or not isinstance(model, nn.parallel.DistributedDataParallel):
+        return False
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(model.process_group) < 2:
+        return False
+    if engine._flat is None:
+        engine.flatten_grads()
+    return model.process_group
 
 
 def train_engine_for(module: nn.Module, criterion) -> Optional["TrainEngine"]:

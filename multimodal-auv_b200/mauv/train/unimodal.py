@@ -15,7 +15,7 @@ from torch import nn
 from .. import ops
 from ..bayesian import get_kl_loss
 from ..engine import MCEngine
-from .multimodal import _confusion_matrix_png, _save_model, train_engine_for
+from .multimodal import _confusion_matrix_png, _save_model, ddp_sync_group, train_engine_for
 
 
 def _pick_input(batch, device, model_type):
@@ -46,6 +46,7 @@ def train_unimodal_model(model: nn.Module, dataloader, criterion: nn.Module, opt
             total_loss, correct, total = 0, 0, 0
             module = model.module if isinstance(model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else model
             engine = train_engine_for(module, criterion)
+            sync_group = ddp_sync_group(model, engine)
             for i, batch in enumerate(dataloader):
                 logging.info(f"Train batch {i+1}/{len(dataloader)} - Model: {model_type}")
                 model_input, labels = _pick_input(batch, device, model_type)
@@ -53,7 +54,15 @@ def train_unimodal_model(model: nn.Module, dataloader, criterion: nn.Module, opt
                     engine.zero_grad()
                     res = engine.step((model_input,), labels, num_mc, kl_weight / dataloader.batch_size)
                     output, loss = res["mean_logit"], res["loss"]
-                    optimizer.step()
+                    if sync_group is not False:
+                        engine.allreduce_grads(sync_group)       # DDP's reducer is bypassed by the engine (see ddp_sync_group)
+                    # The reference's unimodal loop has no NaN/Inf guard (train/unimodal.py:140-142). The engine's
+                    # gradients travel in scaled fp16, so one overflow would poison the Adam moments for good: skip the
+                    # update for such a batch (what train/multimodal.py:141-145 does) instead of applying it.
+                    if bool(engine.grads_finite()):
+                        optimizer.step()
+                    else:
+                        logging.warning("Skipping optimizer step due to NaN/Inf gradients")
                 else:
                     optimizer.zero_grad()
                     outputs = [model(model_input) for _ in range(num_mc)]

@@ -92,7 +92,7 @@ class TrainEngine(MCEngine):
         self.live_samples = int(os.environ.get("MAUV_TRAIN_LIVE_SAMPLES", "0")) or None
         self._kl_plan = None
         self._bayes = [l for _, l in bayesian_layers(self.model)]
-        self._sample_cursor = max([l._calls for l in self._bayes] + [0])
+        self._sample_cursor = max([l._calls for l in self._bayes] + [self._sample_cursor])
 
     # ------------------------------------------------------------------ forward with tape
     def _conv_bn_rec(self, c: _Conv, bn, x, G, B, s0, eps, seed) -> tuple:
@@ -365,14 +365,16 @@ class TrainEngine(MCEngine):
         -> {"loss", "ce", "kl" (unscaled), "mean_logit" [B, C]} (device tensors; nothing is synchronised)."""
         seed = current_seed() if seed is None else seed
         stale = reference_stale_eps()
-        if sample0 is None:                   # fresh Philox sample ids every step, in step with the layers' own counters
-            sample0 = self._sample_cursor
-            self._sample_cursor += S
-            for l in self._bayes:
-                l._calls += S
         if eps is None:
             from . import engine as _engine
             eps = _engine.DEBUG_EPS               # test hook: injected eps instead of Philox (see engine.py)
+        if sample0 is None:                   # fresh Philox sample ids every step, in step with the layers' own counters
+            if eps is not None:
+                sample0 = 0                   # injected eps is indexed by sample id
+            else:
+                sample0 = self.take_samples(S)
+                for l in self._bayes:
+                    l._calls += S
         xs = [x.to(self.device, F32).contiguous() for x in inputs]
         labels = labels.to(self.device, torch.int64).contiguous()
         B = xs[0].shape[0]

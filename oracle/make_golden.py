@@ -223,9 +223,29 @@ def main():
     gold["eval_uni_csv_header"] = rows[0]
     gold["eval_uni_csv_row"] = rows[1]
 
+    # ---- (6) train_unimodal_model: one ELBO step with Adam on the image branch ---------------------
+    um.load_state_dict(o_um.state_dict())
+    opt_u = torch.optim.Adam(um.parameters(), lr=1e-4)
+    inj = _EpsInjector(um, eps_u)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "logs", "utrain.csv")
+        os.makedirs(os.path.dirname(p))
+        acc_u, loss_u = tum.train_unimodal_model(um, loader, nn.CrossEntropyLoss(), opt_u, epoch=1, total_num_epochs=20, num_mc=S,
+                                                 sum_writer=_W(), device=torch.device("cpu"), model_type="image", csv_path=p)
+        rows = list(csv.reader(open(p)))
+    inj.remove()
+    gold["train_uni_return"] = (float(acc_u), float(loss_u))
+    gold["train_uni_csv_header"] = rows[0]
+    gold["train_uni_csv_row"] = rows[1]
+    sd = um.state_dict()
+    gold["train_uni_after"] = {k: sd[k].flatten()[:8].clone() for k in
+                               ("model.fc.mu_weight", "model.fc.rho_weight", "model.fc.mu_bias", "model.conv1.mu_kernel",
+                                "model.conv1.rho_kernel", "model.layer4.2.conv3.rho_kernel")}
+    gold["train_uni_before"] = {k: o_um.state_dict()[k].flatten()[:8].clone() for k in gold["train_uni_after"]}
+
     torch.save(gold, OUT / "reference_small.pt")
     print("wrote", OUT / "reference_small.pt", {k: (tuple(v.shape) if torch.is_tensor(v) else v)
-                                                for k, v in gold.items() if k != "train_mm_after"})
+                                                for k, v in gold.items() if not k.endswith(("_after", "_before"))})
 
 
 if __name__ == "__main__":

@@ -23,8 +23,8 @@ S = 7
 img, bathy, sss, _ = O.synthetic_batch(4, size=64)
 xs = [t.cuda() for t in (img, bathy, sss)]
 pred = MCPredictor(model, S)
-out = pred.predict_device(xs, seed=99)
-single = MCEngine(model).forward_mc(xs, S, seed=99)          # all samples on this rank
+out = pred.predict_device(xs, seed=99, sample0=0)
+single = MCEngine(model).forward_mc(xs, S, seed=99, sample0=0)          # all samples on this rank
 ok = torch.equal(out["logits"], single)
 gathered = [torch.empty_like(out["mean_prob"]) for _ in range(world)]
 torch.distributed.all_gather(gathered, out["mean_prob"])

@@ -163,17 +163,17 @@ def test_grouping_and_sharding_invariance(bu):
     img, bathy, sss, _ = O.synthetic_batch(4, size=64)
     xs = [t.cuda() for t in (img, bathy, sss)]
     S = 5
-    full = eng.forward_mc(xs, S, seed=123, group=5)
-    one = eng.forward_mc(xs, S, seed=123, group=1)
-    two = eng.forward_mc(xs, S, seed=123, group=2)
+    full = eng.forward_mc(xs, S, seed=123, group=5, sample0=0)
+    one = eng.forward_mc(xs, S, seed=123, group=1, sample0=0)
+    two = eng.forward_mc(xs, S, seed=123, group=2, sample0=0)
     assert torch.equal(full, one) and torch.equal(full, two)
     parts = []
     for r in range(3):
         lo, hi = shard_samples(S, 3, r)
         parts.append(eng.forward_mc(xs, hi - lo, sample0=lo, seed=123))
     assert torch.equal(full, torch.cat(parts))
-    again = eng.forward_mc(xs, S, seed=123)
-    other = eng.forward_mc(xs, S, seed=124)
+    again = eng.forward_mc(xs, S, seed=123, sample0=0)
+    other = eng.forward_mc(xs, S, seed=124, sample0=0)
     assert torch.equal(full, again) and not torch.equal(full, other)
     assert not torch.equal(full[0], full[1])          # disjoint Philox streams per sample
 
@@ -189,11 +189,11 @@ def test_odd_batch_full_resolution_inference_and_training(bu):
     img, bathy, sss, labels = O.synthetic_batch(3, size=256)
     xs = [t.cuda() for t in (img, bathy, sss)]
     eng = MCEngine(model)
-    a = eng.forward_mc(xs, 5, seed=9, group=5)
-    b = eng.forward_mc(xs, 5, seed=9, group=2)
+    a = eng.forward_mc(xs, 5, seed=9, group=5, sample0=0)
+    b = eng.forward_mc(xs, 5, seed=9, group=2, sample0=0)
     assert torch.equal(a, b) and torch.isfinite(a).all()
     eng.fuse_conv3 = False                                   # unfused plan: raw conv outputs + separate BN passes
-    c = eng.forward_mc(xs, 5, seed=9, group=5)
+    c = eng.forward_mc(xs, 5, seed=9, group=5, sample0=0)
     # same mathematics, different rounding points (BN statistics from fp32 accumulators vs fp16-rounded outputs, scales folded
     # into weights): agreement at the level of the fp16 noise amplification of DESIGN 4.3
     assert (a - c).abs().max().item() < 0.1 * max(1.0, c.abs().max().item())
@@ -249,7 +249,7 @@ def test_philox_production_path_matches_oracle_with_regenerated_eps(bu):
     assert worst < 1.5e-3, worst                      # at most one fp16 ulp on isolated elements (libm differences in eps)
     img, bathy, sss, _ = O.synthetic_batch(2, size=64)
     xs = [t.cuda() for t in (img, bathy, sss)]
-    got_philox = eng.forward_mc(xs, S, seed=seed)
+    got_philox = eng.forward_mc(xs, S, seed=seed, sample0=0)
     got_inject = eng.forward_mc(xs, S, eps=eps)
     ref = O.mc_logits(o_model, (img, bathy, sss), S, eps)
     assert (got_philox - got_inject).abs().max().item() < 2e-3
@@ -303,7 +303,7 @@ def test_full_size_properties_cfg2_shape(bu):
     g = torch.Generator().manual_seed(5)
     xs = [torch.randn((256, 3, 256, 256), generator=g).cuda(), torch.rand((256, 3, 256, 256), generator=g).cuda(),
           torch.rand((256, 1, 256, 256), generator=g).cuda()]
-    o = pred.predict_device(xs, seed=7)
+    o = pred.predict_device(xs, seed=7, sample0=0)
     torch.cuda.synchronize()
     assert o["logits"].shape == (2, 256, 7) and torch.isfinite(o["logits"]).all()
     assert torch.allclose(o["mean_prob"].sum(1), torch.ones(256, device="cuda"), atol=1e-5)
@@ -313,7 +313,7 @@ def test_full_size_properties_cfg2_shape(bu):
     assert torch.equal(o["argmax_prob"], o["mean_prob"].argmax(1))
     # batch-permutation equivariance: BN batch statistics are permutation invariant
     perm = torch.randperm(256, generator=g).cuda()
-    o2 = pred.predict_device([x[perm] for x in xs], seed=7)
+    o2 = pred.predict_device([x[perm] for x in xs], seed=7, sample0=0)
     assert (o2["logits"] - o["logits"][:, perm]).abs().max().item() < 2e-2 * o["logits"].abs().max().item() + 1e-3
 
 
@@ -756,14 +756,16 @@ def test_multimodal_predict_and_save_writes_reference_csv_format(bu, tmp_path):
         batches.append((img, bathy, sss, [f"im_{i}_0", f"im_{i}_1"]))
     manual_seed(7)
     p = tmp_path / "pred.csv"
+    cursor0 = model.__dict__.get("_mauv_sample_cursor", 0)     # every batch takes the next 4 Philox sample ids
     multimodal_predict_and_save(model, batches, torch.device("cuda"), str(p), num_mc_samples=4)
+    assert model.__dict__["_mauv_sample_cursor"] == cursor0 + 4 * len(batches)
     import csv as _csv
     rows = list(_csv.reader(open(p)))
     assert rows[0] == ["Image Name", "Predicted Class", "Predictive Uncertainty", "Aleatoric Uncertainty"]
     assert [r[0] for r in rows[1:]] == [n for b in batches for n in b[3]]
     pred = MCPredictor(model, 4)
     for bi, b in enumerate(batches):
-        o = pred.predict_device([t.cuda() for t in b[:3]])        # same Philox seed / sample ids -> same samples
+        o = pred.predict_device([t.cuda() for t in b[:3]], sample0=cursor0 + 4 * bi)   # same seed / sample ids -> same samples
         for j in range(2):
             r = rows[1 + 2 * bi + j]
             assert int(r[1]) == int(o["argmax_prob"][j])

@@ -183,3 +183,119 @@ def test_bench_roofline_launch_model():
     f, b = bench.tc_launch_model("mauv_conv3x3_c64_f16", "G10 M1048576 N64 K576 stream")
     assert b == 10 * 1048576 * 64 * 2 * 2 + 10 * 64 * 576 * 2
     assert bench.tc_launch_model("mauv_bn_act_f16", "G10 M100 C64 res0 dual0") is None
+
+
+# ------------------------------------------------------------------ a10: the product's own dnn_to_bnn + MOPED vs the oracle
+def test_product_dnn_to_bnn_moped_equals_oracle_and_reference_checksum():
+    """mauv.models.model_utils.define_models -> mauv.bayesian.dnn_to_bnn (the path bench.py and users take) against the
+    oracle's restatement of bayesian-torch's converter on the same seeded torchvision nets: every parameter and buffer
+    bit-equal, and the parameter checksum equal to the one recorded from the REFERENCE's define_models (tests/golden)."""
+    import logging
+    import bnn_oracle as O
+    from mauv.bayesian import Conv2dReparameterization, LinearReparameterization
+    from mauv.models.model_utils import define_models
+    logging.disable(logging.WARNING)
+    try:
+        torch.manual_seed(1234)
+        prod = define_models(torch.device("cpu"), 7, dict(O.DEFAULT_PRIOR))
+    finally:
+        logging.disable(logging.NOTSET)
+    orac = O.define_models(7, seed=1234, unimodal=True)
+    for key in ("multimodal_model", "image_model", "bathy_model", "sss_model"):
+        ps, os_ = prod[key].state_dict(), orac[key].state_dict()
+        assert list(ps.keys()) == list(os_.keys()), key
+        for k in ps:
+            assert torch.equal(ps[k], os_[k]), (key, k)
+    mm = prod["multimodal_model"]
+    layers = [m for m in mm.modules() if isinstance(m, (Conv2dReparameterization, LinearReparameterization))]
+    assert len(layers) == 174 and all(l.dnn_to_bnn_flag for l in layers)
+    assert not any(isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) for m in mm.modules())
+    # MOPED: mu = w, softplus(rho) = delta * |w| (delta = 0.1); rho is NOT the constant posterior_rho_init
+    conv = mm.image_model_feat.layer2[0].conv2
+    sigma = torch.log1p(torch.exp(conv.rho_kernel.double()))
+    assert torch.allclose(sigma, 0.1 * conv.mu_kernel.double().abs(), rtol=1e-4, atol=1e-12)
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_small.pt"), weights_only=False)
+    assert abs(float(sum(p.detach().double().sum() for p in mm.parameters())) - gold["param_checksum"]) < 1e-6
+    # without MOPED the posterior starts at N(posterior_mu_init, 0.1) / N(posterior_rho_init, 0.1) like bayesian-torch's layers
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Linear(8, 4))
+    from mauv.bayesian import dnn_to_bnn
+    dnn_to_bnn(net, dict(O.DEFAULT_PRIOR, moped_enable=False))
+    assert abs(float(net[0].rho_kernel.mean()) + 3.0) < 0.1 and abs(float(net[1].mu_weight.mean())) < 0.1
+
+
+def test_load_models_and_pathlike_checkpoints(tmp_path):
+    """models/model_utils.py:66-101 mirror: existing paths are loaded, missing ones only warn; load_reference_weights takes
+    a pathlib.Path (what the reference passes around)."""
+    import logging
+    import pathlib
+    from mauv.models.model_utils import load_models, load_pretrained_resnet_as_feature_extractor, load_reference_weights
+    logging.disable(logging.ERROR)
+    try:
+        torch.manual_seed(3)
+        src = load_pretrained_resnet_as_feature_extractor(input_channels=1)
+        p = tmp_path / "sss.pth"
+        torch.save(src.state_dict(), p)
+        img, chan, sss = load_models({"image": str(tmp_path / "missing.pth"), "sss": str(p)}, torch.device("cpu"), 7)
+        assert all(torch.equal(a, b) for a, b in zip(sss.state_dict().values(), src.state_dict().values()))
+        assert img.conv1.in_channels == 3 and chan.conv1.in_channels == 3 and sss.conv1.in_channels == 1
+        lin = torch.nn.Linear(2, 2)
+        ck = tmp_path / "lin.pth"
+        torch.save({"module." + k: v for k, v in lin.state_dict().items()}, ck)
+        missing, unexpected = load_reference_weights(torch.nn.Linear(2, 2), pathlib.Path(ck))
+        assert missing == [] and unexpected == []
+        with pytest.raises(TypeError):
+            load_reference_weights(lin, 12345)
+    finally:
+        logging.disable(logging.NOTSET)
+
+
+class _FakeEngine:
+    """Stands in for TrainEngine in the CPU test of the drivers' gradient exchange: same flatten / all-reduce plumbing
+    (mauv.flatgrad.FlatGrads), gradients written straight into `.grad` like the engine does."""
+
+    def __init__(self, module):
+        self.module, self._flat = module, None
+
+    def flatten_grads(self):
+        from mauv.flatgrad import FlatGrads
+        self._flat = FlatGrads(self.module.parameters())
+
+    def allreduce_grads(self, group=None):
+        self._flat.all_reduce_mean(group)
+
+
+def _ddp_sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from mauv.train.multimodal import ddp_sync_group
+    m = _small_model()
+    ddp = torch.nn.parallel.DistributedDataParallel(m)
+    eng = _FakeEngine(m)
+    assert ddp_sync_group(m, eng) is False                      # not wrapped: nothing to exchange
+    assert ddp_sync_group(ddp, None) is False                   # layer path: DDP's own reducer does it
+    group = ddp_sync_group(ddp, eng)
+    assert group is not False and eng._flat is not None
+    for p in m.parameters():                                    # the "engine" writes rank-dependent gradients into .grad
+        p.grad.fill_(float(rank + 1))
+    eng.allreduce_grads(group)
+    ok = all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5)) for p in m.parameters())
+    q.put((rank, ok))
+    torch.distributed.destroy_process_group()
+
+
+def test_drop_in_train_loops_average_engine_gradients_under_ddp_world2_gloo():
+    """TrainEngine bypasses DistributedDataParallel's reducer, so train_*_model must all-reduce the flat
+    gradient buffer themselves when handed a DDP-wrapped model (mauv.train.multimodal.ddp_sync_group)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
