@@ -33,6 +33,15 @@ METRIC = "MC-sampled patch-triplets/sec (S=30)"
 UNIT = "triplets/s"
 
 
+def load_traffic():
+    """Average DRAM bytes per launch of the tcgen05 kernels from the committed ncu launch list (profiles/traffic.json)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return float(json.loads(p.read_text())["tcgen05_dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -224,6 +233,27 @@ def run_ours(args):
     step_dev()
     prof = ops.stop_profile()
 
+    # per-rank view of the instrumented step (strong scaling: which terms shrink with N and which do not)
+    fam_local = {}
+    for k, (c, t) in prof.items():
+        b = k.split("|")[0]
+        fam_local[b] = fam_local.get(b, 0.0) + t
+    per_rank = None
+    if dist:
+        names = sorted(fam_local)
+        gathered = [None] * world
+        torch.distributed.all_gather_object(gathered, {"samples": hi - lo, "group": group,
+                                                       "kernel_ms": {k: round(fam_local[k], 3) for k in names}})
+        per_rank = gathered
+
+    # free the inference engine's workspaces, then the cfg3 training leg (every rank takes part: DP all-reduce)
+    train_rec = None
+    if not args.no_train_leg and MODEL_KIND == "multimodal":
+        del pred, dev_in
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        train_rec = train_leg(args, 8, S_FULL, max(3, min(args.steps, 5)), 2)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and MODEL_KIND == "multimodal":   # the CPU arm is the headline config
         cores = os.cpu_count() or 1
@@ -302,9 +332,10 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tc_kernel + conv3x3_c64_stream_kernel (tcgen05 implicit-GEMM conv, all 159 convs)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_source": peak_src,
-                         # mean DRAM read+write bytes per launch of these kernels over their 587 launches in one step,
-                         # profiles/r1b_bench_launch_list.csv.gz (ncu dram__bytes_read.sum + dram__bytes_write.sum)
-                         "traffic": 2.586e9,
+                         # mean DRAM read+write bytes per launch of these kernels in one step, from the committed ncu
+                         # capture of this command (profiles/traffic.json, written by tests/tools/ncu_summary.py from
+                         # dram__bytes_read.sum + dram__bytes_write.sum); null when no capture of this tree exists
+                         "traffic": load_traffic(),
                          "note": "algorithmic FLOPs (31.824 GFLOP per triplet-sample, recompute passes not counted) / "
                                  "summed launch durations; by shape the kernel runs at 0.89-0.94 of the tensor peak "
                                  "(K >= 2304) and at ~0.87 of the 3.9 TB/s HBM write-only peak on the wide-N 1x1 layers",
@@ -319,6 +350,10 @@ def run_ours(args):
             "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu_base,
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
+        if train_rec is not None:
+            line["train"] = train_rec
         print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()
@@ -351,18 +386,125 @@ def tc_launch_model(base: str, tag: str):
     return flops, a_bytes + w_bytes + y_bytes
 
 
-def run_train(args):
-    """cfg3 ELBO training step (secondary workload, not the headline metric): S stochastic passes of the multimodal BNN,
-    CE(mean logits) + KL/B * 2^(e+1)/2^E, backward, Adam - the body of reference train/multimodal.py:104-145.
-    --train-path engine (default): the S-batched TrainEngine (one grouped forward + one grouped backward);
-    --train-path layers: the drop-in layer path (S walks of torch autograd over the per-layer CUDA kernels).
-    N > 1: the minibatch is split over the ranks (B triplets per GPU, all S samples on every rank), gradients averaged
-    with one NCCL all-reduce per step (engine) / DistributedDataParallel (layers)."""
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device")
+def train_leg(args, B: int, S: int, steps: int, warmup: int, detail: bool = False) -> dict:
+    """cfg3 ELBO training step (BASELINE configs[2]; reference train/multimodal.py:104-145): S stochastic passes of the
+    multimodal BNN through the S-batched TrainEngine (one grouped forward + one grouped hand-written backward), loss =
+    CE(mean logits) + KL/B * 2^(e+1)/2^E, NaN/Inf guard + Adam in one fused device pass. N > 1: the minibatch is split over
+    the ranks (B triplets per GPU, all S samples on every rank - nn.DataParallel semantics) and the flat
+    fp32 gradient buffer is averaged with one NCCL all-reduce per step. Must be called by every rank. Returns the record
+    (max over ranks of the device-timed step)."""
     from mauv import ops
     from mauv.bayesian import get_kl_loss
     from mauv.train_engine import TrainEngine
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = world > 1
+    use_engine = args.train_path == "engine"
+    model = build_model_cpu().cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-5)
+    g = torch.Generator().manual_seed(4321 + rank)             # every rank trains on its own shard of the global minibatch
+    xs = [x.cuda() for x in synthetic_inputs(B, seed=4321 + rank)]
+    labels = torch.randint(0, C_CLASSES, (B,), generator=g).cuda()
+    kl_w = 2.0 / 2 ** 20                                       # epoch 0 of 20 (SURVEY 8d cfg3)
+    ar_events = []
+    if use_engine:
+        eng = TrainEngine(model)
+        eng.flatten_grads()
+
+        def step(timed_ar=False):
+            eng.zero_grad()
+            res = eng.step(xs, labels, S, kl_w / (B * world))
+            if dist:
+                if timed_ar:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    eng.allreduce_grads()
+                    e1.record()
+                    ar_events.append((e0, e1))
+                else:
+                    eng.allreduce_grads()
+            eng.optimizer_step(opt)                            # fused finite guard + Adam (mauv.optim.FusedAdam)
+            return res["loss"]
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False) if dist else model
+
+        def step(timed_ar=False):
+            opt.zero_grad(set_to_none=False)
+            out = torch.mean(torch.stack([net(*xs) for _ in range(S)]), dim=0)
+            loss = torch.nn.functional.cross_entropy(out, labels) + get_kl_loss(model) / (B * world) * kl_w
+            loss.backward()
+            opt.step()
+            return loss
+
+    for _ in range(max(1, warmup)):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        torch.distributed.barrier()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(timed_ar=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        torch.distributed.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in ar_events) / max(1, len(ar_events))],
+                     device="cuda")
+    if dist:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ar_ms = t.tolist()
+    launches = ops.launch_count - l0
+    prof_detail = None
+    if detail and use_engine and rank == 0:
+        ops.start_profile()
+        step()
+        prof = ops.stop_profile()
+        agg = {}
+        for k, (c, tms) in prof.items():
+            n = k.split("|")[0]
+            a = agg.get(n, (0, 0.0))
+            agg[n] = (a[0] + c, a[1] + tms)
+        prof_detail = {k: {"calls": c, "ms": round(tms, 3)} for k, (c, tms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        for k, (c, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:60]:
+            print(f"{tms:9.3f} ms {c:4d} x {k}", file=sys.stderr)
+    elif detail and dist:
+        step()                                                 # keep the ranks' collectives in lockstep with rank 0's extra step
+    # SURVEY 8(d): forward + dgrad + wgrad per triplet-sample (a unimodal branch: ~1/3 of it)
+    _, tf_peak, peak_src = load_peaks()
+    flops = 94.77e9 * (GFLOP_PER_SAMPLE[MODEL_KIND] / CONV_GFLOP_PER_TRIPLET_SAMPLE) * world * B * S
+    tfl = flops / (ms / 1e3) / 1e12
+    rec = {"metric": "ELBO training triplets/sec" if MODEL_KIND == "multimodal" else f"ELBO training patches/sec (unimodal {MODEL_KIND})",
+           "value": world * B / (ms / 1e3), "unit": UNIT if MODEL_KIND == "multimodal" else "patches/s",
+           "n_gpus": world, "scaling": "weak", "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "higher_is_better": True, "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients, fp32 Adam",
+           "config": {"workload": f"{'cfg3 multimodal' if MODEL_KIND == 'multimodal' else 'cfg4 unimodal ' + MODEL_KIND} ELBO step, "
+                                  f"{B} triplets per GPU, S={S}, 256x256, C=7, fused guarded Adam, "
+                                  f"path={args.train_path}, gradient all-reduce over {world} GPU(s)",
+                      "triplet_samples_per_s": world * B * S / (ms / 1e3)},
+           "model_tflops": tfl,
+           "roofline": {"bound": "tensor", "achieved": tfl / world, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfl / world / tf_peak,
+                        "peak_source": peak_src,
+                        "note": "whole step (forward + hand-written backward + KL + all-reduce + Adam) against 94.77 GFLOP per "
+                                "triplet-sample (SURVEY 8d: fwd + dgrad + wgrad), per GPU"},
+           "allreduce_ms": ar_ms if dist else 0.0,
+           "gpu_launches": launches, "loss": float(loss.detach()),
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if prof_detail is not None:
+        rec["kernel_ms_per_step"] = prof_detail
+    del model, opt, xs
+    if use_engine:
+        del eng
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args):
+    """`--workload train`: the cfg3 (or, with --model, cfg4) ELBO training step as its own bench line."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,80 +514,9 @@ def run_train(args):
     use_engine = args.train_path == "engine"
     B = args.batch if args.batch != B_FULL else 8
     S = args.samples if args.samples != S_FULL else (30 if use_engine else 5)
-    model = build_model_cpu().cuda().train()
-    opt = torch.optim.Adam(model.parameters(), lr=5e-5)
-    xs = [x.cuda() for x in synthetic_inputs(B)]
-    labels = torch.randint(0, C_CLASSES, (B,), device="cuda")
-    kl_w = 2.0 / 2 ** 20
-    if use_engine:
-        eng = TrainEngine(model)
-        eng.flatten_grads()
-
-        def step():
-            eng.zero_grad()
-            res = eng.step(xs, labels, S, kl_w / B)
-            if world > 1:
-                eng.allreduce_grads()
-            opt.step()
-            return res["loss"]
-    else:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False) if world > 1 else model
-
-        def step():
-            opt.zero_grad(set_to_none=False)
-            out = torch.mean(torch.stack([net(*xs) for _ in range(S)]), dim=0)
-            loss = torch.nn.functional.cross_entropy(out, labels) + get_kl_loss(model) / B * kl_w
-            loss.backward()
-            opt.step()
-            return loss
-
-    for _ in range(max(1, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    l0 = ops.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = t.item()
-    detail = None
-    if args.detail and use_engine and rank == 0:
-        ops.start_profile()
-        step()
-        prof = ops.stop_profile()
-        agg = {}
-        for k, (c, tms) in prof.items():
-            n = k.split("|")[0]
-            a = agg.get(n, (0, 0.0))
-            agg[n] = (a[0] + c, a[1] + tms)
-        detail = {k: {"calls": c, "ms": round(tms, 3)} for k, (c, tms) in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-        for k, (c, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:60]:
-            print(f"{tms:9.3f} ms {c:4d} x {k}", file=sys.stderr)
-    if rank != 0:
-        torch.distributed.destroy_process_group()
-        return 0
-    # forward + dgrad + wgrad per triplet-sample (a unimodal branch: ~1/3 of it)
-    flops = 94.77e9 * (GFLOP_PER_SAMPLE[MODEL_KIND] / CONV_GFLOP_PER_TRIPLET_SAMPLE) * world * B * S
-    line = {"metric": "ELBO training triplets/sec", "value": world * B / (ms / 1e3), "unit": UNIT,
-            "n_gpus": world, "scaling": "weak", "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "data": "synthetic", "dtype": "f16 operands / f32 accumulate, fp32 parameter gradients",
-            "config": {"workload": f"{'cfg3 multimodal' if MODEL_KIND == 'multimodal' else 'cfg4 unimodal ' + MODEL_KIND} ELBO step, "
-                                   f"{B} triplets per GPU, S={S}, 256x256, C=7, Adam, "
-                                   f"path={args.train_path}, gradient all-reduce over {world} GPU(s)",
-                       "triplet_samples_per_s": world * B * S / (ms / 1e3)},
-            "model_tflops": flops / (ms / 1e3) / 1e12,
-            "gpu_launches": (ops.launch_count - l0), "loss": float(loss.detach()),
-            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
-    if detail is not None:
-        line["kernel_ms_per_step"] = detail
-    print(json.dumps(line))
+    rec = train_leg(args, B, S, args.steps, args.warmup, detail=args.detail)
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -461,6 +532,7 @@ def main():
     ap.add_argument("--samples", type=int, default=S_FULL)
     ap.add_argument("--group", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the cfg3 ELBO training sub-record of the default line")
     ap.add_argument("--detail", action="store_true", help="per-shape kernel table on stderr")
     ap.add_argument("--train-path", default="engine", choices=["engine", "layers"],
                     help="--workload train: S-batched TrainEngine (default) or the drop-in layer path")

@@ -262,17 +262,19 @@ int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_par
                          int imgs_per_sample, int H, int W, void* stream);
 /* mauv_gemm_f16 whose [N][K] operand is shared by groups of batches: y[g] = a[g] * w[g % w_batches]^T (the stem's weight
  * gradient: per-sample dY^T chunks against the chunks of the one im2col matrix all samples share). */
-int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int G, long long M, int N, int K, void* stream);
+int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int out_f32, int G, long long M, int N, int K,
+                       void* stream);   /* out_f32 != 0: y is float [G][M][N], the fp32 accumulator stored unrounded */
 /* Weight gradient of the grouped conv straight from the NHWC tensors (no transposed copies): dy [G*imgs][Ho][Wo][Cout],
- * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] fp16 partial sums over pixel chunks (K order (r, s, c)). Both
+ * x [G*imgs][H][W][Cin] -> dw [G*splits][Cout][kh*kw*Cin] FP32 partial sums over pixel chunks (K order (r, s, c)): the
+ * accumulator is stored unrounded (a correlated sum over thousands of pixels can exceed fp16's range). Both
  * operands enter the tcgen05 MMA MN-major from [64 pixels][64 channels] TMA boxes (tiled for 1x1/stride 1, im2col mode
  * otherwise). Cin % 64 == 0; pixels per chunk (imgs*Ho*Wo / splits) % 64 == 0. */
 int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
                    int Cout, int kh, int kw, int stride, int pad, void* stream);
-/* dw_partial fp16 [G*splits][cout][k_pad] (value = dW_g * *scale / inv_alpha) -> grad_mu += sum_g dW_g,
+/* dw_partial fp16 or (partial_f32 != 0) fp32 [G*splits][cout][k_pad] (value = dW_g * *scale / inv_alpha) -> grad_mu += sum_g dW_g,
  * grad_rho += sum_g dW_g * eps_g * sigmoid(rho); eps injected [G][n] or Philox(seed, layer_id, sample0+g).
  * stale_eps != 0 reproduces the reference's saved-eps-buffer behaviour (every pass sees the last pass's eps). */
-int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
+int mauv_wgrad_finalize_group(const void* dw_partial, int partial_f32, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
                               float inv_alpha, const float* scale, const float* rho, const float* eps, uint64_t seed,
                               uint32_t layer_id, uint32_t sample0, int stale_eps, float* grad_mu, float* grad_rho,
                               void* stream);
@@ -293,6 +295,21 @@ int mauv_softmax_gate_bwd_f32(const float* score, const float* v, const float* d
  * [0, C) makes the loss NaN (torch: device assert) and leaves that row's gradient zero - never read out of bounds. */
 int mauv_ce_mean_fwd_bwd_f32(const float* logits, const long long* labels, int S, int B, int C, float* mean_logit,
                              float* dlogits, float* loss, void* stream);
+
+/* ---- f1: fused Adam + finite-gradient guard over flat buffers ------------------------------------------------------
+ * Replaces the reference's NaN/Inf guard loop + optimizer.step() (train/multimodal.py:141-145; the optimizers are
+ * `optim.Adam(model.parameters(), lr=...)`, train/loop_utils.py:46-52). p, g, m, v: n contiguous fp32 each (parameters,
+ * gradients, exp_avg, exp_avg_sq); state: mauv_adam_state_bytes() device bytes, zeroed once by the caller, layout
+ * {int step, int applied, int scratch, int pad, float step_size, float inv_sqrt_bc2, pad[2]}. If any gradient is NaN/Inf
+ * nothing is updated, `applied` = 0 and the step count does not advance - decided on the device, no host sync. Arithmetic
+ * as torch.optim.Adam (amsgrad=False, maximize=False; weight_decay = L2 added to the gradient). */
+int mauv_adam_state_bytes(void);
+int mauv_adam_step_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, void* state, void* stream);
+
+/* ---- measurement aid (not on the product path): HBM write probes, see csrc/membench.cu ---------------------------
+ * mode 0 st.global.v4, 1 st.global.cs.v4, 2 cp.async.bulk shared->global (the engine TMA stores use). */
+int mauv_membench_fill(void* dst, long long bytes, unsigned int value, int mode, void* stream);
 
 #ifdef __cplusplus
 }

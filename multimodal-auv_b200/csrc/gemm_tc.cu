@@ -63,6 +63,8 @@ struct GemmParams {
   int a_wrap_kb;         // tiled A: k-block count after which A's column coordinate wraps to 0 (0 = never)
   int a_cwrap;           // im2col A: channel-block period of A (0 = never)
   int split;             // epilogue writes (hi | lo) fp16 pairs: hi at column n, lo at column N + n
+  int out_f32;           // EPI 0: the fp32 accumulator is written as is to y (float [G][M][N], plain vector stores, no TMA, no
+                         // statistics): weight-gradient partial sums must not be rounded to / overflow fp16
   // weight-gradient mode (mauv_wgrad_f16): Y[batch][co][k] = sum_pixels dY[pixel][co] * Xcol[pixel][k]. Both operands are
   // MN-major: TMA boxes of [64 pixels][64 channels] straight from the row-major dY and the NHWC activations (tiled for
   // 1x1 / stride 1, im2col-mode for everything else); the batch index is (sample, pixel chunk), k_blocks = chunk / 64.
@@ -163,26 +165,38 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const long long tiles_per_sample = static_cast<long long>(p.m_tiles) * p.n_tiles;
   // tile -> (g, m_tile, n_tile). n-tile fastest so concurrent CTAs share their A tile through L2; when A is shared
   // by all samples (stem) the sample index is the fastest instead, so the G samples of one m-tile run together.
-  auto decode = [&](long long tile, int& g, int& m_tile, int& n_tile) {
+  // (32-bit unsigned arithmetic: total_tiles < 2^31 is checked on the host; a 64-bit division costs ~100 instructions and
+  // the epilogue decodes once per 64-column block)
+  const uint32_t tps32 = static_cast<uint32_t>(tiles_per_sample);
+  auto decode = [&](long long tile64, int& g, int& m_tile, int& n_tile) {
+    const uint32_t tile = static_cast<uint32_t>(tile64);
+    const uint32_t mt = static_cast<uint32_t>(p.m_tiles), nt = static_cast<uint32_t>(p.n_tiles);
     if (EPI == EPI_STATS_T) {       // channel tile fastest: the (big) pixel operand is fetched from HBM once
-      m_tile = static_cast<int>(tile % p.m_tiles);
-      const long long rem = tile / p.m_tiles;
-      n_tile = static_cast<int>(rem % p.n_tiles);
-      g = static_cast<int>(rem / p.n_tiles);
+      const uint32_t rem = tile / mt;
+      m_tile = static_cast<int>(tile - rem * mt);
+      const uint32_t gg = rem / nt;
+      n_tile = static_cast<int>(rem - gg * nt);
+      g = static_cast<int>(gg);
     } else if (p.stack > 1) {       // g = first sample of the tile's sample block; a single n-tile
-      g = static_cast<int>(tile % p.g_blocks) * p.stack;
-      m_tile = static_cast<int>(tile / p.g_blocks);
+      const uint32_t gbk = static_cast<uint32_t>(p.g_blocks);
+      const uint32_t mm = tile / gbk;
+      g = static_cast<int>(tile - mm * gbk) * p.stack;
+      m_tile = static_cast<int>(mm);
       n_tile = 0;
     } else if (p.a_batch_mul == 0) {
-      g = static_cast<int>(tile % p.G);
-      const long long rem = tile / p.G;
-      n_tile = static_cast<int>(rem % p.n_tiles);
-      m_tile = static_cast<int>(rem / p.n_tiles);
+      const uint32_t G = static_cast<uint32_t>(p.G);
+      const uint32_t rem = tile / G;
+      g = static_cast<int>(tile - rem * G);
+      const uint32_t mm = rem / nt;
+      n_tile = static_cast<int>(rem - mm * nt);
+      m_tile = static_cast<int>(mm);
     } else {
-      g = static_cast<int>(tile / tiles_per_sample);
-      const long long rem = tile - g * tiles_per_sample;
-      m_tile = static_cast<int>(rem / p.n_tiles);
-      n_tile = static_cast<int>(rem - static_cast<long long>(m_tile) * p.n_tiles);
+      const uint32_t gg = tile / tps32;
+      const uint32_t rem = tile - gg * tps32;
+      const uint32_t mm = (nt == 1u) ? rem : rem / nt;
+      g = static_cast<int>(gg);
+      m_tile = static_cast<int>(mm);
+      n_tile = static_cast<int>(rem - mm * nt);
     }
   };
 
@@ -391,122 +405,200 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tma_load_3d(my_out + (b % 3u) * L::kOutBufBytes, &tmR, bar, nb, rmax > 0 ? row0 : 0, gb);
         }
       };
+      // flat loop over this warp's work items (tile, 64-column block) with a one-item look-ahead on the TMEM side: the
+      // tcgen05.ld of the next item's half is issued as soon as the current half has been transformed (see EPI 0 below)
+      long long tile = blockIdx.x;
+      int cb = cset;
       uint32_t it = 0, b = 0;
-      if (lane == 0 && blockIdx.x < p.total_tiles) issue_residual(0, blockIdx.x, cset);
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
-        mbar_wait(tmem_full_bar(acc), acc_phase);
+      uint32_t ra[32], rb[32];
+      float* my_ss = stat_smem + wq * 128;          // the statistics staging area is unused by this epilogue flavour
+      const uint32_t my_ss_addr = smem_u32(my_ss);
+      int ss_g = -1, ss_n = -1;
+      auto acc_addr = [&](uint32_t it_, int cb_) {
+        return tmem_base + (it_ & 1u) * BN + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(cb_ * 64);
+      };
+      if (tile < p.total_tiles && cb < kBlocksPerTile) {
+        if (lane == 0) issue_residual(0, tile, cb);
+        mbar_wait(tmem_full_bar(0), 0);
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int cb = cset; cb < kBlocksPerTile; cb += kColSets, ++b) {
-          int gb, nb, row0, rmax;
-          block_coords(tile, cb, gb, nb, row0, rmax);
-          if (lane == 0) {
-            // buffer (b+1)%3 was last used by block b-2: its store must have finished reading smem
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            long long ntile = tile;
-            int ncb = cb + kColSets;
-            if (ncb >= kBlocksPerTile) { ntile += gridDim.x; ncb = cset; }
-            if (ntile < p.total_tiles) issue_residual(b + 1, ntile, ncb);
+        tmem_ld_32x32b_x32(acc_addr(0, cb), ra);
+        tmem_ld_32x32b_x32(acc_addr(0, cb) + 32, rb);
+      }
+      while (tile < p.total_tiles && cb < kBlocksPerTile) {
+        int gb, nb, row0, rmax;
+        block_coords(tile, cb, gb, nb, row0, rmax);
+        long long ntile = tile;
+        int ncb = cb + kColSets;
+        uint32_t nit = it;
+        if (ncb >= kBlocksPerTile) { ncb = cset; ntile += gridDim.x; ++nit; }
+        const bool last_of_tile = ntile != tile;
+        const bool has_next = ntile < p.total_tiles;
+        if (lane == 0) {
+          // buffer (b+1)%3 was last used by block b-2: its store must have finished reading smem
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (has_next) issue_residual(b + 1, ntile, ncb);
+        }
+        tmem_ld_wait();
+        if (last_of_tile) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(it & 1u));
+        }
+        auto prefetch = [&](uint32_t (&dst)[32], int half) {
+          if (!has_next) return;
+          if (last_of_tile && half == 0) {
+            mbar_wait(tmem_full_bar(nit & 1u), (nit >> 1) & 1u);
+            tcgen05_fence_after();
           }
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32b_x32(taddr + cb * 64, ra);
-          tmem_ld_32x32b_x32(taddr + cb * 64 + 32, rb);
-          tmem_ld_wait();
-          if (cb + kColSets >= kBlocksPerTile) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-          }
-          const uint32_t buf = my_out + (b % 3u) * L::kOutBufBytes;
-          if (p.has_res) mbar_wait(res_bar(wq, b % 3u), (b / 3u) & 1u);
-          const float2* ssp = p.ss + static_cast<long long>(gb) * p.N + nb;
+          tmem_ld_32x32b_x32(acc_addr(nit, ncb) + 32 * half, dst);
+        };
+        const uint32_t buf = my_out + (b % 3u) * L::kOutBufBytes;
+        if (p.has_res) mbar_wait(res_bar(wq, b % 3u), (b / 3u) & 1u);
+        // (scale, shift) of this block's 64 channels, de-interleaved into this warp's private shared-memory slice (scale[64] |
+        // shift[64]) and re-read with broadcast 16-byte loads: 32 LDS.128 per block instead of 64 LDG.64, and the pairs come
+        // out as packed fp32x2 operands. Reloaded only when the (sample, channel block) changes - with N = BN once per sample.
+        if (gb != ss_g || nb != ss_n) {
+          __syncwarp();
+          const float4 two = __ldg(reinterpret_cast<const float4*>(p.ss + static_cast<long long>(gb) * p.N + nb) + lane);
+          my_ss[2 * lane] = two.x; my_ss[2 * lane + 1] = two.z;               // scales of channels 2*lane, 2*lane+1
+          my_ss[64 + 2 * lane] = two.y; my_ss[64 + 2 * lane + 1] = two.w;     // shifts
+          __syncwarp();
+          ss_g = gb; ss_n = nb;
+        }
+        auto transform_half = [&](const uint32_t (&r)[32], int half) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t* src = (q < 4) ? &ra[q * 8] : &rb[(q - 4) * 8];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int q = half * 4 + q4;                 // 16-byte chunk of the 128-byte row = channels 8q .. 8q+7
+            const uint32_t* src = &r[q4 * 8];
             const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
-            float v[8];
+            unsigned long long sc[4], sh[4], v[4];
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[0]), "=l"(sc[1]) : "r"(my_ss_addr + q * 32u));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[2]), "=l"(sc[3]) : "r"(my_ss_addr + q * 32u + 16u));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[0]), "=l"(sh[1]) : "r"(my_ss_addr + 256u + q * 32u));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[2]), "=l"(sh[3]) : "r"(my_ss_addr + 256u + q * 32u + 16u));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 t = __ldg(ssp + q * 8 + j);
-              v[j] = fmaf(__uint_as_float(src[j]), t.x, t.y);
+            for (int j = 0; j < 4; ++j) {
+              unsigned long long a2;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(src[2 * j]), "r"(src[2 * j + 1]));
+              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v[j]) : "l"(a2), "l"(sc[j]), "l"(sh[j]));
             }
             if (p.has_res) {
-              uint32_t r0, r1, r2, r3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-              const uint32_t rr[4] = {r0, r1, r2, r3};
+              uint32_t rr[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(addr));
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
+                unsigned long long f2;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(f.x), "f"(f.y));
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v[j]) : "l"(f2));
               }
             }
-            if (p.relu) {
+            uint32_t h[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 4; ++j) {
+              float lo, hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[j]));
+              __half2 hh = __floats2half2_rn(lo, hi);
+              if (p.relu) hh = __hmax2(hh, __float2half2_rn(0.f));      // ReLU after rounding == rounding after ReLU
+              h[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-            __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h3))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          }
+        };
+        transform_half(ra, 0);
+        prefetch(ra, 0);
+        transform_half(rb, 1);
+        prefetch(rb, 1);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (rmax > 0)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmY)),
+                         "r"(buf), "r"(nb), "r"(row0), "r"(gb)
                          : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (rmax > 0)
-              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmY)),
-                           "r"(buf), "r"(nb), "r"(row0), "r"(gb)
-                           : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        tile = ntile; cb = ncb; it = nit; ++b;
       }
     } else {
+    // Flat loop over this warp's work items (tile, 64-column block) with a one-item look-ahead on the TMEM side: as soon as
+    // a half (32 columns) of the accumulator has been converted and staged, the tcgen05.ld of the NEXT item's half is
+    // issued, so the TMEM read (64 B/clk per SM: 2 048 clk for a 128x256 fp32 tile) overlaps the staging, the TMA store
+    // and the statistics pass instead of being waited for by all 8 warps at once. The two column sets (warps 4-7 / 8-11)
+    // combine their statistics behind their OWN named barrier and may drift apart by up to one tile.
+    constexpr int kBlocks = BN / 64;
+    constexpr int kSetThreads = 128;
+    const int es = threadIdx.x - 128 - cset * kSetThreads;        // 0..127 inside this column set
+    long long tile = blockIdx.x;
+    int cb = cset;
     uint32_t it = 0, blk = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    uint32_t ra[32], rb[32];
+    auto acc_addr = [&](uint32_t it_, int cb_) {
+      return tmem_base + (it_ & 1u) * BN + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(cb_ * 64);
+    };
+    if (tile < p.total_tiles && cb < kBlocks) {
+      mbar_wait(tmem_full_bar(0), 0);
+      tcgen05_fence_after();
+      tmem_ld_32x32b_x32(acc_addr(0, cb), ra);
+      tmem_ld_32x32b_x32(acc_addr(0, cb) + 32, rb);
+    }
+    while (tile < p.total_tiles && cb < kBlocks) {
       int g, m_tile, n_tile;
       decode(tile, g, m_tile, n_tile);
       const uint32_t acc = it & 1u;
-      const uint32_t acc_phase = (it >> 1) & 1u;
       const int row0 = m_tile * BM + ew * 32;
       int rmax = p.M - row0;            // valid rows of this warp's 32-row slab
       rmax = rmax < 0 ? 0 : (rmax > 32 ? 32 : rmax);
       const int n0 = n_tile * BN;
       const float* bias = p.bias ? p.bias + static_cast<long long>(g) * p.N + n0 : nullptr;
       float* stat_buf = stat_smem + (it & 1u) * (4 * BN * 2);
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+      // next work item of this warp
+      long long ntile = tile;
+      int ncb = cb + kColSets;
+      uint32_t nit = it;
+      if (ncb >= kBlocks) { ncb = cset; ntile += gridDim.x; ++nit; }
+      const bool last_of_tile = ntile != tile;
+      const bool has_next = ntile < p.total_tiles;
+      const int col0 = cb * 64;
+      // stacked mode: this 64-column block belongs to sample gb at channel offset nb
+      const int gb = (p.stack > 1) ? g + col0 / p.N : g;
+      const int nb = (p.stack > 1) ? col0 % p.N : n0 + col0;
+      const bool cols_ok = (p.stack > 1) ? (gb < p.G) : (nb < p.N);     // warp uniform
 
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int cb = cset; cb < BN / 64; cb += kColSets) {
-        const int col0 = cb * 64;
-        // stacked mode: this 64-column block belongs to sample gb at channel offset nb
-        const int gb = (p.stack > 1) ? g + col0 / p.N : g;
-        const int nb = (p.stack > 1) ? col0 % p.N : n0 + col0;
-        const bool cols_ok = (p.stack > 1) ? (gb < p.G) : (nb < p.N);     // warp uniform
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32b_x32(taddr + col0, ra);
-        tmem_ld_32x32b_x32(taddr + col0 + 32, rb);
-        tmem_ld_wait();
-        if (cb + kColSets >= BN / 64) {
-          // every TMEM read of this accumulator stage is complete -> hand it back to the MMA warp early
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      tmem_ld_wait();                   // ra / rb of this item are in registers
+      if (last_of_tile) {
+        // every TMEM read of this accumulator stage by this warp is complete -> hand it back to the MMA warp early
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      }
+      auto prefetch = [&](uint32_t (&dst)[32], int half) {    // next item's half, once its registers are dead
+        if (!has_next) return;
+        if (last_of_tile && half == 0) {
+          mbar_wait(tmem_full_bar(nit & 1u), (nit >> 1) & 1u);
+          tcgen05_fence_after();
         }
-        if (!cols_ok) {
-          if (p.stats) {
-            *reinterpret_cast<float4*>(stat_buf + (ew * BN + col0 + 2 * lane) * 2) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          continue;
-        }
+        tmem_ld_32x32b_x32(acc_addr(nit, ncb) + 32 * half, dst);
+      };
+      if (p.out_f32) {
+        // lane = output row (a Cout index in weight-gradient mode), 64 consecutive fp32 columns = 256 contiguous bytes
+        float* dst = reinterpret_cast<float*>(p.y) + (static_cast<long long>(gb) * p.M + row0 + lane) * p.N + nb;
+        const bool row_ok = cols_ok && static_cast<int>(lane) < rmax;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (row_ok && nb + j < p.N) *reinterpret_cast<uint4*>(dst + j) = make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]);
+        prefetch(ra, 0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (row_ok && nb + 32 + j < p.N)
+            *reinterpret_cast<uint4*>(dst + 32 + j) = make_uint4(rb[j], rb[j + 1], rb[j + 2], rb[j + 3]);
+        prefetch(rb, 1);
+      } else if (!cols_ok) {
+        prefetch(ra, 0);
+        prefetch(rb, 1);
+        if (p.stats) *reinterpret_cast<float4*>(stat_buf + (ew * BN + col0 + 2 * lane) * 2) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
         if (bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -523,32 +615,39 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         __syncwarp();
+        auto stage_half = [&](const uint32_t (&r)[32], int half) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t* src = (q < 4) ? &ra[q * 8] : &rb[(q - 4) * 8];
-          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]), __uint_as_float(src[1]));
-          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]), __uint_as_float(src[3]));
-          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]), __uint_as_float(src[5]));
-          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]), __uint_as_float(src[7]));
-          const uint32_t off = lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                       "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
-                       "r"(*reinterpret_cast<uint32_t*>(&h3))
-                       : "memory");
-          if (p.split) {
-            const __half2 hh[4] = {h0, h1, h2, h3};
-            uint32_t lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(hh[j]);
-              __half2 l = __floats2half2_rn(__uint_as_float(src[2 * j]) - f.x, __uint_as_float(src[2 * j + 1]) - f.y);
-              lo[j] = *reinterpret_cast<uint32_t*>(&l);
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
-                         "r"(lo[3])
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int q = half * 4 + q4;
+            const uint32_t* src = &r[q4 * 8];
+            __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]), __uint_as_float(src[1]));
+            __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]), __uint_as_float(src[3]));
+            __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]), __uint_as_float(src[5]));
+            __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            const uint32_t off = lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h3))
                          : "memory");
+            if (p.split) {
+              const __half2 hh[4] = {h0, h1, h2, h3};
+              uint32_t lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hh[j]);
+                __half2 l = __floats2half2_rn(__uint_as_float(src[2 * j]) - f.x, __uint_as_float(src[2 * j + 1]) - f.y);
+                lo[j] = *reinterpret_cast<uint32_t*>(&l);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                           "r"(lo[3])
+                           : "memory");
+            }
           }
-        }
+        };
+        stage_half(ra, 0);
+        prefetch(ra, 0);
+        stage_half(rb, 1);
+        prefetch(rb, 1);
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (EPI == EPI_STORE_STATS && lane == 0 && rmax > 0) {
@@ -604,10 +703,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ++blk;
       }
 
-      if (p.stats) {
-        // combine the 4 epilogue warps and emit one deterministic partial per (tile, channel)
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        for (int j = et; j < BN; j += kEpiThreads) {
+      if (p.stats && last_of_tile) {
+        // combine the 4 lane-quarter warps of THIS column set and emit one deterministic partial per (tile, channel)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + cset), "n"(kSetThreads) : "memory");
+        for (int jj = es; jj < 64 * ((kBlocks - cset + kColSets - 1) / kColSets); jj += kSetThreads) {
+          const int j = (cset + (jj >> 6) * kColSets) * 64 + (jj & 63);        // this set's column blocks
           const int gj = (p.stack > 1) ? g + j / p.N : g;
           const int nj = (p.stack > 1) ? j % p.N : n0 + j;
           if (nj < p.N && gj < p.G) {
@@ -623,6 +723,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      tile = ntile; cb = ncb; it = nit;
     }
     }
     // smem must stay valid until the last bulk stores have read it; global visibility at kernel end
@@ -741,7 +842,7 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
   const int bn = (p.stack > 1 || epi == EPI_STATS_T) ? 256 : pick_bn(p.N);
   // output [G][M][N] fp16 written by TMA: box = 64 channels x 32 rows (one epilogue warp's slab)
   CUtensorMap tmY;
-  const int n_out = p.split ? 2 * p.N : p.N;
+  const int n_out = (p.split || p.out_f32) ? 2 * p.N : p.N;      // out_f32: the (unused) map spans the same bytes
   if (int rc = make_tiled_map(&tmY, p.y, n_out, p.M, p.G, static_cast<int64_t>(p.M) * n_out, 32)) return rc;
   p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
   p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
@@ -752,6 +853,7 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
     p.total_tiles = static_cast<long long>(p.m_tiles) * p.g_blocks;
   }
   if (p.total_tiles == 0) return MAUV_OK;
+  MAUV_CHECK_ARG(p.total_tiles < (1LL << 31), "gemm_f16_tc: too many tiles (%lld)", p.total_tiles);
   CUtensorMap tmR = tmY;
   if (epi == EPI_FUSED_BN && residual) {
     if (int rc = make_tiled_map(&tmR, residual, p.N, p.M, p.G, static_cast<int64_t>(p.M) * p.N, 32)) return rc;
@@ -1163,7 +1265,8 @@ int mauv_conv3x3_c64_f16(const void* x, const void* w, void* y, float* stats_par
 
 // mauv_gemm_f16 whose [N][K] operand is shared by groups of batches: y[g] = a[g] * w[g % w_batches]^T. Used by the stem's
 // weight gradient (dY_s^T chunks against the chunks of the ONE im2col matrix all samples share): one launch for all samples.
-int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int G, long long M, int N, int K, void* stream) {
+int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int out_f32, int G, long long M, int N, int K,
+                       void* stream) {
   MAUV_CHECK_ARG(a && w && y && w_batches >= 1 && G >= 1 && M >= 1, "mauv_gemm_wmod_f16: bad argument");
   MAUV_CHECK_ARG(N >= 8 && K >= 8 && K % 8 == 0 && N % 8 == 0, "mauv_gemm_wmod_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
   MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -1181,12 +1284,14 @@ int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int
   p.a_mode = 0;
   p.a_batch_mul = 1;
   p.b_mod = w_batches;
+  p.out_f32 = out_f32 ? 1 : 0;
   p.y = static_cast<__half*>(y);
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
 // ---- weight gradient of the grouped conv, straight from NHWC operands ---------------------------------------------
 // dw[(g, chunk)][co][(r, s, c)] = sum over the chunk's output pixels of dy[pixel][co] * x[pixel shifted by tap (r,s)][c]
+// dw is FP32 ([G*splits][Cout][kh*kw*Cin] floats): the accumulator is stored unrounded.
 int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
                    int Cout, int kh, int kw, int stride, int pad, void* stream) {
   MAUV_CHECK_ARG(dy && x && dw && G >= 1 && splits >= 1, "mauv_wgrad_f16: bad argument");
@@ -1236,6 +1341,7 @@ int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, i
   p.cin = Cin;
   p.Wo = Wo; p.Ho = Ho; p.imgs_per_sample = imgs_per_sample; p.stride = stride; p.pad = pad; p.kw = kw;
   p.y = static_cast<__half*>(dw);
+  p.out_f32 = 1;          // fp32 partial sums: a correlated dy*x sum over thousands of pixels can exceed fp16's 65504
   p.stats = nullptr;
   p.bias = nullptr;
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
@@ -1334,6 +1440,7 @@ int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial
     q.m_tiles = static_cast<int>(ceil_div_i64(q.M, BM));
     q.n_tiles = static_cast<int>(ceil_div_i64(q.N, 256));
     q.total_tiles = static_cast<long long>(q.m_tiles) * q.n_tiles * q.G;
+    MAUV_CHECK_ARG(q.total_tiles < (1LL << 31), "mauv_gemm_bn_f16: too many tiles (%lld)", q.total_tiles);
     return launch_gemm<256, 3>(tmA, tmB, tmY, tmY, q, static_cast<cudaStream_t>(stream));
   }
   if (int rc = make_tiled_map(&tmA, a, K, M, G, M * K, BM)) return rc;

@@ -396,8 +396,9 @@ avgpool_bwd_kernel(const float* __restrict__ dfeat, const unsigned* __restrict__
 // dw fp16 [G*splits][cout][Kp] (K order (r,s,c)), value = true dW * (*s) / inv_alpha.
 // Block = 32 element-quads x 8 sample lanes: a thread finalises 4 consecutive PyTorch-order elements (one Philox4x32 block
 // per sample) for the samples g = lane, lane+8, ...; the 8 lanes are then summed in a fixed order (deterministic).
+template <typename DW>   // __half (explicit-transpose path) or float (direct weight-gradient GEMM) partial sums
 __global__ void __launch_bounds__(256)
-wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, int cout, int cin, int kh, int kw, int Kp,
+wgrad_finalize_group_kernel(const DW* __restrict__ dw, int G, int splits, int cout, int cin, int kh, int kw, int Kp,
                             float inv_alpha, const float* __restrict__ s, const float* __restrict__ rho,
                             const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0, int stale,
                             float* __restrict__ grad_mu, float* __restrict__ grad_rho) {
@@ -428,15 +429,25 @@ wgrad_finalize_group_kernel(const __half* __restrict__ dw, int G, int splits, in
     for (int g = gl; g < G; g += 8) {
       float d[4] = {0.f, 0.f, 0.f, 0.f};
       for (int sp = 0; sp < splits; ++sp) {
-        const __half* base = dw + (static_cast<long long>(g) * splits + sp) * gstride;
-        if (vec) {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + off[0]));
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-          d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
-        } else {
+        const DW* base = dw + (static_cast<long long>(g) * splits + sp) * gstride;
+        if constexpr (sizeof(DW) == 4) {
+          if (vec) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + off[0]));
+            d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) d[i] += live[i] ? __half2float(__ldg(base + off[i])) : 0.f;
+            for (int i = 0; i < 4; ++i) d[i] += live[i] ? __ldg(base + off[i]) : 0.f;
+          }
+        } else {
+          if (vec) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + off[0]));
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] += live[i] ? __half2float(__ldg(base + off[i])) : 0.f;
+          }
         }
       }
 #pragma unroll
@@ -858,16 +869,22 @@ int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float t
   return MAUV_OK;
 }
 
-int mauv_wgrad_finalize_group(const void* dw_partial, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
+int mauv_wgrad_finalize_group(const void* dw_partial, int partial_f32, int G, int splits, int cout, int cin, int kh, int kw, int k_pad,
                               float inv_alpha, const float* scale, const float* rho, const float* eps, uint64_t seed,
                               uint32_t layer_id, uint32_t sample0, int stale_eps, float* grad_mu, float* grad_rho,
                               void* stream) {
   MAUV_CHECK_ARG(dw_partial && scale && rho && grad_mu && grad_rho && G >= 1 && splits >= 1, "mauv_wgrad_finalize_group: bad argument");
   const long long n = static_cast<long long>(cout) * cin * kh * kw;
   MAUV_CHECK_ARG(n < (1LL << 31), "mauv_wgrad_finalize_group: tensor too large");
-  wgrad_finalize_group_kernel<<<static_cast<unsigned>(ceil_div_i64(ceil_div_i64(n, 4), 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
-      sample0, stale_eps, grad_mu, grad_rho);
+  const unsigned grid = static_cast<unsigned>(ceil_div_i64(ceil_div_i64(n, 4), 32));
+  if (partial_f32)
+    wgrad_finalize_group_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
+        sample0, stale_eps, grad_mu, grad_rho);
+  else
+    wgrad_finalize_group_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
+        sample0, stale_eps, grad_mu, grad_rho);
   MAUV_LAUNCH_CHECK("wgrad_finalize_group_kernel");
   return MAUV_OK;
 }

@@ -69,14 +69,17 @@ SIGNATURES = {
     "mauv_subsample_f16": (i32, [vp, i64, i32, i32, i32, i32, vp, vp]),
     "mauv_conv3x3_c64_tiles": (i32, [i32, i32, i32]),
     "mauv_conv3x3_c64_f16": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "mauv_gemm_wmod_f16": (i32, [vp, vp, i32, vp, i32, i64, i32, i32, vp]),
+    "mauv_gemm_wmod_f16": (i32, [vp, vp, i32, vp, i32, i32, i64, i32, i32, vp]),
     "mauv_wgrad_f16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    "mauv_wgrad_finalize_group": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, u64, u32, u32, i32, vp, vp, vp]),
+    "mauv_wgrad_finalize_group": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, u64, u32, u32, i32, vp, vp, vp]),
     "mauv_sampled_linear_bwd_group_f32": (i32, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32,
                                                 i32, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp, vp]),
     "mauv_tanh_bwd_f32": (i32, [vp, vp, i64, vp, vp]),
     "mauv_softmax_gate_bwd_f32": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp]),
     "mauv_ce_mean_fwd_bwd_f32": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "mauv_adam_state_bytes": (i32, []),
+    "mauv_adam_step_f32": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, vp]),
+    "mauv_membench_fill": (i32, [vp, i64, u32, i32, vp]),
     "mauv_kl_chunk_elems": (i32, []),
     "mauv_kl_ws_bytes": (i64, []),
     "mauv_kl_fwd_bwd": (i32, [vp, vp, i32, i64, f32, f32, f32, vp, vp, vp]),

@@ -61,6 +61,8 @@ class MCPredictor:
         self.S = int(num_mc_samples)
         self.eps_entropy = eps_entropy
         self.device = self.engine.device
+        self._staging = None
+        self._slots = None
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.world = torch.distributed.get_world_size() if self.dist else 1
         self.rank = torch.distributed.get_rank() if self.dist else 0
@@ -87,6 +89,27 @@ class MCPredictor:
         C = local.shape[-1] if local is not None else self._num_classes()
         return gather_sample_blocks(local, self.S, inputs[0].shape[0], C, self.world, self.device)
 
+    def staging_stream(self) -> torch.cuda.Stream:
+        if self._staging is None:
+            self._staging = torch.cuda.Stream(self.device)
+        return self._staging
+
+    def _staging_slot(self, host_inputs) -> dict:
+        """Two persistent sets of device input buffers (double buffering), re-created only when the batch geometry changes."""
+        key = tuple((tuple(x.shape), x.dtype) for x in host_inputs)
+        if self._slots is None or self._slots[0] != key:
+            bufs = []
+            for _ in range(2):
+                one = []
+                for x in host_inputs:
+                    rows = x.shape[0] if self.world == 1 else batch_slice(x.shape[0], self.world, 0)[2] * self.world
+                    one.append(torch.empty((rows, *x.shape[1:]), dtype=x.dtype, device=self.device))
+                bufs.append({"bufs": one, "done": None})
+            self._slots = (key, bufs, 0)
+        key, bufs, nxt = self._slots
+        self._slots = (key, bufs, nxt ^ 1)
+        return bufs[nxt]
+
     def _want_graph(self, B: int, S_local: int) -> bool:
         if self.use_graph == "auto":
             G = min(self.engine.max_group, S_local)
@@ -101,7 +124,9 @@ class MCPredictor:
         seed = current_seed() if seed is None else seed
         # the graph is recorded for sample ids lo .. hi-1 PLUS a device-resident base word (ops.sample_base): the batch's
         # sample0 is written into that word before every replay, so one graph serves every batch with fresh draws
-        key = (tuple(tuple(x.shape) for x in inputs), lo, hi, seed, self.engine.precision)
+        # (the first parameter's address is part of the key: FusedAdam / load_state_dict may re-home the weights)
+        key = (tuple(tuple(x.shape) for x in inputs), lo, hi, seed, self.engine.precision,
+               next(self.engine.model.parameters()).data_ptr())
         entry = self._graphs.get(key)
         if entry is None:
             static_in = [torch.empty(x.shape, dtype=torch.float32, device=self.device) for x in inputs]
@@ -140,8 +165,10 @@ class MCPredictor:
     def predict_batch(self, host_inputs: Sequence[torch.Tensor], eps: Optional[dict] = None,
                       seed: Optional[int] = None, sample0: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Host tensors in, host results out: (class [B] int64, predictive unc. [B], aleatoric [B], MI [B])."""
-        dev_in = [x.to(self.device, non_blocking=True) for x in host_inputs]
-        o = self.predict_device(dev_in, eps, seed, sample0)
+        st = stage_batch(self, host_inputs)                                   # 1/N slice per rank + NVLink all-gather
+        torch.cuda.current_stream(self.device).wait_event(st.event)
+        o = self.predict_device(st.tensors, eps, seed, sample0)
+        st.release(self.device)
         return _unpack_results(_pack_results(o).cpu())                       # one [B, 5] D2H
 
 
@@ -155,12 +182,79 @@ def _unpack_results(host: torch.Tensor) -> Dict[str, torch.Tensor]:
             "aleatoric_uncertainty": host[:, 2], "pred_entropy": host[:, 3], "mutual_info": host[:, 4]}
 
 
+def batch_slice(B: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Row range [lo, hi) of a batch that `rank` uploads, and the common (padded) chunk length of the gather."""
+    chunk = (B + world - 1) // world
+    lo = min(rank * chunk, B)
+    return lo, min(lo + chunk, B), chunk
+
+
+class StagedBatch:
+    """Device-resident inputs of one batch, the event that marks them complete on the staging stream, and the staging slot
+    they occupy (released - for the staging stream - by `done`, recorded on the compute stream after the batch's forward)."""
+
+    def __init__(self, tensors, event, h2d_bytes, slot=None):
+        self.tensors, self.event, self.h2d_bytes, self.slot = tensors, event, h2d_bytes, slot
+
+    def release(self, device) -> None:
+        if self.slot is not None:
+            self.slot["done"] = torch.cuda.Event()
+            self.slot["done"].record(torch.cuda.current_stream(device))
+
+
+def stage_batch(predictor: "MCPredictor", host_inputs: Sequence[torch.Tensor]) -> StagedBatch:
+    """Input staging (the reference's loaders hand every process the whole pinned batch,
+    data/loaders.py:48-51): enqueue, on the predictor's staging stream, the host->device copy of one batch into one of two
+    persistent device slots (no allocator traffic, no implicit synchronisation). With N ranks every rank uploads only ITS
+    1/N slice of the rows and the slices are all-gathered over NVLink, so the PCIe / host-memory traffic per batch is B rows
+    in total instead of N x B. Nothing here waits on the host: the caller overlaps it with the previous batch's compute and
+    makes the compute stream wait on `.event`."""
+    dev, world, rank = predictor.device, predictor.world, predictor.rank
+    side = predictor.staging_stream()
+    slot = predictor._staging_slot(host_inputs)
+    out, nbytes = [], 0
+    with torch.cuda.stream(side):
+        if slot["done"] is not None:
+            side.wait_event(slot["done"])          # the batch that used this slot two calls ago has been consumed
+        for x, full in zip(host_inputs, slot["bufs"]):
+            if x.is_cuda:
+                out.append(x)
+                continue
+            B = x.shape[0]
+            if world == 1:
+                full.copy_(x, non_blocking=True)
+                nbytes += x.numel() * x.element_size()
+                out.append(full)
+            else:
+                lo, hi, chunk = batch_slice(B, world, rank)
+                mine = full[rank * chunk:(rank + 1) * chunk]
+                if hi > lo:
+                    mine[: hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    nbytes += (hi - lo) * x[0].numel() * x.element_size()
+                torch.distributed.all_gather_into_tensor(full, mine)        # in place: rank r's chunk is rows [r*chunk, ..)
+                out.append(full[:B])
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return StagedBatch(out, ev, nbytes, slot)
+
+
 def predict_stream(predictor: "MCPredictor", host_batches):
-    """predict_batch over an iterable of host batches, one result dict (host tensors) per batch. The H2D copy of a
-    cfg2 batch (470 MB, pinned) takes 8.5 ms against 680 ms of compute, so it is simply issued in stream order; a
-    copy-stream double-buffered variant measured SLOWER on this platform (770 vs 690 ms/step) and was dropped."""
-    for hb in host_batches:
-        yield predictor.predict_batch(hb)
+    """predict_batch over an iterable of host batches, one result dict (host tensors) per batch. The staging of batch i+1
+    (H2D of this rank's slice + NVLink all-gather, `stage_batch`) is enqueued on a side stream BEFORE batch i is computed,
+    so it overlaps the compute; the results of batch i are read back with one [B, 5] D2H."""
+    it = iter(host_batches)
+    try:
+        nxt = stage_batch(predictor, next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        cur = nxt
+        hb = next(it, None)
+        nxt = stage_batch(predictor, hb) if hb is not None else None
+        torch.cuda.current_stream(predictor.device).wait_event(cur.event)
+        o = predictor.predict_device(cur.tensors)
+        cur.release(predictor.device)
+        yield _unpack_results(_pack_results(o).cpu())
 
 
 def multimodal_predict_and_save(multimodal_model: nn.Module, dataloader, device: torch.device, csv_path: str,

@@ -178,14 +178,14 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] =
     return out, (stats_out if stats else None)
 
 
-def gemm_wmod_f16(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """a [G, M, K], w [Gw, N, K] with G % Gw == 0 -> y [G, M, N] = a[g] @ w[g % Gw]^T"""
+def gemm_wmod_f16(a: torch.Tensor, w: torch.Tensor, out_f32: bool = False) -> torch.Tensor:
+    """a [G, M, K], w [Gw, N, K] with G % Gw == 0 -> y [G, M, N] = a[g] @ w[g % Gw]^T (fp16, or the fp32 accumulator)"""
     lib = _lib.require_device()
     G, M, K = a.shape
     Gw, N, _ = w.shape
     assert w.shape[2] == K and G % Gw == 0
-    out = torch.empty((G, M, N), dtype=F16, device=a.device)
-    _run("mauv_gemm_wmod_f16", lib.mauv_gemm_wmod_f16, _ptr(a, F16), _ptr(w, F16), Gw, _ptr(out), G, M, N, K, _stream(),
+    out = torch.empty((G, M, N), dtype=F32 if out_f32 else F16, device=a.device)
+    _run("mauv_gemm_wmod_f16", lib.mauv_gemm_wmod_f16, _ptr(a, F16), _ptr(w, F16), Gw, _ptr(out), int(out_f32), G, M, N, K, _stream(),
          tag=f"G{G} M{M} N{N} K{K} wmod{Gw}" if _prof is not None else None)
     return out
 
@@ -667,11 +667,11 @@ def avgpool_bwd_f16(gs: GradScratch, dfeat: torch.Tensor, HW: int):
 
 
 def wgrad_f16(dy: torch.Tensor, x: torch.Tensor, G: int, splits: int, kh: int, kw: int, stride: int, pad: int) -> torch.Tensor:
-    """dy [G*B, Ho, Wo, Cout], x [G*B, H, W, Cin] NHWC fp16 -> dw partials [G*splits, Cout, kh*kw*Cin] fp16"""
+    """dy [G*B, Ho, Wo, Cout], x [G*B, H, W, Cin] NHWC fp16 -> dw partials [G*splits, Cout, kh*kw*Cin] FP32"""
     lib = _lib.require_device()
     NB, H, W, Cin = x.shape
     Cout = dy.shape[-1]
-    dw = torch.empty((G * splits, Cout, kh * kw * Cin), dtype=F16, device=x.device)
+    dw = torch.empty((G * splits, Cout, kh * kw * Cin), dtype=F32, device=x.device)
     _run("mauv_wgrad_f16", lib.mauv_wgrad_f16, _ptr(dy, F16), _ptr(x, F16), _ptr(dw), G, splits, NB // G, H, W, Cin, Cout,
          kh, kw, stride, pad, _stream(),
          tag=f"G{G}x{splits} Cout{Cout} K{kh * kw * Cin} px{dy.numel() // (G * splits * Cout)}" if _prof is not None else None)
@@ -686,7 +686,10 @@ def wgrad_finalize_group(dw_partial, G, mu_shape, inv_alpha, scale_addr, rho, gr
         cin, kh, kw = mu_shape[1], 1, 1
     else:
         _, cin, kh, kw = mu_shape
-    _run("mauv_wgrad_finalize_group", lib.mauv_wgrad_finalize_group, _ptr(dw_partial, F16), G, gsplits // G, cout, cin, kh, kw,
+    if dw_partial.dtype not in (F16, F32):
+        raise _lib.MauvError("wgrad_finalize_group: partial sums must be fp16 or fp32")
+    _run("mauv_wgrad_finalize_group", lib.mauv_wgrad_finalize_group, _ptr(dw_partial), int(dw_partial.dtype == F32), G, gsplits // G,
+         cout, cin, kh, kw,
          k_pad, inv_alpha, scale_addr, _ptr(rho, F32), _ptr(eps, F32), seed, layer_id, sample0, int(stale), _ptr(grad_mu, F32),
          _ptr(grad_rho, F32), _stream(),
          tag=f"G{G} sp{gsplits // G} cout{cout} cin{cin} k{kh}" if _prof is not None else None)
@@ -740,6 +743,20 @@ def ce_mean_fwd_bwd_f32(logits: torch.Tensor, labels: torch.Tensor):
     _run("mauv_ce_mean_fwd_bwd_f32", lib.mauv_ce_mean_fwd_bwd_f32, _ptr(logits, F32), _ptr(labels, I64), S, B, Cc,
          _ptr(mean_logit), _ptr(dlogits), _ptr(loss), _stream())
     return loss, mean_logit, dlogits
+
+
+# ------------------------------------------------------------------ optimizer
+KERNELS_PER_CALL["mauv_adam_step_f32"] = 3
+
+
+def adam_step_f32(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
+                  eps: float, weight_decay: float, state: torch.Tensor) -> None:
+    """Guarded Adam over flat fp32 buffers (see include/mauv_b200.h): p, m, v updated in place iff every g is finite."""
+    lib = _lib.require_device()
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n and state.numel() * 4 >= lib.mauv_adam_state_bytes()
+    _run("mauv_adam_step_f32", lib.mauv_adam_step_f32, _ptr(p, F32), _ptr(g, F32), _ptr(m, F32), _ptr(v, F32), n, lr, beta1, beta2,
+         eps, weight_decay, state.data_ptr(), _stream())
 
 
 # ------------------------------------------------------------------ statistics

@@ -91,8 +91,8 @@ def train_multimodal_model(multimodal_model: nn.Module, dataloader, criterion: n
                         logging.warning(f"Skipping batch {i} due to NaN/Inf loss: {loss}")
                         engine.zero_grad()       # the engine has already accumulated this batch's gradients: drop them
                         continue
-                    if bool(engine.grads_finite()):
-                        optimizer.step()
+                    # NaN/Inf guard + Adam in one device pass (mauv.optim.FusedAdam; reference :141-145)
+                    if bool(engine.optimizer_step(optimizer)):
                         engine.zero_grad()
                     else:
                         logging.warning("Skipping optimizer step due to NaN/Inf gradients")

@@ -59,9 +59,7 @@ def train_unimodal_model(model: nn.Module, dataloader, criterion: nn.Module, opt
                     # The reference's unimodal loop has no NaN/Inf guard (train/unimodal.py:140-142). The engine's
                     # gradients travel in scaled fp16, so one overflow would poison the Adam moments for good: skip the
                     # update for such a batch (what train/multimodal.py:141-145 does) instead of applying it.
-                    if bool(engine.grads_finite()):
-                        optimizer.step()
-                    else:
+                    if not bool(engine.optimizer_step(optimizer)):
                         logging.warning("Skipping optimizer step due to NaN/Inf gradients")
                 else:
                     optimizer.zero_grad()

@@ -83,9 +83,14 @@ class TrainEngine(MCEngine):
 
     def __init__(self, model: nn.Module, max_group: int = 32):
         super().__init__(model, max_group=max_group, precision="fp16")
+        frozen = [n for n, p in self.model.named_parameters() if not p.requires_grad]
+        if frozen:      # raised here, before any epoch loop starts (train_engine_for then selects the autograd layer path)
+            raise _lib.MauvError(f"TrainEngine computes gradients for every parameter; {len(frozen)} are frozen "
+                                 f"(requires_grad=False), e.g. {frozen[0]}")
         self.direct_wgrad = os.environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
         self._update_running = True
         self._flat: Optional[FlatGrads] = None
+        self._fused = {}        # id(optimizer) -> FusedAdam | None (optimizer_step)
         # activations kept per (triplet, MC sample) for the backward walk, bytes at 256x256 (raw conv outputs + activations of
         # 53 convs per trunk in fp16, plus the transient gradient tensors); scaled with the input resolution
         self.tape_bytes_256 = (230 if self.kind == "multimodal" else 80) * 2 ** 20
@@ -225,7 +230,7 @@ class TrainEngine(MCEngine):
         splits = _group_splits(M, G, Cout, Kp)
         b_t = ops.transpose_chunks_f16(tr.a0, splits)                                         # [splits, Kp, Mc] (all samples)
         a_t = ops.transpose_chunks_f16(dy.view(G * M, Cout), G * splits)                      # [G*splits, Cout, Mc]
-        dw = ops.gemm_wmod_f16(a_t, b_t)                                                      # batch (g, sp) uses b_t[sp]
+        dw = ops.gemm_wmod_f16(a_t, b_t, out_f32=True)                                        # batch (g, sp) uses b_t[sp]; fp32 sums
         ops.wgrad_finalize_group(dw.view(G * splits, Cout, Kp), G, tuple(layer.mu_kernel.shape), 1.0, s_dy,
                                  layer.rho_kernel.detach(), layer.mu_kernel.grad, layer.rho_kernel.grad,
                                  eps=self._eps_w(eps, c.name, s0, G), seed=seed, layer_id=c.layer_id, sample0=s0, stale=stale)
@@ -332,6 +337,26 @@ class TrainEngine(MCEngine):
         if self._flat is not None:
             return self._flat.finite()
         return torch.stack([torch.isfinite(p.grad).all() for p in self.model.parameters() if p.grad is not None]).all()
+
+    def optimizer_step(self, optimizer) -> torch.Tensor:
+        """Guarded optimizer step (reference train/multimodal.py:141-145): the update is applied iff every gradient is
+        finite. A plain torch.optim.Adam over this model's parameters is adopted by mauv.optim.FusedAdam (guard + update
+        in one pass over flat buffers, decided on the device); any other optimizer keeps its own step() behind the
+        one-pass device guard. -> 0-d device tensor, non-zero iff the step was applied."""
+        from .optim import FusedAdam
+        if self._flat is None:
+            self.flatten_grads()
+        key = id(optimizer)
+        if key not in self._fused:
+            self._fused[key] = FusedAdam.adopt(optimizer, self._flat)
+            self._kl_plan = None        # adoption moved the parameters into a flat buffer: drop cached device pointers
+        fa = self._fused[key]
+        if fa is not None:
+            return fa.step()
+        ok = self.grads_finite()
+        if bool(ok):
+            optimizer.step()
+        return ok
 
     def _ensure_grads(self):
         if self._flat is not None:

@@ -26,6 +26,17 @@ pred = MCPredictor(model, S)
 out = pred.predict_device(xs, seed=99, sample0=0)
 single = MCEngine(model).forward_mc(xs, S, seed=99, sample0=0)          # all samples on this rank
 ok = torch.equal(out["logits"], single)
+# end-to-end staging: every rank is handed the whole pinned host batch, uploads only its 1/N slice of the rows and the slices
+# are all-gathered over NVLink (mauv.inference.predictors.stage_batch) - same results as device-resident inputs
+from mauv.inference.predictors import predict_stream
+host = [t.pin_memory() for t in (img, bathy, sss)]
+c0 = pred.engine._sample_cursor
+res = list(predict_stream(pred, [host, host]))
+ref0 = pred.predict_device(xs, sample0=c0)
+ref1 = pred.predict_device(xs, sample0=c0 + S)
+ok = ok and torch.equal(res[0]["predicted_class"], ref0["argmax_prob"].cpu()) and \
+    torch.equal(res[0]["aleatoric_uncertainty"], ref0["aleatoric"].cpu()) and \
+    torch.equal(res[1]["aleatoric_uncertainty"], ref1["aleatoric"].cpu())
 gathered = [torch.empty_like(out["mean_prob"]) for _ in range(world)]
 torch.distributed.all_gather(gathered, out["mean_prob"])
 same = all(torch.equal(g, gathered[0]) for g in gathered)

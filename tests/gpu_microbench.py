@@ -5,7 +5,7 @@
   python tests/gpu_microbench.py mcreduce S B C [iters]
   python tests/gpu_microbench.py wgrad G B H W Cin Cout k stride pad [splits]
   python tests/gpu_microbench.py bnbwd G M C
-  python tests/gpu_microbench.py kl | sample
+  python tests/gpu_microbench.py kl | sample | hbm | hbmwrite
   python tests/gpu_microbench.py layers        (the ResNet-50 trunk shapes at B=256)
 """
 import sys
@@ -167,6 +167,32 @@ def hbm():
     print(f"copy (2 GiB -> 2 GiB): {ms:.3f} ms  {2 * n / ms / 1e6:.1f} GB/s", flush=True)
 
 
+def hbmwrite():
+    """VERDICT r1 task 2(iii): is ~3.9 TB/s the write-only ceiling of HBM on this GPU? 4 GiB written five ways."""
+    import ctypes
+    from mauv import _lib
+    lib = _lib.require_device()
+    n = 1 << 32
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMemsetAsync.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for name, fn in (("cudaMemsetAsync", lambda: rt.cudaMemsetAsync(a.data_ptr(), 0, n, st)),
+                     ("torch fill_", lambda: a.fill_(1)),
+                     ("st.global.v4", lambda: _lib.check(lib.mauv_membench_fill(a.data_ptr(), n, 7, 0, st))),
+                     ("st.global.cs.v4", lambda: _lib.check(lib.mauv_membench_fill(a.data_ptr(), n, 7, 1, st))),
+                     ("cp.async.bulk shared->global (TMA store engine)", lambda: _lib.check(lib.mauv_membench_fill(a.data_ptr(), n, 7, 2, st)))):
+        ms = timeit(fn, 10, 3)
+        rows.append((name, ms, n / ms / 1e6))
+        print(f"write-only {name}: {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s", flush=True)
+    b = torch.empty(n // 2, dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: b.copy_(a[: n // 2]), 10, 3)
+    print(f"copy 2 GiB -> 2 GiB: {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s (read + write)", flush=True)
+    ms = timeit(lambda: a.view(torch.float32).sum(), 10, 3)
+    print(f"read-only (sum 4 GiB): {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s", flush=True)
+
+
 def layers():
     G, B = 4, 256
     for (M, N, K) in [(B * 4096, 256, 64), (B * 4096, 64, 256), (B * 4096, 64, 64), (B * 1024, 512, 128),
@@ -182,4 +208,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)

@@ -5,9 +5,11 @@ CPU and injected it into oracle/bnn_oracle.py). Nothing here reads /root/referen
 Stated tolerances (max abs error of the logits, relative to max |logit| of the oracle = "scale"):
 
   config                                   precision "x3" (fp32-class)      precision "fp16" (benchmarked path)
-  cfg1  multimodal B=8   S=10 256x256      1e-3 * scale  (north_star rtol)  TOL_FP16_MM  * scale
-  cfg2  multimodal B=256 S=2/30 256x256    1e-3 * scale                     TOL_FP16_MM  * scale
-  cfg4  unimodal   B=8   S=4  256x256      1e-3 * scale                     TOL_FP16_UNI * scale
+  cfg1  multimodal B=8   S=10 256x256      1e-3 * scale  (north_star rtol)  1.5e-3 * scale   (TOL_FP16_MM)
+  cfg2  multimodal B=256 S=2/30 256x256    1e-3 * scale                     1.5e-3 * scale
+  cfg4  unimodal   B=8   S=4  256x256      1e-3 * scale                     0.15   * scale   (TOL_FP16_UNI)
+
+Measured on B200 (round 2): x3 6e-7 / 8e-7 / 9e-5 of scale; fp16 4.7e-4 / 6.4e-4 / 5.7e-2 of scale.
 
 The fp16 figures are what 10-bit-mantissa operands (fp16 or TF32 alike) cost through 174 / 53 stacked layers with
 train-mode BatchNorm - fixed numbers, not calibrated inside the test. The multimodal logits pass
@@ -29,8 +31,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 TOL_X3 = 1e-3          # north_star: logits within rtol 1e-3 of the fp32 reference
-TOL_FP16_MM = 1.5e-2   # multimodal logits, fp16 operands (measured 4e-3 .. 6e-3 of scale at cfg1 / cfg2)
-TOL_FP16_UNI = 0.35    # unimodal logits, fp16 operands (measured ~0.15 of scale: the ill-conditioned case of DESIGN 4.3)
+TOL_FP16_MM = 1.5e-3   # multimodal logits, fp16 operands (measured on B200: 4.7e-4 of scale at cfg1, 6.4e-4 at cfg2 S=30)
+TOL_FP16_UNI = 0.15    # unimodal logits, fp16 operands (measured 5.7e-2 of scale: the ill-conditioned case of DESIGN 4.3)
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,246 @@
+"""GPU tests added in round 2 (pytest -m gpu): fused Adam + finite guard (8f-1), CE label validation, checkpoint
+load-and-predict (8f-3), train_unimodal_model against the reference's own CSV row, full-depth gradients against the fp32
+oracle, and the drop-in training loop under DistributedDataParallel (two ranks, gloo, one GPU)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+GOLD = HERE / "golden" / "reference_small.pt"
+
+
+@pytest.fixture(scope="module")
+def bu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gpu_bringup
+    return gpu_bringup
+
+
+def _toy():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3), torch.nn.Flatten(), torch.nn.Linear(5 * 36, 37), torch.nn.Linear(37, 3))
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam_1e6_and_skips_nonfinite_steps_on_device(bu, wd):
+    """mauv_adam_step_f32 through mauv.optim.FusedAdam vs torch.optim.Adam on identical gradients: parameters within 1e-6
+    after every step; a step whose gradients contain a NaN / Inf is skipped on the device (parameters, moments and the
+    step count untouched - the reference's guard, train/multimodal.py:141-145) and the next one continues at t + 1."""
+    from mauv.flatgrad import FlatGrads
+    from mauv.optim import FusedAdam
+    ours, ref = _toy().cuda(), _toy().cuda()
+    opt_o = torch.optim.Adam(ours.parameters(), lr=3e-3, weight_decay=wd)
+    opt_r = torch.optim.Adam(ref.parameters(), lr=3e-3, weight_decay=wd)
+    flat = FlatGrads(ours.parameters())
+    fa = FusedAdam.adopt(opt_o, flat)
+    assert fa is not None
+    assert all(p.data_ptr() >= fa.p.data_ptr() for p in ours.parameters())            # parameters live in the flat buffer
+    g = torch.Generator(device="cuda").manual_seed(1)
+    applied = []
+    for it in range(6):
+        grads = [torch.randn(p.shape, device="cuda", generator=g) * (10.0 ** (it - 3)) for p in ref.parameters()]
+        poison = it in (2, 4)
+        for p, q, gr in zip(ours.parameters(), ref.parameters(), grads):
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        if poison:
+            list(ours.parameters())[1 + it % 2].grad.view(-1)[0] = float("nan") if it == 2 else float("inf")
+        before = [p.detach().clone() for p in ours.parameters()]
+        a = bool(fa.step())
+        applied.append(a)
+        if poison:
+            assert not a and all(torch.equal(p, b) for p, b in zip(ours.parameters(), before))
+            continue
+        opt_r.step()
+        for p, q in zip(ours.parameters(), ref.parameters()):
+            assert (p - q).abs().max().item() <= 1e-6 * max(1.0, q.abs().max().item()), it
+    assert applied == [True, True, False, True, False, True]
+    assert fa.sync_state() == 4 and int(opt_r.state[next(iter(ref.parameters()))]["step"]) == 4
+    sd = opt_o.state_dict()                                    # the torch handle still describes the optimizer
+    assert len(sd["state"]) == len(list(ours.parameters())) and sd["param_groups"][0]["lr"] == 3e-3
+    # lr schedulers keep working on the adopted optimizer: the fused step reads param_groups[0]["lr"] every call
+    sched = torch.optim.lr_scheduler.StepLR(opt_o, step_size=1, gamma=0.5)
+    sched.step()
+    sched_r = torch.optim.lr_scheduler.StepLR(opt_r, step_size=1, gamma=0.5)
+    sched_r.step()
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        gr = torch.randn(p.shape, device="cuda", generator=g)
+        p.grad.copy_(gr)
+        q.grad = gr.clone()
+    assert bool(fa.step())
+    opt_r.step()
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        assert (p - q).abs().max().item() <= 1e-6 * max(1.0, q.abs().max().item())
+
+
+def test_fused_adam_adopts_an_optimizer_that_already_stepped_and_refuses_what_it_cannot_express(bu):
+    from mauv.flatgrad import FlatGrads
+    from mauv.optim import FusedAdam
+    ours, ref = _toy().cuda(), _toy().cuda()
+    opt_o, opt_r = torch.optim.Adam(ours.parameters(), lr=1e-3), torch.optim.Adam(ref.parameters(), lr=1e-3)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(2):                                          # two ordinary torch steps first
+        for p, q in zip(ours.parameters(), ref.parameters()):
+            gr = torch.randn(p.shape, device="cuda", generator=g)
+            p.grad, q.grad = gr.clone(), gr.clone()
+        opt_o.step()
+        opt_r.step()
+    fa = FusedAdam.adopt(opt_o, FlatGrads(ours.parameters()))
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        gr = torch.randn(p.shape, device="cuda", generator=g)
+        p.grad.copy_(gr)
+        q.grad = gr.clone()
+    assert bool(fa.step()) and fa.sync_state() == 3
+    opt_r.step()
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        assert (p - q).abs().max().item() <= 1e-6 * max(1.0, q.abs().max().item())
+    m = _toy().cuda()
+    assert FusedAdam.adopt(torch.optim.SGD(m.parameters(), lr=0.1), FlatGrads(m.parameters())) is None
+    assert FusedAdam.adopt(torch.optim.Adam(m.parameters(), amsgrad=True), FlatGrads(m.parameters())) is None
+    assert FusedAdam.adopt(torch.optim.Adam(list(m.parameters())[:2]), FlatGrads(m.parameters())) is None
+
+
+def test_cross_entropy_of_mean_logits_validates_labels_like_torch(bu):
+    """mauv_ce_mean_fwd_bwd_f32: ignore_index = -100 rows are skipped exactly like F.cross_entropy; any other label
+    outside [0, C) gives a NaN loss (torch: device assert) and a zero gradient for that row - never an out-of-bounds read."""
+    from mauv import ops
+    torch.manual_seed(0)
+    S, B, C = 3, 9, 7
+    logits = torch.randn(S, B, C, device="cuda")
+    labels = torch.randint(0, C, (B,), device="cuda")
+    labels[2] = labels[5] = -100
+    loss, mean_logit, dl = ops.ce_mean_fwd_bwd_f32(logits, labels)
+    lg = logits.clone().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(lg.mean(0), labels)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-6
+    assert (dl - lg.grad).abs().max().item() < 1e-7 and float(dl[:, 2].abs().max()) == 0.0
+    bad = labels.clone()
+    bad[0] = C + 3
+    loss_b, _, dl_b = ops.ce_mean_fwd_bwd_f32(logits, bad)
+    assert torch.isnan(loss_b) and torch.isfinite(dl_b).all() and float(dl_b[:, 0].abs().max()) == 0.0
+    loss_n, _, dl_n = ops.ce_mean_fwd_bwd_f32(logits, torch.full((B,), -100, device="cuda"))
+    assert torch.isnan(loss_n) and float(dl_n.abs().max()) == 0.0           # torch: mean over zero targets = NaN
+
+
+def test_reference_checkpoint_loads_on_gpu_and_reproduces_oracle_predictions(bu, tmp_path):
+    """8f-3: a checkpoint in the PUBLISHED layout (Examples/Example_Inference_model.py:82-112: DataParallel `module.` prefix,
+    trunks one `.model.` level deeper) written from the oracle's weights -> mauv.models.model_utils.load_reference_weights
+    (pathlib.Path) into a freshly built product model on the GPU -> MCPredictor reproduces the oracle's logits and classes
+    for the same inputs and injected eps. (The shipped pytorch_model.bin itself is unreachable offline.)"""
+    import logging
+    import bnn_oracle as O
+    from mauv.inference.predictors import MCPredictor
+    from mauv.models.model_utils import define_models, load_reference_weights
+    o_model = O.define_models(7, seed=77, unimodal=False)["multimodal_model"]
+    published = {}
+    for k, v in o_model.state_dict().items():
+        for br in ("image_model_feat", "bathy_model_feat", "sss_model_feat"):
+            if k.startswith(br + "."):
+                k = br + ".model." + k[len(br) + 1:]
+                break
+        published["module." + k] = v.clone()
+    ck = tmp_path / "pytorch_model.bin"
+    torch.save(published, ck)
+    logging.disable(logging.WARNING)
+    torch.manual_seed(5)                                               # different initial weights: everything must be loaded
+    model = define_models(torch.device("cpu"), 7, dict(O.DEFAULT_PRIOR))["multimodal_model"]
+    logging.disable(logging.NOTSET)
+    missing, unexpected = load_reference_weights(model, Path(ck))
+    assert missing == [] and unexpected == []
+    model = model.cuda().train()
+    B, S = 4, 3
+    img, bathy, sss, _ = O.synthetic_batch(B, seed=9, size=64)
+    eps = O.draw_eps(o_model, S, seed=13)
+    ref = O.mc_logits(o_model, (img, bathy, sss), S, eps)
+    out = MCPredictor(model, S).predict_device([t.cuda() for t in (img, bathy, sss)], eps=eps)
+    scale = ref.abs().max().item()
+    assert (out["logits"].cpu() - ref).abs().max().item() <= 1.5e-2 * scale
+    st = O.predictor_stats(ref)
+    top2 = torch.softmax(ref, -1).mean(0).topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * 1.5e-2 * scale
+    assert torch.equal(out["argmax_prob"].cpu()[decided], st["predicted_class"][decided])
+
+
+class _Loader(list):
+    batch_size = None
+
+
+class _W:
+    def add_scalar(self, *a, **k):
+        pass
+
+
+def test_train_unimodal_model_reproduces_reference_csv_and_adam_update(bu, tmp_path):
+    """mauv.train.unimodal.train_unimodal_model (S-batched engine + fused Adam) for one step against the CSV row, the return
+    value and the Adam-updated head parameters the REFERENCE's train_unimodal_model (train/unimodal.py:21-175) produced for
+    the same weights, inputs and eps (tests/golden, oracle/make_golden.py section 6). Tolerances: loss 3e-3 abs (unimodal
+    logits carry the fp16 trunk noise of DESIGN 4.3), head parameters after Adam 2e-5 (|step| = lr = 1e-4: pins the sign of
+    every head gradient), accuracy exact."""
+    gold = torch.load(GOLD, weights_only=False)
+    if "train_uni_csv_row" not in gold:
+        pytest.skip("golden fixture predates the unimodal training record")
+    import bnn_oracle as O
+    import mauv.bayesian as MB
+    import mauv.engine as E
+    from mauv.bayesian import dnn_to_bnn
+    from mauv.models.base_models import ResNet50Custom
+    from mauv.train.unimodal import train_unimodal_model
+    torch.manual_seed(gold["seed_w"])
+    o = O.define_models(gold["C"], seed=None, unimodal=True)["image_model"]
+    torch.manual_seed(0)
+    model = ResNet50Custom(3, gold["C"])
+    dnn_to_bnn(model, O.DEFAULT_PRIOR)
+    model.load_state_dict(o.state_dict(), strict=True)
+    model = model.cuda().train()
+    for k, v in gold["train_uni_before"].items():
+        assert torch.equal(model.state_dict()[k].flatten()[:8].cpu(), v), k
+    img, bathy, sss, labels = O.synthetic_batch(gold["B"], seed=gold["seed_x"], size=gold["size"])
+    loader = _Loader([{"main_image": img, "label": labels, "bathy_image": bathy, "sss_image": sss}])
+    loader.batch_size = gold["B"]
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    E.DEBUG_EPS = O.draw_eps(o, gold["S"], gold["seed_eps"] + 1)
+    MB.set_reference_stale_eps(True)
+    try:
+        csv_path = tmp_path / "logs" / "utrain.csv"
+        csv_path.parent.mkdir()
+        acc, loss = train_unimodal_model(model, loader, torch.nn.CrossEntropyLoss(), opt, epoch=1, total_num_epochs=20,
+                                         num_mc=gold["S"], sum_writer=_W(), device=torch.device("cuda"), model_type="image",
+                                         csv_path=str(csv_path))
+    finally:
+        E.DEBUG_EPS = None
+        MB.set_reference_stale_eps(False)
+    eng = model.__dict__.get("_mauv_train_engine")
+    assert eng is not None and any(v is not None for v in eng._fused.values())      # engine + fused Adam ran
+    import csv as _csv
+    rows = list(_csv.reader(open(csv_path)))
+    assert rows[0] == gold["train_uni_csv_header"]
+    got, ref = rows[1], gold["train_uni_csv_row"]
+    assert got[:2] == ref[:2] and got[4] == ref[4]
+    assert abs(acc - gold["train_uni_return"][0]) < 1e-9
+    assert abs(loss - gold["train_uni_return"][1]) < 3e-3, (loss, gold["train_uni_return"])
+    assert abs(float(got[2]) - float(ref[2])) < 3e-3
+    sd = model.state_dict()
+    for k in ("model.fc.mu_weight", "model.fc.rho_weight", "model.fc.mu_bias"):
+        got_p = sd[k].flatten()[:8].cpu()
+        assert (got_p - gold["train_uni_after"][k]).abs().max() < 2e-5, (k, got_p, gold["train_uni_after"][k])
+        assert (got_p - gold["train_uni_before"][k]).abs().min() > 5e-5
+
+
+def test_train_unimodal_model_two_ranks_ddp_gradients_are_synchronised(bu):
+    """train_unimodal_model under DistributedDataParallel (2 ranks, gloo, both on cuda:0) - after one epoch on
+    different per-rank data both ranks must hold identical parameters (tests/dist_train_loop_check.py)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29731", str(HERE / "dist_train_loop_check.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ranks identical: True" in r.stdout

@@ -299,3 +299,19 @@ def test_drop_in_train_loops_average_engine_gradients_under_ddp_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_batch_slice_partitions_rows_for_the_sliced_upload():
+    """8f-2 staging: every rank uploads rows [lo, hi) and the slices tile the batch exactly; chunk is the padded length the
+    all-gather uses (equal on all ranks)."""
+    from mauv.inference.predictors import batch_slice
+    for B in (1, 7, 8, 255, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            rows, chunks = [], set()
+            for r in range(world):
+                lo, hi, chunk = batch_slice(B, world, r)
+                assert 0 <= lo <= hi <= B and hi - lo <= chunk
+                rows += list(range(lo, hi))
+                chunks.add(chunk)
+                assert lo == min(r * chunk, B)          # gathered position of the slice = r * chunk
+            assert rows == list(range(B)) and len(chunks) == 1 and chunks.pop() * world >= B
