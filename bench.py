@@ -273,7 +273,8 @@ def run_ours(args):
             fc, ft = fam.get(b, (0, 0.0))
             fam[b] = (fc + c, ft + t)
         # all launches of the tcgen05 kernels (gemm_f16_tc_kernel and its padded-stream sibling for layer1's 3x3 conv)
-        tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16")
+        tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16",
+              "mauv_wgrad_f16")     # (inference: the K x K second-moment contractions of the closed-form BN statistics)
         conv_calls = sum(fam.get(k, (0, 0.0))[0] for k in tc)
         conv_ms = sum(fam.get(k, (0, 0.0))[1] for k in tc)
         if args.detail:
@@ -284,12 +285,12 @@ def run_ours(args):
                 base, tag = k.split("|")
                 toks = {x[0]: x[1:] for x in tag.split() if x[0] in "GMNKC" and x[1:].isdigit()}
                 gf = gb = 0.0
-                if "K" in toks:
+                if all(q in toks for q in "GMNK"):
                     g_, m_, n_, k_ = (int(toks[q]) for q in "GMNK")
                     gf = 2.0 * g_ * m_ * n_ * k_ * c / 1e9
                     kin = k_ if "x" not in tag or tag.split()[-1].startswith("1x1") else k_ // 9
                     gb = g_ * m_ * (kin + n_) * 2 * c / 1e9
-                elif "C" in toks:
+                elif all(q in toks for q in "GMC"):
                     g_, m_, c_ = (int(toks[q]) for q in "GMC")
                     nbuf = 2 + int("res1" in tag) + int("dual1" in tag)
                     gb = g_ * m_ * c_ * 2 * nbuf * c / 1e9
@@ -362,6 +363,11 @@ def run_ours(args):
 
 def tc_launch_model(base: str, tag: str):
     """Algorithmic (flops, minimum HBM bytes) of ONE launch of gemm_f16_tc_kernel from its profiling tag."""
+    if base == "mauv_wgrad_f16":            # "G10x32 Cout64 K64 px4096": [Cout x px] x [px x K] per (sample, chunk); reads a once
+        t = tag.split()
+        g, sp = (int(v) for v in t[0][1:].split("x"))
+        cout, k, px = int(t[1][4:]), int(t[2][1:]), int(t[3][2:])
+        return 2.0 * g * sp * cout * k * px, g * sp * px * max(cout, k) * 2 + g * sp * cout * k * 4
     toks = {x[0]: int(x[1:]) for x in tag.split() if x[0] in "GMNK" and x[1:].isdigit()}
     if not all(q in toks for q in "GMNK"):
         return None

@@ -105,9 +105,25 @@ int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long
                      const float* gamma, const float* beta, float eps, float momentum,
                      float* running_mean, float* running_var, long long* num_batches_tracked,
                      float* scale_shift, float* batch_stats, void* ws, void* stream);
-/* out = relu?( y*ss + [residual] + [y2*ss2] ), all [G][M][C] fp16. */
+/* out = relu?( y*ss + [residual] + [y2*ss2] ), all [G][M][C] fp16. colsum_partial (nullable): [G][mauv_bn_act_blocks(G, M, C)][C]
+ * fp32 per-block column sums of the fp16 OUTPUT (first moment for mauv_bn_stats_from_gram). */
+int mauv_bn_act_blocks(int G, long long M, int C);
 int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residual, const void* y2,
-                    const float* scale_shift2, int relu, int G, long long M, int C, void* out, void* stream);
+                    const float* scale_shift2, int relu, int G, long long M, int C, void* out, float* colsum_partial,
+                    void* stream);
+/* Column sums of x [G][M][C] fp16 in the same per-block layout (C: power of two in [8, 2048]). */
+int mauv_colsum_f16(const void* x, int G, long long M, int C, float* colsum_partial, void* stream);
+/* Closed-form BatchNorm(train) statistics of a 1x1 conv y = a W^T (nn.BatchNorm2d after the bottleneck's conv3 / downsample
+ * conv, torchvision resnet.py:154-160) from the moments of its INPUT a [G][M][K]: sum_m y[m][n] = w_n . colsum(a),
+ * sum_m y[m][n]^2 = w_n^T (a^T a) w_n. gram_partial: [G*splits][K][K] fp32 from mauv_wgrad_f16(dy = x = a) (pixel-chunk
+ * partial sums of a^T a); colsum_partial: [G][nblk][K]; w: the sampled fp16 weights [G][N][K] the contraction uses. Outputs
+ * and running-statistics updates exactly as mauv_bn_finalize. Replaces the N x K statistics pass of the recompute scheme
+ * (mauv_gemm_bn_f16 mode 1) by a K x K contraction. K % 8 == 0, K <= 512, G <= 64. */
+long long mauv_bn_stats_from_gram_ws_bytes(int G, int N, int K);
+int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* colsum_partial, int nblk, const void* w,
+                            int G, int N, int K, long long count, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float* scale_shift, float* batch_stats, void* ws, void* stream);
 int mauv_bn_relu_maxpool_f16(const void* y, const float* scale_shift, int G, int imgs_per_sample, int H,
                              int W, int C, void* out, void* stream);
 int mauv_avgpool_f16(const void* x, long long N, int HW, int C, float* out, void* stream);

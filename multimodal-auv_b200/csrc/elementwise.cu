@@ -160,11 +160,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // One thread owns one 8-channel group (c0 is loop invariant because the thread stride is a multiple of C/8),
 // keeps its 8 (scale, shift) pairs in registers and streams rows with 4 independent 16-byte loads in flight.
+// colsum (nullable) [G][gridDim.x][C]: per-block column sums of the fp16 OUTPUT values (what the next conv reads) - the
+// first moment of the closed-form BatchNorm statistics of that conv (mauv_bn_stats_from_gram).
 template <bool HAS_Y2, bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const uint4* __restrict__ res,
               const uint4* __restrict__ y2, const float2* __restrict__ ss2, int relu,
-              long long per_sample_vec /* M*C/8 */, int C, uint4* __restrict__ out) {
+              long long per_sample_vec /* M*C/8 */, int C, uint4* __restrict__ out, float* __restrict__ colsum) {
   const int g = blockIdx.y;
   const unsigned cvec = C >> 3;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -192,6 +194,7 @@ bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const 
   if (HAS_Y2) y2 += base;
   if (HAS_RES) res += base;
   constexpr int U = 4;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long i0 = tid; i0 < per_sample_vec; i0 += stride * U) {
     uint4 vy[U], v2[U], vr[U];
 #pragma unroll
@@ -227,11 +230,165 @@ bn_act_kernel(const uint4* __restrict__ y, const float2* __restrict__ ss, const 
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        out[i] = pack8(f);
+        const uint4 o = pack8(f);
+        out[i] = o;
+        if (colsum) {
+          float fo[8];
+          unpack8(o, fo);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] += fo[j];
+        }
       }
     }
   }
+  if (colsum) {      // threads t, t + cvec, t + 2 cvec .. of the block own the same 8 channels (cvec <= 256 divides 256)
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = cs[j];
+    __syncthreads();
+    if (threadIdx.x < cvec) {
+      for (unsigned t = threadIdx.x + cvec; t < 256; t += cvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += red[t][j];
+      }
+      float* dst = colsum + (static_cast<long long>(g) * gridDim.x + blockIdx.x) * C + threadIdx.x * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+    }
+  }
 }
+
+// Column sums of a [G][M][C] fp16 tensor: colsum [G][gridDim.x][C] per-block partials (same layout as bn_act's).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const uint4* __restrict__ x, long long per_sample_vec, int C, float* __restrict__ colsum) {
+  const int g = blockIdx.y;
+  const unsigned cvec = C >> 3;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  x += static_cast<long long>(g) * per_sample_vec;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i0 = tid; i0 < per_sample_vec; i0 += stride * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < per_sample_vec) v[u] = __ldcs(x + i0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < per_sample_vec) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += f[j];
+      }
+  }
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = cs[j];
+  __syncthreads();
+  if (threadIdx.x < cvec) {
+    for (unsigned t = threadIdx.x + cvec; t < 256; t += cvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] += red[t][j];
+    }
+    float* dst = colsum + (static_cast<long long>(g) * gridDim.x + blockIdx.x) * C + threadIdx.x * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Closed-form BatchNorm batch statistics of a 1x1 convolution y = a W^T from the moments of its INPUT:
+//     sum_m y[m][n]   = w_n . s            s = column sums of a        (K values per sample)
+//     sum_m y[m][n]^2 = w_n^T S w_n        S = a^T a (second moments)   (K x K per sample)
+// so the statistics pass of the recompute scheme (a full N x K contraction over all pixels whose M x N result is only
+// reduced) becomes one K x K contraction over the pixels (mauv_wgrad_f16 with dy = x = a: MN-major tcgen05 operands,
+// fp32 partial sums per pixel chunk) plus this small evaluation. Stage A reduces the partials (double accumulation),
+// stage B evaluates the two forms for 32 output channels per block with S staged through shared memory, and writes
+// (sum, sum of squares) in the double2 layout bn_finalize_kernel consumes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const float* __restrict__ gram, int splits, long long kk /* K*K */, const float* __restrict__ colsum,
+                   int nblk, int K, float* __restrict__ S /*[G][K*K]*/, float* __restrict__ s1 /*[G][K]*/) {
+  const int g = blockIdx.y;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < kk) {
+    const float* src = gram + static_cast<long long>(g) * splits * kk + i;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;       // fixed summation order: deterministic
+    int sp = 0;
+    for (; sp + 3 < splits; sp += 4) {
+      const float v0 = __ldcs(src + static_cast<long long>(sp) * kk), v1 = __ldcs(src + static_cast<long long>(sp + 1) * kk);
+      const float v2 = __ldcs(src + static_cast<long long>(sp + 2) * kk), v3 = __ldcs(src + static_cast<long long>(sp + 3) * kk);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; sp < splits; ++sp) a0 += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
+    S[static_cast<long long>(g) * kk + i] = static_cast<float>((a0 + a1) + (a2 + a3));
+  }
+  if (i < K) {
+    const float* src = colsum + static_cast<long long>(g) * nblk * K + i;
+    double acc = 0.0;
+    for (int b = 0; b < nblk; ++b) acc += static_cast<double>(src[static_cast<long long>(b) * K]);
+    s1[static_cast<long long>(g) * K + i] = static_cast<float>(acc);
+  }
+}
+
+constexpr int GQ_N = 32;      // output channels per block (8 warps x 4)
+constexpr int GQ_ROWS = 32;   // rows of S staged per step (one per lane)
+__global__ void __launch_bounds__(256)
+gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, const __half* __restrict__ w /*[G][N][K]*/,
+                     int N, int K, double2* __restrict__ out /*[G][1][N] (sum, sum of squares)*/) {
+  extern __shared__ __align__(16) float gq_smem[];
+  const int pitch = K + 1;                         // lanes read different rows of S at the same column: odd pitch
+  float* wt = gq_smem;                             // [K][GQ_N]   this block's weights, transposed: 4 channels = one LDS.128
+  float* Ss = gq_smem + GQ_N * K;                  // [GQ_ROWS][pitch]
+  const int g = blockIdx.y, n0 = blockIdx.x * GQ_N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < GQ_N * K; i += 256) {
+    const int nn = i / K, c = i - nn * K;          // coalesced read of w rows
+    const int n = n0 + nn;
+    wt[c * GQ_N + nn] = n < N ? __half2float(w[(static_cast<long long>(g) * N + n) * K + c]) : 0.f;
+  }
+  const float* Sg = S + static_cast<long long>(g) * K * K;
+  double q[4] = {0.0, 0.0, 0.0, 0.0};
+  const float* wq = wt + warp * 4;
+  for (int r0 = 0; r0 < K; r0 += GQ_ROWS) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < GQ_ROWS * K; i += 256) {
+      const int r = i / K, c = i - r * K;
+      Ss[r * pitch + c] = (r0 + r < K) ? Sg[static_cast<long long>(r0 + r) * K + c] : 0.f;
+    }
+    __syncthreads();
+    // lane = row r0 + lane of S: t[j] = S[row][:] . w_j for this warp's 4 channels, then q_j += w_j[row] * t[j]
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* srow = Ss + lane * pitch;
+#pragma unroll 4
+    for (int c = 0; c < K; ++c) {
+      const float sv = srow[c];
+      const float4 w4 = *reinterpret_cast<const float4*>(wq + c * GQ_N);    // broadcast
+      t[0] = fmaf(sv, w4.x, t[0]); t[1] = fmaf(sv, w4.y, t[1]); t[2] = fmaf(sv, w4.z, t[2]); t[3] = fmaf(sv, w4.w, t[3]);
+    }
+    if (r0 + lane < K) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wq + (r0 + lane) * GQ_N);
+      q[0] += static_cast<double>(w4.x) * t[0]; q[1] += static_cast<double>(w4.y) * t[1];
+      q[2] += static_cast<double>(w4.z) * t[2]; q[3] += static_cast<double>(w4.w) * t[3];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = warp_sum_d(q[j]);
+  // first moment: w_n . s1
+  double m[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c = lane; c < K; c += 32) {
+    const double sv = s1[static_cast<long long>(g) * K + c];
+    const float4 w4 = *reinterpret_cast<const float4*>(wq + c * GQ_N);
+    m[0] += sv * w4.x; m[1] += sv * w4.y; m[2] += sv * w4.z; m[3] += sv * w4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = warp_sum_d(m[j]);
+  if (lane < 4) {
+    const int n = n0 + warp * 4 + lane;
+    if (n < N) out[static_cast<long long>(g) * N + n] = make_double2(m[lane], q[lane]);
+  }
+}
+
 
 // Stem tail: BN + ReLU + 3x3/2 max-pool (pad 1) in one pass.
 // y: [G*B][H][W][C] fp16 raw conv output -> out: [G*B][Ho][Wo][C]. One block per (image, output row): no integer
@@ -391,18 +548,24 @@ int mauv_bn_finalize(const float* stats_partial, int G, int m_tiles, int C, long
   return MAUV_OK;
 }
 
+int mauv_bn_act_blocks(int G, long long M, int C) {
+  const long long per = M * C / 8;
+  long long bx = ceil_div_i64(per, 256 * 4);
+  const long long cap = static_cast<long long>(mauv_num_sms()) * 16 / (G < 16 ? G : 16) + 1;
+  if (bx > cap) bx = cap;
+  return static_cast<int>(bx < 1 ? 1 : bx);
+}
+
 int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residual, const void* y2,
-                    const float* scale_shift2, int relu, int G, long long M, int C, void* out, void* stream) {
+                    const float* scale_shift2, int relu, int G, long long M, int C, void* out, float* colsum_partial,
+                    void* stream) {
   MAUV_CHECK_ARG(y && scale_shift && out, "mauv_bn_act_f16: null pointer");
   MAUV_CHECK_ARG(C % 8 == 0, "mauv_bn_act_f16: C must be a multiple of 8");
   MAUV_CHECK_ARG((y2 == nullptr) == (scale_shift2 == nullptr), "mauv_bn_act_f16: y2 and scale_shift2 go together");
   MAUV_CHECK_ARG((C & (C - 1)) == 0 && C <= 2048, "mauv_bn_act_f16: C must be a power of two <= 2048 (got %d)", C);
   const long long per = M * C / 8;
-  long long bx = ceil_div_i64(per, 256 * 4);
-  const long long cap = static_cast<long long>(mauv_num_sms()) * 16 / (G < 16 ? G : 16) + 1;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  dim3 grid(static_cast<unsigned>(bx), G);
+  MAUV_CHECK_ARG(!colsum_partial || C >= 8, "mauv_bn_act_f16: column sums need C >= 8");
+  dim3 grid(static_cast<unsigned>(mauv_bn_act_blocks(G, M, C)), G);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint4* py = static_cast<const uint4*>(y);
   const float2* pss = reinterpret_cast<const float2*>(scale_shift);
@@ -410,10 +573,10 @@ int mauv_bn_act_f16(const void* y, const float* scale_shift, const void* residua
   const uint4* py2 = static_cast<const uint4*>(y2);
   const float2* pss2 = reinterpret_cast<const float2*>(scale_shift2);
   uint4* po = static_cast<uint4*>(out);
-  if (y2 && residual) bn_act_kernel<true, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
-  else if (y2) bn_act_kernel<true, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
-  else if (residual) bn_act_kernel<false, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
-  else bn_act_kernel<false, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po);
+  if (y2 && residual) bn_act_kernel<true, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po, colsum_partial);
+  else if (y2) bn_act_kernel<true, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po, colsum_partial);
+  else if (residual) bn_act_kernel<false, true><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po, colsum_partial);
+  else bn_act_kernel<false, false><<<grid, 256, 0, st>>>(py, pss, pres, py2, pss2, relu, per, C, po, colsum_partial);
   MAUV_LAUNCH_CHECK("bn_act_kernel");
   return MAUV_OK;
 }
@@ -479,6 +642,57 @@ int mauv_subsample_f16(const void* x, long long N, int H, int W, int C, int stri
   subsample_kernel<<<static_cast<unsigned>(ceil_div_i64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), H, W, C / 8, Ho, Wo, stride, total, static_cast<uint4*>(out));
   MAUV_LAUNCH_CHECK("subsample_kernel");
+  return MAUV_OK;
+}
+
+// Column sums of x [G][M][C] fp16 -> colsum_partial [G][mauv_bn_act_blocks(G, M, C)][C] fp32 (per-block partials).
+int mauv_colsum_f16(const void* x, int G, long long M, int C, float* colsum_partial, void* stream) {
+  MAUV_CHECK_ARG(x && colsum_partial && G >= 1 && M >= 1, "mauv_colsum_f16: bad argument");
+  MAUV_CHECK_ARG(C >= 8 && (C & (C - 1)) == 0 && C <= 2048, "mauv_colsum_f16: C must be a power of two in [8, 2048] (got %d)", C);
+  dim3 grid(static_cast<unsigned>(mauv_bn_act_blocks(G, M, C)), G);
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), M * C / 8, C, colsum_partial);
+  MAUV_LAUNCH_CHECK("colsum_kernel");
+  return MAUV_OK;
+}
+
+// workspace of mauv_bn_stats_from_gram: S [G][K*K] + s1 [G][K] floats, then double2 [G][N]
+long long mauv_bn_stats_from_gram_ws_bytes(int G, int N, int K) {
+  const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;   // 16-byte aligned
+  return f * 4 + static_cast<long long>(G) * N * sizeof(double2);
+}
+
+int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* colsum_partial, int nblk, const void* w,
+                            int G, int N, int K, long long count, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float* scale_shift, float* batch_stats, void* ws, void* stream) {
+  MAUV_CHECK_ARG(gram_partial && colsum_partial && w && scale_shift && ws && splits >= 1 && nblk >= 1,
+                 "mauv_bn_stats_from_gram: null pointer");
+  MAUV_CHECK_ARG(G >= 1 && G <= BN_MAX_G && N >= 1 && K >= 8 && K <= 512 && K % 8 == 0 && count >= 1,
+                 "mauv_bn_stats_from_gram: bad shape G=%d N=%d K=%d", G, N, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* S = static_cast<float*>(ws);
+  float* s1 = S + static_cast<long long>(G) * K * K;
+  const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;
+  double2* sums = reinterpret_cast<double2*>(static_cast<float*>(ws) + f);
+  const long long kk = static_cast<long long>(K) * K;
+  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk, 256)), G);
+  gram_reduce_kernel<<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
+  MAUV_LAUNCH_CHECK("gram_reduce_kernel");
+  const int smem = (GQ_N * K + GQ_ROWS * (K + 1)) * static_cast<int>(sizeof(float));
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    MAUV_CUDA(cudaFuncSetAttribute(gram_quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 g2((N + GQ_N - 1) / GQ_N, G);
+  gram_quadform_kernel<<<g2, 256, smem, st>>>(S, s1, static_cast<const __half*>(w), N, K, sums);
+  MAUV_LAUNCH_CHECK("gram_quadform_kernel");
+  dim3 fblock(32, G < 16 ? G : 16);
+  bn_finalize_kernel<<<(N + 31) / 32, fblock, 0, st>>>(sums, G, 1, N, count, gamma, beta, eps, momentum, running_mean,
+                                                       running_var, num_batches_tracked,
+                                                       reinterpret_cast<float2*>(scale_shift),
+                                                       reinterpret_cast<float2*>(batch_stats));
+  MAUV_LAUNCH_CHECK("bn_finalize_kernel(gram)");
   return MAUV_OK;
 }
 

@@ -74,6 +74,8 @@ struct GemmParams {
                          //      groups of batches: the stem's im2col matrix in the weight gradient)
   int mn;                // 1: weight-gradient mode
   int b_im2col;          // mn: B boxes come from im2col-mode TMA (else tiled rows of [pixels][Cin])
+  int gram;              // mn: dY and X are the SAME tensor (second moments a^T a): only the B boxes are loaded and the A
+                         //     descriptor points at boxes m0/64, m0/64+1 of the B tile (N = K <= BN: one n-tile)
   int cin;               // mn: input channels (column -> (tap, channel block))
   long long chunk;       // mn: pixels per batch entry
 };
@@ -230,10 +232,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = tiles_base + stage * L::kStageBytes;
             const uint32_t b_dst = a_dst + L::kABytes;
-            mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(a_boxes + b_boxes) * 8192u);
+            mbar_expect_tx(full_bar(stage), static_cast<uint32_t>((p.gram ? 0 : a_boxes) + b_boxes) * 8192u);
             const long long pix0 = static_cast<long long>(g) * p.chunk + static_cast<long long>(kb) * 64;
-            for (int j = 0; j < a_boxes; ++j)
-              tma_load_3d(a_dst + j * 8192, &tmA, full_bar(stage), m0 + 64 * j, static_cast<int>(pix0), 0);
+            if (!p.gram)
+              for (int j = 0; j < a_boxes; ++j)
+                tma_load_3d(a_dst + j * 8192, &tmA, full_bar(stage), m0 + 64 * j, static_cast<int>(pix0), 0);
             if (p.b_im2col) {
               const int img = static_cast<int>(pix0 / hw);
               const int r2 = static_cast<int>(pix0 - static_cast<long long>(img) * hw);
@@ -291,6 +294,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        int tile_m0 = 0;
+        if (p.gram) {
+          int g_, m_tile_, n_tile_;
+          decode(tile, g_, m_tile_, n_tile_);
+          tile_m0 = m_tile_ * BM;
+        }
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -301,7 +310,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (p.mn) {
             // MN-major boxes [64 pixels][64 channels]: one MMA consumes 16 pixel rows = 2048 bytes (+128 in the >>4 field)
             constexpr uint32_t idesc_mn = umma_idesc_f16_mn(BM, BN);
-            const uint64_t a_desc = umma_smem_desc_mn_sw128(a_addr, 8192);
+            // gram mode: the A rows (channels m0 .. m0+127) are boxes m0/64, m0/64+1 of the B tile
+            const uint32_t a_src = p.gram ? a_addr + L::kABytes + static_cast<uint32_t>((tile_m0 >> 6) * 8192) : a_addr;
+            const uint64_t a_desc = umma_smem_desc_mn_sw128(a_src, 8192);
             const uint64_t b_desc = umma_smem_desc_mn_sw128(a_addr + L::kABytes, 8192);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
@@ -1337,6 +1348,9 @@ int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, i
   p.a_mode = 0;
   p.a_batch_mul = 1;
   p.mn = 1;
+  // second moments (dy and x are one tensor): load the boxes once. Needs one n-tile holding all K columns (K <= 256) and the
+  // M tile's 128 channels inside it
+  p.gram = (dy == x && plain && K <= 256 && Cout == K && (K % 128 == 0 || K == 64)) ? 1 : 0;
   p.b_im2col = plain ? 0 : 1;
   p.cin = Cin;
   p.Wo = Wo; p.Ho = Ho; p.imgs_per_sample = imgs_per_sample; p.stride = stride; p.pad = pad; p.kw = kw;

@@ -106,6 +106,9 @@ class MCEngine:
         self.fuse_conv3 = True
         self.fuse_input_bn = os.environ.get("MAUV_FUSE_INPUT_BN", "0") == "1"
         self.fuse_conv3_max_k = int(os.environ.get('MAUV_FUSE_CONV3_MAX_K', '256'))
+        # statistics of the recompute scheme in closed form: sum y = w . colsum(a), sum y^2 = w^T (a^T a) w - one K x K
+        # second-moment contraction over the pixels instead of the N x K statistics pass (N = 4K)
+        self.gram_stats = os.environ.get("MAUV_GRAM_STATS", "1") != "0"
 
     # Philox sample-id cursor, shared by every engine built on the same model (it lives on the model object): each
     # forward_mc / TrainEngine.step / predictor batch that is not given explicit sample ids takes the next S ids, so
@@ -178,6 +181,17 @@ class MCEngine:
                              bn.running_mean if track else None, bn.running_var if track else None,
                              num_batches_tracked=bn.num_batches_tracked if track else None)
         return ss
+
+    def _bn_gram(self, a, colsum, w, count, bn: nn.BatchNorm2d, G):
+        """BN scale/shift of the 1x1 conv a @ w^T from the input's moments (ops.bn_stats_from_gram); same running-statistics
+        bookkeeping as _bn."""
+        self.launches += 4
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        track = bn.track_running_stats and bn.running_mean is not None
+        return ops.bn_stats_from_gram(a, colsum, w, count, bn.weight.detach() if bn.weight is not None else None,
+                                      bn.bias.detach() if bn.bias is not None else None, bn.eps, mom,
+                                      bn.running_mean if track else None, bn.running_var if track else None,
+                                      bn.num_batches_tracked if track else None)
 
     def _conv_bn(self, c: _Conv, bn, x, G, B, s0, eps, seed):
         """x: [G*B, H, W, Cin] fp16 -> raw conv output [G*B, Ho, Wo, Cout] fp16 + BN scale/shift [G, Cout, 2]."""
@@ -268,21 +282,32 @@ class MCEngine:
             else:
                 a1 = ops.bn_act_f16(y1, ss1, G, blk.conv1.cout, relu=True)
                 y2, ss2 = self._conv_bn(blk.conv2, blk.bn2, a1, G, B, s0, eps, seed)
-            a2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True)
-            if blk.down is None and self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k:
-                # HBM-write-bound tail of the bottleneck: recompute scheme. Pass 1 = statistics of conv3 only,
-                # pass 2 = conv3 again with BN-apply + residual + ReLU in the epilogue; y3 never reaches HBM.
+            fuse_tail = self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k and (
+                blk.down is None or (blk.down.cin <= self.fuse_conv3_max_k and blk.down.k == 1 and blk.down.pad == 0))
+            M2 = y2.shape[0] // G * y2.shape[1] * y2.shape[2]
+            gram = fuse_tail and self.gram_stats and ops.gram_splits(M2, G, blk.conv2.cout) > 0
+            cs2 = None
+            if gram:    # the activation pass also emits the column sums of a2 (first moment of conv3's closed-form statistics)
+                a2, cs2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True, colsum=True)
+            else:
+                a2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True)
+            if blk.down is None and fuse_tail:
+                # HBM-write-bound tail of the bottleneck: recompute scheme. Pass 1 = statistics of conv3 only (closed form
+                # from a2's second moments, or the statistics-only contraction), pass 2 = conv3 with BN-apply + residual +
+                # ReLU in the epilogue; y3 never reaches HBM.
                 c3 = blk.conv3
                 w3 = self._sample(c3, G, s0, eps, seed)
                 NB, H, W, Cm = a2.shape
                 a2v = a2.view(G, B * H * W, Cm)
-                ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), B * H * W, blk.bn3, G)
+                if gram:
+                    ss3 = self._bn_gram(a2v, cs2, w3, B * H * W, blk.bn3, G)
+                else:
+                    ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), B * H * W, blk.bn3, G)
                 x = ops.gemm_bn_act_f16(a2v, w3, ss3, residual=x.view(G, B * H * W, c3.cout), relu=True).view(NB, H, W, c3.cout)
                 self.launches += 2
                 continue
-            if (blk.down is not None and self.fuse_conv3 and blk.conv3.cin <= self.fuse_conv3_max_k
-                    and blk.down.cin <= self.fuse_conv3_max_k and blk.down.k == 1 and blk.down.pad == 0):
-                x = self._fused_downsample_tail(blk, a2, x, G, B, s0, eps, seed)
+            if blk.down is not None and fuse_tail:
+                x = self._fused_downsample_tail(blk, a2, x, G, B, s0, eps, seed, cs2)
                 continue
             y3, ss3 = self._conv_bn(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
             if blk.down is not None:
@@ -295,7 +320,7 @@ class MCEngine:
         self.launches += 1
         return feat.view(G, B, -1)
 
-    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed):
+    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed, cs2=None):
         """relu(bn3(conv3(a2)) + bn_d(conv_d(x))) without either raw conv output in HBM: two statistics passes (recompute
         scheme), then ONE contraction over K-concatenated operands [a2 | x'] * [s3*W3 | sd*Wd]^T + (t3 + td) - the BN scales
         folded into freshly sampled weights, the shifts into the epilogue. x' = x for stride 1, else x subsampled."""
@@ -308,8 +333,14 @@ class MCEngine:
         xv = xs.view(G, M, cd.cin)
         w3 = self._sample(c3, G, s0, eps, seed)
         wd = self._sample(cd, G, s0, eps, seed)
-        ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), M, blk.bn3, G)
-        ssd = self._bn(ops.gemm_stats_f16(xv, wd), M, blk.down_bn, G)
+        if cs2 is not None:
+            ss3 = self._bn_gram(a2v, cs2, w3, M, blk.bn3, G)
+        else:
+            ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), M, blk.bn3, G)
+        if self.gram_stats and ops.gram_splits(M, G, cd.cin) > 0:
+            ssd = self._bn_gram(xv, ops.colsum_f16(xv, G, cd.cin), wd, M, blk.down_bn, G)
+        else:
+            ssd = self._bn(ops.gemm_stats_f16(xv, wd), M, blk.down_bn, G)
         wcat = torch.empty((G, c3.cout, Cm + cd.cin), dtype=F16, device=self.device)
         ops.sample_weights_scaled_f16(c3.layer.mu_kernel.detach(), c3.layer.rho_kernel.detach(), G, ss3, wcat, 0,
                                       eps=self._eps_w(eps, c3.name, s0, G), seed=seed, layer_id=c3.layer_id, sample0=s0)

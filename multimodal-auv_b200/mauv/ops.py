@@ -332,15 +332,67 @@ def bn_finalize(stats_partial: torch.Tensor, count: int, gamma: Optional[torch.T
 
 def bn_act_f16(y: torch.Tensor, ss: torch.Tensor, G: int, C: int, *, residual: Optional[torch.Tensor] = None,
                y2: Optional[torch.Tensor] = None, ss2: Optional[torch.Tensor] = None, relu: bool = True,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, colsum: bool = False):
+    """out = relu?(y*ss [+ residual] [+ y2*ss2]). colsum=True -> (out, per-block column sums [G, nblk, C] fp32 of out)."""
     lib = _lib.require_device()
     M = y.numel() // (G * C)
     if out is None:
         out = torch.empty_like(y)
+    cs = torch.empty((G, lib.mauv_bn_act_blocks(G, M, C), C), dtype=F32, device=y.device) if colsum else None
     _run("mauv_bn_act_f16", lib.mauv_bn_act_f16, _ptr(y, F16), _ptr(ss, F32), _ptr(residual, F16), _ptr(y2, F16), _ptr(ss2, F32),
-                                   int(relu), G, M, C, _ptr(out, F16), _stream(),
+                                   int(relu), G, M, C, _ptr(out, F16), _ptr(cs), _stream(),
          tag=f"G{G} M{M} C{C} res{int(residual is not None)} dual{int(y2 is not None)}" if _prof is not None else None)
-    return out
+    return (out, cs) if colsum else out
+
+
+def colsum_f16(x: torch.Tensor, G: int, C: int) -> torch.Tensor:
+    """per-block column sums [G, nblk, C] fp32 of x [G, M, C] fp16"""
+    lib = _lib.require_device()
+    M = x.numel() // (G * C)
+    cs = torch.empty((G, lib.mauv_bn_act_blocks(G, M, C), C), dtype=F32, device=x.device)
+    _run("mauv_colsum_f16", lib.mauv_colsum_f16, _ptr(x, F16), G, M, C, _ptr(cs), _stream())
+    return cs
+
+
+KERNELS_PER_CALL["mauv_bn_stats_from_gram"] = 3
+
+
+def gram_splits(M: int, G: int, K: int) -> int:
+    """Pixel chunks per sample for the second-moment contraction a^T a (0 = shape not eligible). Chunks are a multiple of 64
+    pixels (the weight-gradient kernel's k-block) and at most 4096 pixels long: the tensor core accumulates in fp32 with
+    truncation, and a sum of same-sign products (the diagonal of a^T a) picks up a relative bias of ~n_adds * 2^-25, so
+    the long sums are split and the partials are combined in double precision (4096 px = 256 MMA accumulations: < 1e-5);
+    shorter chunks (down to 2048) only when that is needed to fill the GPU."""
+    if K % 64 != 0 or K > 256 or M % 64 != 0:
+        return 0
+    tiles = G * ((K + 127) // 128) * ((K + 255) // 256)
+    s = 1
+    while M % (2 * s * 64) == 0 and (M // (2 * s) >= 4096 or (tiles * s < 2 * 148 and M // (2 * s) >= 2048)):
+        s *= 2
+    return s
+
+
+def bn_stats_from_gram(a: torch.Tensor, colsum: torch.Tensor, w: torch.Tensor, count: int, gamma, beta, eps: float,
+                       momentum: float, running_mean=None, running_var=None, num_batches_tracked=None,
+                       want_batch_stats: bool = False, splits: Optional[int] = None):
+    """BatchNorm(train) scale/shift [G, N, 2] of y = a w^T without computing y: a [G, M, K] fp16 (contiguous), colsum
+    [G, nblk, K] (bn_act_f16(colsum=True) / colsum_f16), w [G, N, K] fp16."""
+    lib = _lib.require_device()
+    G, M, K = a.shape
+    N = w.shape[1]
+    assert w.shape[0] == G and w.shape[2] == K and colsum.shape[0] == G and colsum.shape[2] == K
+    splits = splits or gram_splits(M, G, K)
+    if splits == 0:
+        raise _lib.MauvError(f"bn_stats_from_gram: shape M={M} K={K} is not eligible")
+    x4 = a.view(G, M, 1, K)                     # NHWC view [G*B', H, W, C] with B'=1, H=M, W=1
+    gram = wgrad_f16(x4, x4, G, splits, 1, 1, 1, 0)            # [G*splits, K, K] fp32
+    out = torch.empty((G, N, 2), dtype=F32, device=a.device)
+    bs = torch.empty((G, N, 2), dtype=F32, device=a.device) if want_batch_stats else None
+    ws = torch.empty(lib.mauv_bn_stats_from_gram_ws_bytes(G, N, K), dtype=torch.uint8, device=a.device)
+    _run("mauv_bn_stats_from_gram", lib.mauv_bn_stats_from_gram, _ptr(gram, F32), splits, _ptr(colsum, F32), colsum.shape[1],
+         _ptr(w, F16), G, N, K, count, _ptr(gamma, F32), _ptr(beta, F32), eps, momentum, _ptr(running_mean, F32),
+         _ptr(running_var, F32), _ptr(num_batches_tracked, I64), _ptr(out), _ptr(bs), _ptr(ws), _stream())
+    return (out, bs) if want_batch_stats else out
 
 
 def bn_relu_maxpool_f16(y: torch.Tensor, ss: torch.Tensor, G: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

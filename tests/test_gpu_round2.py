@@ -244,3 +244,41 @@ def test_train_unimodal_model_two_ranks_ddp_gradients_are_synchronised(bu):
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ranks identical: True" in r.stdout
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 256, 64), (3, 8192, 512, 128), (2, 2048, 1024, 256), (1, 64 * 37, 256, 64)])
+def test_closed_form_batchnorm_statistics_from_input_second_moments(bu, shape):
+    """mauv_bn_stats_from_gram (sum y = w . colsum(a), sum y^2 = w^T (a^T a) w; the K x K contraction runs on the tcgen05
+    weight-gradient kernel) against fp64 BatchNorm statistics of y = a w^T computed directly, and against the N x K
+    statistics pass it replaces: mean 2e-5, variance and scale / shift 5e-5 relative (of the tensor max; the fp32
+    tensor-core accumulation of the same-sign diagonal sums truncates - chunks are capped at 4096 pixels for that reason),
+    running statistics 1e-4."""
+    from mauv import ops
+    G, M, N, K = shape
+    torch.manual_seed(sum(shape))
+    y_prev = torch.randn(G, M, K, device="cuda", dtype=torch.float16)
+    ss_prev = torch.stack([torch.rand(G, K, device="cuda") + 0.5, torch.randn(G, K, device="cuda") * 0.3], -1).contiguous()
+    a, cs = ops.bn_act_f16(y_prev, ss_prev, G, K, relu=True, colsum=True)            # post-ReLU activations + column sums
+    assert torch.allclose(cs.sum(1), a.float().sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(ops.colsum_f16(a, G, K).sum(1), a.float().sum(1), rtol=1e-5, atol=1e-2)
+    w = (torch.randn(G, N, K, device="cuda") * 0.05).half()
+    gamma, beta = torch.rand(N, device="cuda") + 0.5, torch.randn(N, device="cuda")
+    rm, rv = torch.zeros(N, device="cuda"), torch.ones(N, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    ss, bs = ops.bn_stats_from_gram(a, cs, w, M, gamma, beta, 1e-5, 0.1, rm, rv, nbt, want_batch_stats=True)
+    y = torch.einsum("gmk,gnk->gmn", a.double(), w.double())
+    mean, var = y.mean(1), y.var(1, unbiased=False)
+    sc = gamma.double() / torch.sqrt(var + 1e-5)
+    ref = torch.stack([sc, beta.double() - mean * sc], -1)
+    assert (bs[..., 0].double() - mean).abs().max().item() <= 2e-5 * mean.abs().max().item() + 1e-7
+    assert (bs[..., 1].double() - var).abs().max().item() <= 5e-5 * var.abs().max().item()
+    assert (ss.double() - ref).abs().max().item() <= 5e-5 * ref.abs().max().item()
+    rm_ref, rv_ref = torch.zeros(N, dtype=torch.float64, device="cuda"), torch.ones(N, dtype=torch.float64, device="cuda")
+    for g in range(G):
+        rm_ref = 0.9 * rm_ref + 0.1 * mean[g]
+        rv_ref = 0.9 * rv_ref + 0.1 * var[g] * M / (M - 1)
+    assert torch.allclose(rm.double(), rm_ref, rtol=1e-4, atol=1e-6) and torch.allclose(rv.double(), rv_ref, rtol=1e-4)
+    assert int(nbt) == G
+    # the statistics pass it replaces (accumulator statistics of the same contraction)
+    old = ops.bn_finalize(ops.gemm_stats_f16(a, w), M, gamma, beta, 1e-5, 0.0)
+    assert (old - ss).abs().max().item() <= 1e-4 * ss.abs().max().item()
