@@ -20,7 +20,7 @@ PARITY UNPINNED (bayesian-torch part): the reference's tests mock `get_kl_loss`/
 Bayesian layer, a KL value or an uncertainty value, and the package itself cannot be installed
 offline. The model/driver part IS pinned: oracle/make_golden.py runs the reference's own
 models/base_models.py and inference/predictors.py (loaded by file path) on top of these layers
-and tests/test_oracle_golden.py checks this file against those outputs.
+and tests/test_oracle.py checks this file against those outputs.
 
 Two additions over the reference semantics, both opt-in: eps injection/capture (so the CUDA
 path and the oracle can share identical noise) and a float64 mode.
