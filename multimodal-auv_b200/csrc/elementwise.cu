@@ -306,28 +306,30 @@ colsum_kernel(const uint4* __restrict__ x, long long per_sample_vec, int C, floa
 // stage B evaluates the two forms for 32 output channels per block with S staged through shared memory, and writes
 // (sum, sum of squares) in the double2 layout bn_finalize_kernel consumes.
 // ---------------------------------------------------------------------------
+// block = 32 elements x 8 partial lanes: element e < K*K is an entry of S (partials `splits` apart by K*K), element
+// K*K + c is column sum c (partials `nblk` apart by K); every lane sums its partials p = ty, ty+8, .. in double, the 8 lanes
+// are combined in a fixed order (deterministic). Short dependent chains instead of one thread walking 256 partials.
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const float* __restrict__ gram, int splits, long long kk /* K*K */, const float* __restrict__ colsum,
                    int nblk, int K, float* __restrict__ S /*[G][K*K]*/, float* __restrict__ s1 /*[G][K]*/) {
-  const int g = blockIdx.y;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < kk) {
-    const float* src = gram + static_cast<long long>(g) * splits * kk + i;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;       // fixed summation order: deterministic
-    int sp = 0;
-    for (; sp + 3 < splits; sp += 4) {
-      const float v0 = __ldcs(src + static_cast<long long>(sp) * kk), v1 = __ldcs(src + static_cast<long long>(sp + 1) * kk);
-      const float v2 = __ldcs(src + static_cast<long long>(sp + 2) * kk), v3 = __ldcs(src + static_cast<long long>(sp + 3) * kk);
-      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-    }
-    for (; sp < splits; ++sp) a0 += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
-    S[static_cast<long long>(g) * kk + i] = static_cast<float>((a0 + a1) + (a2 + a3));
+  __shared__ double red[8][33];
+  const int g = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long e = static_cast<long long>(blockIdx.x) * 32 + tx;
+  double acc = 0.0;
+  if (e < kk) {
+    const float* src = gram + static_cast<long long>(g) * splits * kk + e;
+    for (int sp = ty; sp < splits; sp += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
+  } else if (e < kk + K) {
+    const float* src = colsum + static_cast<long long>(g) * nblk * K + (e - kk);
+    for (int b = ty; b < nblk; b += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(b) * K));
   }
-  if (i < K) {
-    const float* src = colsum + static_cast<long long>(g) * nblk * K + i;
-    double acc = 0.0;
-    for (int b = 0; b < nblk; ++b) acc += static_cast<double>(src[static_cast<long long>(b) * K]);
-    s1[static_cast<long long>(g) * K + i] = static_cast<float>(acc);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && e < kk + K) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) acc += red[j][tx];
+    if (e < kk) S[static_cast<long long>(g) * kk + e] = static_cast<float>(acc);
+    else s1[static_cast<long long>(g) * K + (e - kk)] = static_cast<float>(acc);
   }
 }
 
@@ -675,7 +677,7 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
   const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;
   double2* sums = reinterpret_cast<double2*>(static_cast<float*>(ws) + f);
   const long long kk = static_cast<long long>(K) * K;
-  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk, 256)), G);
+  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32)), G);
   gram_reduce_kernel<<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
   MAUV_LAUNCH_CHECK("gram_reduce_kernel");
   const int smem = (GQ_N * K + GQ_ROWS * (K + 1)) * static_cast<int>(sizeof(float));

@@ -83,14 +83,27 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
         x[c] = (CC > 0 || c < C) ? row[c] : -INFINITY;
         mx = fmaxf(mx, x[c]);
       }
-      float z = 0.f;
+      // Per-sample entropy with ONE logarithm instead of C: with u_c = x_c - max, e_c = exp(u_c), z = sum e_c,
+      //   -sum_c p_c log(p_c + eps) = log z - (sum_c e_c u_c) / z - sum_c p_c log1p(eps / p_c)
+      // and the last term is C_eff * eps to first order (eps = 1e-7 / 1e-8; classes with p_c << eps contribute
+      // -p_c log(eps) ~ 0 exactly and -eps in the expansion): |error| <= C * eps = 7e-7, far inside the 1e-5 tolerance the
+      // statistics are checked to. p_c = 0 (underflow) is harmless in this form: e_c u_c = 0 * finite.
+      float z = 0.f, eu = 0.f;
+      int n_live = 0;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        if (CC > 0 || c < C) { sum_l[c] += x[c]; x[c] = __expf(x[c] - mx); } else { x[c] = 0.f; }
+        if (CC > 0 || c < C) {
+          sum_l[c] += x[c];
+          const float u = x[c] - mx;
+          x[c] = __expf(u);
+          eu = fmaf(x[c], u, eu);
+          n_live += (u > -16.f) ? 1 : 0;          // p_c >= ~1e-7: the eps correction applies
+        } else {
+          x[c] = 0.f;
+        }
         z += x[c];
       }
       const float inv_z = __fdividef(1.f, z);
-      float h = 0.f;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (CC > 0 || c < C) {
@@ -100,10 +113,9 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
           const float d = pc - p0[c];
           sd[c] += d;
           sdd[c] = fmaf(d, d, sdd[c]);
-          h = fmaf(-pc, __logf(pc + eps_entropy), h);
         }
       }
-      sum_h += h;
+      sum_h += __logf(z) - eu * inv_z - static_cast<float>(n_live) * eps_entropy;
     }
     __syncthreads();   // slab s % MC_STAGES is refilled by the next iteration's issue()
   }

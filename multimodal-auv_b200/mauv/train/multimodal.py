@@ -190,7 +190,8 @@ def evaluate_multimodal_model(multimodal_model: nn.Module, dataloader, device: t
                                      "SSS Patch Type"])
             module = multimodal_model.module if isinstance(
                 multimodal_model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else multimodal_model
-            engine = MCEngine(module)
+            from ..engine import eval_precision
+            engine = MCEngine(module, precision=eval_precision("multimodal"))
             total_loss, correct, total = 0, 0, 0
             all_predicted, all_labels, all_pu, all_mu = [], [], [], []
             kl_weight = (2 ** (epoch + 1)) / (2 ** total_num_epochs)

@@ -101,7 +101,9 @@ def evaluate_unimodal_model(model: nn.Module, dataloader, device: torch.device, 
             if not file_exists:
                 writer.writerow(["Epoch", "Model Type", "Test Loss", "Test Accuracy", "predictive_uncertainty",
                                  "model_uncertainty"])
-            engine = MCEngine(model)
+            from ..engine import eval_precision
+            module = model.module if isinstance(model, (nn.parallel.DistributedDataParallel, nn.DataParallel)) else model
+            engine = MCEngine(module, precision=eval_precision("unimodal"))       # fp32-class arithmetic (see eval_precision)
             correct, total, total_loss = 0, 0, 0
             all_pu, all_au, all_predicted, all_labels = [], [], [], []
             with torch.no_grad():

@@ -88,6 +88,11 @@ class TrainEngine(MCEngine):
             raise _lib.MauvError(f"TrainEngine computes gradients for every parameter; {len(frozen)} are frozen "
                                  f"(requires_grad=False), e.g. {frozen[0]}")
         self.direct_wgrad = os.environ.get("MAUV_DIRECT_WGRAD", "1") != "0"
+        # north_star (1): the S sampled weight copies are never materialised - the forward samples of a layer are dropped as
+        # soon as its contraction has been enqueued and the data-gradient operand is RE-SAMPLED from the same Philox ids in the
+        # backward walk (bit-identical fp16 values; one layer's copies alive at a time). MAUV_KEEP_WEIGHT_SAMPLES=1 keeps them
+        # on the tape instead (4.4 GB at cfg3) and saves the re-sampling launches (~5 % of the step).
+        self.keep_weight_samples = os.environ.get("MAUV_KEEP_WEIGHT_SAMPLES", "0") == "1"
         self._update_running = True
         self._flat: Optional[FlatGrads] = None
         self._fused = {}        # id(optimizer) -> FusedAdam | None (optimizer_step)
@@ -109,7 +114,7 @@ class TrainEngine(MCEngine):
         else:
             y, st = ops.conv2d_im2col_f16(x, w, G, c.k, c.k, c.stride, c.pad, stats=True)
         ss, bs = self._bn_stats(st, y.numel() // (G * c.cout), bn)
-        return _ConvRec(c, bn, x, y, bs, w), ss
+        return _ConvRec(c, bn, x, y, bs, w if self.keep_weight_samples else None), ss
 
     def _bn_stats(self, stats, count, bn: nn.BatchNorm2d):
         if bn.weight is None or bn.bias is None:
@@ -209,10 +214,11 @@ class TrainEngine(MCEngine):
                                  eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0, stale=stale)
         if not need_dx:
             return None
-        if r.w is not None:
-            wd = ops.weights_to_dgrad_f16(r.w, Cin, c.k, c.k)
-        else:
-            wd = ops.sample_weights_dgrad_f16(mu, rho, G, eps=ew, seed=seed, layer_id=c.layer_id, sample0=s0)
+        # forward-layout sample (kept on the tape, or re-sampled from the same Philox ids / injected eps: coalesced writes),
+        # re-laid-out for the data-gradient conv; sampling straight into the transposed layout is 3x slower (scattered stores)
+        w_fwd = r.w if r.w is not None else self._sample(c, G, s0, eps, seed)
+        wd = ops.weights_to_dgrad_f16(w_fwd, Cin, c.k, c.k)
+        del w_fwd
         Hd, Wd = H + 2 * c.pad - c.k + 1, W + 2 * c.pad - c.k + 1
         dyd = dy if c.stride == 1 else ops.dilate_f16(dy, Hd, Wd, c.stride)
         if c.k == 1:

@@ -131,6 +131,23 @@ def wgrad(G, B, H, W, Cin, Cout, k, stride, pad, splits=1, iters=5):
           f"{by / ms / 1e9:.2f} TB/s", flush=True)
 
 
+def gram(G, M, K, N=0, iters=5):
+    """closed-form BN statistics: second-moment contraction a^T a (tcgen05 weight-gradient kernel, gram mode) + evaluation"""
+    N = N or 4 * K
+    a = torch.relu(torch.randn(G, M, K, device=dev, dtype=torch.float16))
+    w = (torch.randn(G, N, K, device=dev) * 0.05).half()
+    cs = ops.colsum_f16(a, G, K)
+    gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+    sp = ops.gram_splits(M, G, K)
+    x4 = a.view(G, M, 1, K)
+    ms = timeit(lambda: ops.wgrad_f16(x4, x4, G, sp, 1, 1, 1, 0), iters)
+    print(f"gram a^T a G={G} M={M} K={K} splits={sp}: {ms:.3f} ms  {a.numel() * 2 / ms / 1e9:.2f} TB/s (reads a once)  "
+          f"{2.0 * G * M * K * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    ms2 = timeit(lambda: ops.bn_stats_from_gram(a, cs, w, M, gamma, beta, 1e-5, 0.0), iters)
+    print(f"   contraction + evaluation (N={N}): {ms2:.3f} ms; statistics pass it replaces: "
+          f"{timeit(lambda: ops.gemm_stats_f16(a, w), iters):.3f} ms", flush=True)
+
+
 def bnbwd(G, M, C, iters=5):
     """one BatchNorm-backward site of a bottleneck tail (two upstream tensors, ReLU mask, dz output)"""
     y = torch.randn(G, M, C, device=dev, dtype=torch.float16)
@@ -208,4 +225,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "gram": gram, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)
