@@ -458,7 +458,10 @@ def train_leg(args, B: int, S: int, steps: int, warmup: int, detail: bool = Fals
             opt.step()
             return loss
 
-    for _ in range(max(1, warmup)):
+    # warm-up: step 1 runs eagerly, the fused optimizer re-homes the parameters, step 2 runs eagerly with the final pointers,
+    # step 3 records the CUDA graph of the step (seconds of host time) - the timed region only sees replays
+    warmup = max(4, warmup)
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     if dist:

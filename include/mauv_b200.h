@@ -41,7 +41,8 @@ const char* mauv_last_error(void);
 int mauv_device_check(void);
 int mauv_num_sms_c(void);
 /* Device-resident Philox sample-id base for the CALLING THREAD's subsequent launches of the forward sampling entry
- * points (mauv_sample_weights_f16, _scaled_f16, _dgrad_f16, _x3_f16, mauv_sampled_linear_f32); NULL = none. Those kernels
+ * points (mauv_sample_weights_f16, _scaled_f16, _dgrad_f16, _x3_f16, mauv_sampled_linear_f32) and of the S-batched backward's
+ * eps replay (mauv_wgrad_finalize_group, mauv_sampled_linear_bwd_group_f32); NULL = none. Those kernels
  * add *sample_base to their sample ids when they RUN, so a CUDA graph captured with a base set draws fresh eps on every
  * replay once the caller bumps the word - the reference draws fresh eps on every pass of every batch
  * (inference/predictors.py:54-66; bayesian-torch `eps.data.normal_()`). The pointer must stay valid while such work

@@ -278,23 +278,21 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// One N(0,1) value for (seed, layer, sample, element index).
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t layer_id, uint32_t sample_id,
-                                               uint64_t elem) {
-  uint32_t r[4];
-  const uint64_t quad = elem >> 2;
-  philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), sample_id, layer_id,
-                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-  const uint32_t which = static_cast<uint32_t>(elem & 3u);
-  // pair (r0, r1) -> z0, z1 ; pair (r2, r3) -> z2, z3
-  const uint32_t a = (which & 2u) ? r[2] : r[0];
-  const uint32_t b = (which & 2u) ? r[3] : r[1];
-  const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float rad = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  return (which & 1u) ? rad * s : rad * c;
+// Box-Muller on the SFU: lg2.approx / sqrt.approx / sin.approx / cos.approx (relative error ~2^-22, absolute error of a
+// normal ~1e-6) instead of libm's logf / sqrtf / sincospif: the sampler is ALU/SFU-bound (Philox + Box-Muller + softplus per
+// weight per sample) and the exact routines were half of its instructions. The stream differs from oracle/philox.py (numpy,
+// exact libm) by ~1e-6 absolute - three orders below the fp16 rounding of the sampled weight it feeds. EVERY kernel that
+// draws or replays eps goes through these two functions, so forward and backward see bit-identical eps.
+__device__ __forceinline__ void box_muller_pair(uint32_t ra_bits, uint32_t rb_bits, float& z0, float& z1) {
+  const float k = 1.0f / 16777216.0f;
+  const float u1 = (static_cast<float>(ra_bits >> 8) + 0.5f) * k;   // (0, 1)
+  const float u2 = (static_cast<float>(rb_bits >> 8) + 0.5f) * k;
+  float rad;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
+  float sn, cs;
+  __sincosf(6.283185307179586f * (u2 - 0.5f), &sn, &cs);     // argument in (-pi, pi): the SFU's accurate range
+  z0 = -rad * cs;                                             // cos(t + pi) = -cos t, sin(t + pi) = -sin t
+  z1 = -rad * sn;
 }
 
 // Four N(0,1) values of one Philox counter block: elements 4*quad .. 4*quad+3 of (seed, layer, sample).
@@ -303,14 +301,21 @@ __device__ __forceinline__ void philox_normals4(uint64_t seed, uint32_t layer_id
   uint32_t r[4];
   philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), sample_id, layer_id,
                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-  const float k = 1.0f / 16777216.0f;
-  const float ra = sqrtf(-2.0f * logf((static_cast<float>(r[0] >> 8) + 0.5f) * k));
-  const float rb = sqrtf(-2.0f * logf((static_cast<float>(r[2] >> 8) + 0.5f) * k));
-  float s, c;
-  sincospif(2.0f * ((static_cast<float>(r[1] >> 8) + 0.5f) * k), &s, &c);
-  z[0] = ra * c; z[1] = ra * s;
-  sincospif(2.0f * ((static_cast<float>(r[3] >> 8) + 0.5f) * k), &s, &c);
-  z[2] = rb * c; z[3] = rb * s;
+  box_muller_pair(r[0], r[1], z[0], z[1]);
+  box_muller_pair(r[2], r[3], z[2], z[3]);
+}
+
+// One N(0,1) value for (seed, layer, sample, element index): pair (r0, r1) -> z0, z1 ; pair (r2, r3) -> z2, z3
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t layer_id, uint32_t sample_id,
+                                               uint64_t elem) {
+  uint32_t r[4];
+  const uint64_t quad = elem >> 2;
+  philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), sample_id, layer_id,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const uint32_t which = static_cast<uint32_t>(elem & 3u);
+  float z0, z1;
+  box_muller_pair((which & 2u) ? r[2] : r[0], (which & 2u) ? r[3] : r[1], z0, z1);
+  return (which & 1u) ? z1 : z0;
 }
 
 // sigma = log1p(exp(rho)) exactly as the reference computes it (no threshold).

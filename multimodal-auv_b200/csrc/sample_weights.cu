@@ -32,21 +32,7 @@ struct SampleParams {
 
 __device__ __forceinline__ void normals4(uint64_t seed, uint32_t layer, uint32_t sample,
                                          uint64_t quad, float (&z)[4]) {
-  uint32_t r[4];
-  philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), sample, layer,
-                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-  const float k = 1.0f / 16777216.0f;
-  const float u1 = (static_cast<float>(r[0] >> 8) + 0.5f) * k;
-  const float u2 = (static_cast<float>(r[1] >> 8) + 0.5f) * k;
-  const float u3 = (static_cast<float>(r[2] >> 8) + 0.5f) * k;
-  const float u4 = (static_cast<float>(r[3] >> 8) + 0.5f) * k;
-  const float ra = sqrtf(-2.0f * logf(u1));
-  const float rb = sqrtf(-2.0f * logf(u3));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  z[0] = ra * c; z[1] = ra * s;
-  sincospif(2.0f * u4, &s, &c);
-  z[2] = rb * c; z[3] = rb * s;
+  philox_normals4(seed, layer, sample, quad, z);      // the one eps stream every kernel shares (common.cuh)
 }
 
 // Each thread handles 4 consecutive elements of the PyTorch-layout parameter tensor ([cout][cin][kh][kw]) for ALL

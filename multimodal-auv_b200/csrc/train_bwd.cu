@@ -401,7 +401,9 @@ __global__ void __launch_bounds__(256)
 wgrad_finalize_group_kernel(const DW* __restrict__ dw, int G, int splits, int cout, int cin, int kh, int kw, int Kp,
                             float inv_alpha, const float* __restrict__ s, const float* __restrict__ rho,
                             const float* __restrict__ eps, uint64_t seed, uint32_t layer_id, uint32_t sample0, int stale,
-                            float* __restrict__ grad_mu, float* __restrict__ grad_rho) {
+                            float* __restrict__ grad_mu, float* __restrict__ grad_rho,
+                            const unsigned int* __restrict__ sample_base) {
+  if (sample_base) sample0 += *sample_base;      // device-resident Philox sample-id base (mauv_set_sample_base)
   __shared__ float red[8][32][9];
   const int ql = threadIdx.x & 31, gl = threadIdx.x >> 5;
   const long long quad = static_cast<long long>(blockIdx.x) * 32 + ql;
@@ -538,6 +540,7 @@ struct LinG {
   const float* gy; long long gy_sg; int gy_sb;    // [G][B][out]
   const float* mu_w; const float* rho_w; const float* eps_w; const float* rho_b; const float* eps_b;
   uint64_t seed; uint32_t layer_id, sample0;
+  const unsigned int* sample_base;     // optional device word added to the sample ids (mauv_set_sample_base)
   int G, B, in, out, stale, accumulate;
   float* gx; long long gx_sg; int gx_sb;          // [G][B][in] (= or +=)
   float* gmu_w; float* grho_w; float* gmu_b; float* grho_b;
@@ -558,7 +561,7 @@ linear_bwd_data_group_kernel(const LinG p) {
     float w = 0.f;
     if (ow < p.out && i < p.in) {
       const long long e = static_cast<long long>(ow) * p.in + i;
-      const float z = ew ? ew[e] : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
+      const float z = ew ? ew[e] : philox_normal(p.seed, p.layer_id, (p.sample0 + (p.sample_base ? *p.sample_base : 0u)) + g, static_cast<uint64_t>(e));
       w = fmaf(softplus_ref(p.rho_w[e]), z, p.mu_w[e]);
     }
     ws[ty][tx] = w;
@@ -604,12 +607,12 @@ linear_bwd_weight_group_kernel(const LinG p) {
     if (!p.stale) {
       if (live) {
         const float z = p.eps_w ? p.eps_w[static_cast<long long>(g) * p.out * p.in + e]
-                                : philox_normal(p.seed, p.layer_id, p.sample0 + g, static_cast<uint64_t>(e));
+                                : philox_normal(p.seed, p.layer_id, (p.sample0 + (p.sample_base ? *p.sample_base : 0u)) + g, static_cast<uint64_t>(e));
         ar = fmaf(acc, z, ar);
       }
       if (bias_lane) {
         const float z = p.eps_b ? p.eps_b[static_cast<long long>(g) * p.out + o]
-                                : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + g, static_cast<uint64_t>(o));
+                                : philox_normal(p.seed, p.layer_id | 0x80000000u, (p.sample0 + (p.sample_base ? *p.sample_base : 0u)) + g, static_cast<uint64_t>(o));
         br = fmaf(accb, z, br);
       }
     }
@@ -618,7 +621,7 @@ linear_bwd_weight_group_kernel(const LinG p) {
   if (live) {
     if (p.stale) {
       const float z = p.eps_w ? p.eps_w[static_cast<long long>(gl) * p.out * p.in + e]
-                              : philox_normal(p.seed, p.layer_id, p.sample0 + gl, static_cast<uint64_t>(e));
+                              : philox_normal(p.seed, p.layer_id, (p.sample0 + (p.sample_base ? *p.sample_base : 0u)) + gl, static_cast<uint64_t>(e));
       ar = am * z;
     }
     const float ex = expf(p.rho_w[e]);
@@ -628,7 +631,7 @@ linear_bwd_weight_group_kernel(const LinG p) {
   if (bias_lane) {
     if (p.stale) {
       const float z = p.eps_b ? p.eps_b[static_cast<long long>(gl) * p.out + o]
-                              : philox_normal(p.seed, p.layer_id | 0x80000000u, p.sample0 + gl, static_cast<uint64_t>(o));
+                              : philox_normal(p.seed, p.layer_id | 0x80000000u, (p.sample0 + (p.sample_base ? *p.sample_base : 0u)) + gl, static_cast<uint64_t>(o));
       br = bm * z;
     }
     const float ex = expf(p.rho_b[o]);
@@ -880,11 +883,11 @@ int mauv_wgrad_finalize_group(const void* dw_partial, int partial_f32, int G, in
   if (partial_f32)
     wgrad_finalize_group_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
-        sample0, stale_eps, grad_mu, grad_rho);
+        sample0, stale_eps, grad_mu, grad_rho, mauv_sample_base());
   else
     wgrad_finalize_group_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(dw_partial), G, splits, cout, cin, kh, kw, k_pad, inv_alpha, scale, rho, eps, seed, layer_id,
-        sample0, stale_eps, grad_mu, grad_rho);
+        sample0, stale_eps, grad_mu, grad_rho, mauv_sample_base());
   MAUV_LAUNCH_CHECK("wgrad_finalize_group_kernel");
   return MAUV_OK;
 }
@@ -902,6 +905,7 @@ int mauv_sampled_linear_bwd_group_f32(const float* x, long long x_sg, int x_sb, 
   p.x = x; p.x_sg = x_sg; p.x_sb = x_sb; p.gy = gy; p.gy_sg = gy_sg; p.gy_sb = gy_sb;
   p.mu_w = mu_w; p.rho_w = rho_w; p.eps_w = eps_w; p.rho_b = rho_b; p.eps_b = eps_b;
   p.seed = seed; p.layer_id = layer_id; p.sample0 = sample0; p.G = G; p.B = B; p.in = in_features; p.out = out_features;
+  p.sample_base = mauv_sample_base();
   p.stale = stale_eps; p.accumulate = accumulate_gx; p.gx = gx; p.gx_sg = gx_sg; p.gx_sb = gx_sb;
   p.gmu_w = grad_mu_w; p.grho_w = grad_rho_w; p.gmu_b = grad_mu_b; p.grho_b = grad_rho_b;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

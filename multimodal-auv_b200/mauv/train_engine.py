@@ -93,6 +93,12 @@ class TrainEngine(MCEngine):
         # backward walk (bit-identical fp16 values; one layer's copies alive at a time). MAUV_KEEP_WEIGHT_SAMPLES=1 keeps them
         # on the tape instead (4.4 GB at cfg3) and saves the re-sampling launches (~5 % of the step).
         self.keep_weight_samples = os.environ.get("MAUV_KEEP_WEIGHT_SAMPLES", "0") == "1"
+        # One ELBO step is ~2 300 C-ABI calls; Python enqueues them at ~57 us each (~130 ms), which is longer than the GPU
+        # needs for cfg3 (~115 ms). The step is therefore recorded once per (shapes, S, kl_scale) as a CUDA graph and
+        # replayed: inputs / labels are copied into static buffers and the Philox sample ids come from a device-resident
+        # base word (ops.sample_base), so every replay draws fresh eps. The first step with a new key runs eagerly.
+        self.use_graph = os.environ.get("MAUV_TRAIN_GRAPH", "1") != "0"
+        self._graphs = {}
         self._update_running = True
         self._flat: Optional[FlatGrads] = None
         self._fused = {}        # id(optimizer) -> FusedAdam | None (optimizer_step)
@@ -422,10 +428,54 @@ class TrainEngine(MCEngine):
         if stale and G < S:
             raise _lib.MauvError("reference stale-eps mode needs all S samples in one group (raise max_group / free memory)")
         self._ensure_grads()
+        if self.use_graph and eps is None and not recompute:
+            return self._step_graphed(xs, labels, S, G, kl_scale, sample0, seed, stale)
         with ops.on_current_stream():
             if recompute:
                 return self._step_recompute(xs, labels, S, G, kl_scale, sample0, eps, seed, stale)
             return self._step(xs, labels, S, G, kl_scale, sample0, eps, seed, stale)
+
+    def _step_graphed(self, xs, labels, S, G, kl_scale, sample0, seed, stale) -> dict:
+        """Replay of the recorded step (see __init__). Returned tensors are the graph's static outputs: valid until the
+        next step with the same key (the scalars are cloned)."""
+        import logging
+        p0 = next(self.model.parameters())
+        key = (tuple(tuple(x.shape) for x in xs), S, G, float(kl_scale), seed, stale, p0.data_ptr(),
+               p0.grad.data_ptr() if p0.grad is not None else 0)
+        ent = self._graphs.get(key)
+        if ent is None:                      # first step with this key: eager (also runs every lazy initialisation)
+            self._graphs[key] = {}
+            with ops.on_current_stream():
+                return self._step(xs, labels, S, G, kl_scale, sample0, None, seed, stale)
+        if "graph" not in ent:
+            try:
+                self._graphs = {key: ent}    # one recorded step at a time: a graph pins its tape (tens of GB) in a private pool
+                torch.cuda.empty_cache()
+                ent["x"] = [torch.empty_like(x) for x in xs]
+                ent["labels"] = torch.empty_like(labels)
+                ent["base"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                n0 = ops.launch_count
+                with torch.cuda.graph(graph), ops.sample_base(ent["base"]), ops.on_current_stream():
+                    ent["out"] = self._step(ent["x"], ent["labels"], S, G, kl_scale, 0, None, seed, stale)
+                ent["launches"] = ops.launch_count - n0
+                ent["graph"] = graph
+            except Exception as e:           # still the CUDA path: the step simply stays Python-driven
+                logging.warning(f"TrainEngine: CUDA-graph capture of the training step failed ({e}); running eagerly")
+                self.use_graph = False
+                self._graphs = {}
+                with ops.on_current_stream():
+                    return self._step(xs, labels, S, G, kl_scale, sample0, None, seed, stale)
+        for d, x in zip(ent["x"], xs):
+            d.copy_(x, non_blocking=True)
+        ent["labels"].copy_(labels, non_blocking=True)
+        ent["base"].fill_(((sample0 & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000)       # uint32 bit pattern in an int32 word
+        ent["graph"].replay()
+        ops.launch_count += ent["launches"]
+        o = ent["out"]
+        return {"loss": o["loss"].clone(), "ce": o["ce"].clone(), "kl": o["kl"].clone(), "mean_logit": o["mean_logit"],
+                "logits": o["logits"]}
 
     def _step_recompute(self, xs, labels, S, G, kl_scale, sample0, eps, seed, stale) -> dict:
         """Memory-bounded variant: the tapes of all S samples do not fit, so phase 1 walks forward for the logits only and

@@ -36,7 +36,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def philox_normal(n: int, seed: int, layer_id: int, sample_id: int) -> np.ndarray:
-    """float32[n] identical (up to libm ulps) to mauv_philox_normal_f32."""
+    """float32[n]: mauv_philox_normal_f32 with exact libm (the device evaluates log / sqrt / sin / cos on the SFU: the two
+    agree to ~1e-6 absolute, checked by tests/gpu_bringup.py t_philox at 1e-5 of the maximum)."""
     quads = (n + 3) // 4
     q = np.arange(quads, dtype=np.uint64)
     c0 = (q & MASK).astype(np.uint32)

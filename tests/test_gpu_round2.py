@@ -303,3 +303,46 @@ def test_full_depth_gradients_vs_fp32_oracle_and_conditioning_floor(bu, kind):
     assert r["trunk_p10"][0] >= 0.60, r["trunk_p10"]
     import math
     assert all(math.isfinite(x[0]) for x in r["engine"])
+
+
+def test_train_step_cuda_graph_replay_is_bit_identical_to_the_eager_step(bu):
+    """TrainEngine records the ELBO step as a CUDA graph on the second call with the same (shapes, S, kl_scale); the Philox
+    sample ids come from a device word, inputs / labels from static buffers. A replay must reproduce the eager step bit for
+    bit - gradients, loss, BN running statistics - for the same sample ids, and draw different eps for different ids."""
+    import bnn_oracle as O
+    from mauv.bayesian import manual_seed
+    from mauv.train_engine import TrainEngine
+    _, model = bu.build_pair("unimodal_shallow")
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    batches = [O.synthetic_batch(4, seed=50 + i, size=64) for i in range(3)]
+    manual_seed(11)
+
+    def run(eng, i, sample0):
+        model.load_state_dict(state0)
+        for p in model.parameters():
+            if p.grad is not None:
+                p.grad.zero_()
+        img, _, _, labels = batches[i]
+        res = eng.step([img.cuda()], labels, 3, 1e-4, sample0=sample0)
+        torch.cuda.synchronize()
+        return ({n: p.grad.clone() for n, p in model.named_parameters()}, res["loss"].item(),
+                {k: v.clone() for k, v in model.state_dict().items() if "running" in k})
+
+    eager = TrainEngine(model)
+    eager.use_graph = False
+    ref = run(eager, 2, 7)
+    other = run(eager, 2, 8)
+    eng = TrainEngine(model)
+    assert eng.use_graph
+    run(eng, 0, 3)                       # eager first call
+    run(eng, 1, 5)                       # capture + first replay
+    ent = next(iter(eng._graphs.values()))
+    assert "graph" in ent and eng.use_graph, "the step was not captured"
+    got = run(eng, 2, 7)                 # replay with new inputs, labels and sample ids
+    assert got[1] == ref[1]
+    for n in ref[0]:
+        assert torch.equal(got[0][n], ref[0][n]), n
+    for k in ref[2]:
+        assert torch.equal(got[2][k], ref[2][k]), k
+    got8 = run(eng, 2, 8)
+    assert got8[1] == other[1] and got8[1] != got[1]
