@@ -12,9 +12,15 @@ namespace {
 // conv (Cin = 1 or 3 cannot feed TMA: a pixel is < 16 bytes). K order (r, s, c). The
 // matrix depends only on the input batch, so one build serves all S MC samples.
 // ---------------------------------------------------------------------------
+// CT / KWT > 0: channel count / filter width known at compile time (the reference's stems: 7x7 over 3 or 1 channels), so the
+// k -> (r, s, c) decomposition is multiply-shift arithmetic instead of two integer divisions per element (the kernel is
+// instruction-bound: ~200 instructions per 16 output bytes in the generic form).
+template <int CT, int KWT>
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kh, int kw,
+stem_im2col_kernel(const float* __restrict__ x, int B, int C_rt, int H, int W, int kh, int kw_rt,
                    int stride, int pad, int Ho, int Wo, int k_pad, __half* __restrict__ out) {
+  const int C = CT > 0 ? CT : C_rt;
+  const int kw = KWT > 0 ? KWT : kw_rt;
   // one thread per (row, 8-wide k chunk)
   const int chunks = k_pad / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -22,9 +28,11 @@ stem_im2col_kernel(const float* __restrict__ x, int B, int C, int H, int W, int 
   if (idx >= rows * chunks) return;
   const long long row = idx / chunks;
   const int ch = static_cast<int>(idx - row * chunks);
-  const int q = static_cast<int>(row % Wo);
-  const int p = static_cast<int>((row / Wo) % Ho);
-  const int b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
+  const unsigned row32 = static_cast<unsigned>(row);             // B*Ho*Wo < 2^31 (checked on the host)
+  const unsigned pq = row32 / static_cast<unsigned>(Wo);
+  const int q = static_cast<int>(row32 - pq * Wo);
+  const int b = static_cast<int>(pq / static_cast<unsigned>(Ho));
+  const int p = static_cast<int>(pq - static_cast<unsigned>(b) * Ho);
   const int K = kh * kw * C;
   __align__(16) __half v[8];
 #pragma unroll
@@ -413,8 +421,6 @@ bn_relu_maxpool_kernel(const uint4* __restrict__ y, const float2* __restrict__ s
       const float4 tt = __ldg(s4 + j);
       sc[2 * j] = tt.x; sh[2 * j] = tt.y; sc[2 * j + 1] = tt.z; sh[2 * j + 1] = tt.w;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
     uint4 v[9];
     bool ok[9];
 #pragma unroll
@@ -426,17 +432,29 @@ bn_relu_maxpool_kernel(const uint4* __restrict__ y, const float2* __restrict__ s
         if (ok[dr * 3 + ds]) v[dr * 3 + ds] = __ldg(y + ((n * H + h) * W + w) * cvec + cv);
       }
     }
+    // x -> x*scale + shift is monotone (increasing for scale >= 0, decreasing otherwise, rounding included), so the window
+    // maximum of the affine values is the affine value of the window max (or min) of the RAW fp16 inputs: 9 x 8 packed
+    // half2 min/max instead of 9 x 8 conversions + FMAs + fp32 max. The centre tap (index 4) is always inside the image.
+    __half2 mx[4], mn[4];
+    {
+      const __half2* c2 = reinterpret_cast<const __half2*>(&v[4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { mx[j] = c2[j]; mn[j] = c2[j]; }
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      if (ok[k]) {
-        float f[8];
-        unpack8(v[k], f);
+      if (k != 4 && ok[k]) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(f[j], sc[j], sh[j]));
+        for (int j = 0; j < 4; ++j) { mx[j] = __hmax2(mx[j], h2[j]); mn[j] = __hmin2(mn[j], h2[j]); }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], 0.f);  // relu(max) == max(relu)
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(mx[j]), b = __half22float2(mn[j]);
+      m[2 * j] = fmaxf(fmaf(sc[2 * j] >= 0.f ? a.x : b.x, sc[2 * j], sh[2 * j]), 0.f);              // relu(max) == max(relu)
+      m[2 * j + 1] = fmaxf(fmaf(sc[2 * j + 1] >= 0.f ? a.y : b.y, sc[2 * j + 1], sh[2 * j + 1]), 0.f);
+    }
     out[((n * Ho + p) * Wo + q) * cvec + cv] = pack8(m);
   }
 }
@@ -512,9 +530,14 @@ int mauv_stem_im2col_f16(const float* x_nchw, int B, int C, int H, int W, int kh
   MAUV_CHECK_ARG(x_nchw && out, "mauv_stem_im2col_f16: null pointer");
   MAUV_CHECK_ARG(k_pad % 8 == 0 && k_pad >= kh * kw * C, "mauv_stem_im2col_f16: bad k_pad=%d", k_pad);
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  MAUV_CHECK_ARG(static_cast<long long>(B) * Ho * Wo < (1LL << 31), "mauv_stem_im2col_f16: too many output pixels");
   const long long work = static_cast<long long>(B) * Ho * Wo * (k_pad / 8);
-  stem_im2col_kernel<<<static_cast<unsigned>(ceil_div_i64(work, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, B, C, H, W, kh, kw, stride, pad, Ho, Wo, k_pad, static_cast<__half*>(out));
+  const unsigned grid = static_cast<unsigned>(ceil_div_i64(work, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* o = static_cast<__half*>(out);
+  if (kw == 7 && C == 3) stem_im2col_kernel<3, 7><<<grid, 256, 0, st>>>(x_nchw, B, C, H, W, kh, kw, stride, pad, Ho, Wo, k_pad, o);
+  else if (kw == 7 && C == 1) stem_im2col_kernel<1, 7><<<grid, 256, 0, st>>>(x_nchw, B, C, H, W, kh, kw, stride, pad, Ho, Wo, k_pad, o);
+  else stem_im2col_kernel<0, 0><<<grid, 256, 0, st>>>(x_nchw, B, C, H, W, kh, kw, stride, pad, Ho, Wo, k_pad, o);
   MAUV_LAUNCH_CHECK("stem_im2col_kernel");
   return MAUV_OK;
 }
