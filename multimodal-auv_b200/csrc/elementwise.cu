@@ -317,31 +317,35 @@ colsum_kernel(const uint4* __restrict__ x, long long per_sample_vec, int C, floa
 // block = 32 elements x 8 partial lanes: element e < K*K is an entry of S (partials `splits` apart by K*K), element
 // K*K + c is column sum c (partials `nblk` apart by K); every lane sums its partials p = ty, ty+8, .. in double, the 8 lanes
 // are combined in a fixed order (deterministic). Short dependent chains instead of one thread walking 256 partials.
+constexpr int GRAM_REDUCE_REPS = 8;
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const float* __restrict__ gram, int splits, long long kk /* K*K */, const float* __restrict__ colsum,
                    int nblk, int K, float* __restrict__ S /*[G][K*K]*/, float* __restrict__ s1 /*[G][K]*/) {
   __shared__ double red[8][33];
   const int g = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long e = static_cast<long long>(blockIdx.x) * 32 + tx;
-  double acc = 0.0;
-  if (e < kk) {
-    const float* src = gram + static_cast<long long>(g) * splits * kk + e;
-    for (int sp = ty; sp < splits; sp += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
-  } else if (e < kk + K) {
-    const float* src = colsum + static_cast<long long>(g) * nblk * K + (e - kk);
-    for (int b = ty; b < nblk; b += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(b) * K));
-  }
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && e < kk + K) {
+  for (int rep = 0; rep < GRAM_REDUCE_REPS; ++rep) {        // a block covers GRAM_REDUCE_REPS x 32 consecutive elements
+    const long long e = (static_cast<long long>(blockIdx.x) * GRAM_REDUCE_REPS + rep) * 32 + tx;
+    double acc = 0.0;
+    if (e < kk) {
+      const float* src = gram + static_cast<long long>(g) * splits * kk + e;
+      for (int sp = ty; sp < splits; sp += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
+    } else if (e < kk + K) {
+      const float* src = colsum + static_cast<long long>(g) * nblk * K + (e - kk);
+      for (int b = ty; b < nblk; b += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(b) * K));
+    }
+    __syncthreads();
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && e < kk + K) {
 #pragma unroll
-    for (int j = 1; j < 8; ++j) acc += red[j][tx];
-    if (e < kk) S[static_cast<long long>(g) * kk + e] = static_cast<float>(acc);
-    else s1[static_cast<long long>(g) * K + (e - kk)] = static_cast<float>(acc);
+      for (int j = 1; j < 8; ++j) acc += red[j][tx];
+      if (e < kk) S[static_cast<long long>(g) * kk + e] = static_cast<float>(acc);
+      else s1[static_cast<long long>(g) * K + (e - kk)] = static_cast<float>(acc);
+    }
   }
 }
 
-constexpr int GQ_N = 32;      // output channels per block (8 warps x 4)
+constexpr int GQ_N = 64;      // output channels per block (8 warps x 8): 2 broadcast LDS.128 of weights per 8 FMAs
 constexpr int GQ_ROWS = 32;   // rows of S staged per step (one per lane)
 __global__ void __launch_bounds__(256)
 gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, const __half* __restrict__ w /*[G][N][K]*/,
@@ -358,8 +362,8 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
     wt[c * GQ_N + nn] = n < N ? __half2float(w[(static_cast<long long>(g) * N + n) * K + c]) : 0.f;
   }
   const float* Sg = S + static_cast<long long>(g) * K * K;
-  double q[4] = {0.0, 0.0, 0.0, 0.0};
-  const float* wq = wt + warp * 4;
+  double q[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const float* wq = wt + warp * 8;
   for (int r0 = 0; r0 < K; r0 += GQ_ROWS) {
     __syncthreads();
     for (int i = threadIdx.x; i < GQ_ROWS * K; i += 256) {
@@ -367,35 +371,38 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
       Ss[r * pitch + c] = (r0 + r < K) ? Sg[static_cast<long long>(r0 + r) * K + c] : 0.f;
     }
     __syncthreads();
-    // lane = row r0 + lane of S: t[j] = S[row][:] . w_j for this warp's 4 channels, then q_j += w_j[row] * t[j]
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    // lane = row r0 + lane of S: t[j] = S[row][:] . w_j for this warp's 8 channels, then q_j += w_j[row] * t[j]
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float* srow = Ss + lane * pitch;
 #pragma unroll 4
     for (int c = 0; c < K; ++c) {
       const float sv = srow[c];
-      const float4 w4 = *reinterpret_cast<const float4*>(wq + c * GQ_N);    // broadcast
-      t[0] = fmaf(sv, w4.x, t[0]); t[1] = fmaf(sv, w4.y, t[1]); t[2] = fmaf(sv, w4.z, t[2]); t[3] = fmaf(sv, w4.w, t[3]);
+      const float4 wa = *reinterpret_cast<const float4*>(wq + c * GQ_N);        // broadcast
+      const float4 wb = *reinterpret_cast<const float4*>(wq + c * GQ_N + 4);
+      t[0] = fmaf(sv, wa.x, t[0]); t[1] = fmaf(sv, wa.y, t[1]); t[2] = fmaf(sv, wa.z, t[2]); t[3] = fmaf(sv, wa.w, t[3]);
+      t[4] = fmaf(sv, wb.x, t[4]); t[5] = fmaf(sv, wb.y, t[5]); t[6] = fmaf(sv, wb.z, t[6]); t[7] = fmaf(sv, wb.w, t[7]);
     }
     if (r0 + lane < K) {
-      const float4 w4 = *reinterpret_cast<const float4*>(wq + (r0 + lane) * GQ_N);
-      q[0] += static_cast<double>(w4.x) * t[0]; q[1] += static_cast<double>(w4.y) * t[1];
-      q[2] += static_cast<double>(w4.z) * t[2]; q[3] += static_cast<double>(w4.w) * t[3];
+      const float* wr = wq + (r0 + lane) * GQ_N;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] += static_cast<double>(wr[j]) * t[j];
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) q[j] = warp_sum_d(q[j]);
+  for (int j = 0; j < 8; ++j) q[j] = warp_sum_d(q[j]);
   // first moment: w_n . s1
-  double m[4] = {0.0, 0.0, 0.0, 0.0};
+  double m[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int c = lane; c < K; c += 32) {
     const double sv = s1[static_cast<long long>(g) * K + c];
-    const float4 w4 = *reinterpret_cast<const float4*>(wq + c * GQ_N);
-    m[0] += sv * w4.x; m[1] += sv * w4.y; m[2] += sv * w4.z; m[3] += sv * w4.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] += sv * wq[c * GQ_N + j];
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) m[j] = warp_sum_d(m[j]);
-  if (lane < 4) {
-    const int n = n0 + warp * 4 + lane;
-    if (n < N) out[static_cast<long long>(g) * N + n] = make_double2(m[lane], q[lane]);
+  for (int j = 0; j < 8; ++j) m[j] = warp_sum_d(m[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + warp * 8 + j;
+    if (lane == j && n < N) out[static_cast<long long>(g) * N + n] = make_double2(m[j], q[j]);
   }
 }
 
@@ -700,7 +707,7 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
   const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;
   double2* sums = reinterpret_cast<double2*>(static_cast<float*>(ws) + f);
   const long long kk = static_cast<long long>(K) * K;
-  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32)), G);
+  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32 * GRAM_REDUCE_REPS)), G);
   gram_reduce_kernel<<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
   MAUV_LAUNCH_CHECK("gram_reduce_kernel");
   const int smem = (GQ_N * K + GQ_ROWS * (K + 1)) * static_cast<int>(sizeof(float));

@@ -65,9 +65,9 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
 
   const bool active = tid < rows;
   // variance by shifted sums: d = p - p(sample 0) keeps sum(d^2) - sum(d)^2/S free of cancellation
-  float sum_p[NC], sum_l[NC], p0[NC], sd[NC], sdd[NC];
+  float sum_l[NC], p0[NC], sd[NC], sdd[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) { sum_p[c] = 0.f; sum_l[c] = 0.f; p0[c] = 0.f; sd[c] = 0.f; sdd[c] = 0.f; }
+  for (int c = 0; c < NC; ++c) { sum_l[c] = 0.f; p0[c] = 0.f; sd[c] = 0.f; sdd[c] = 0.f; }
   float sum_h = 0.f;
   const float* my_row = mc_smem + tid * C;
   for (int s = 0; s < S; ++s) {
@@ -88,16 +88,18 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
       // and the last term is C_eff * eps to first order (eps = 1e-7 / 1e-8; classes with p_c << eps contribute
       // -p_c log(eps) ~ 0 exactly and -eps in the expansion): |error| <= C * eps = 7e-7, far inside the 1e-5 tolerance the
       // statistics are checked to. p_c = 0 (underflow) is harmless in this form: e_c u_c = 0 * finite.
-      float z = 0.f, eu = 0.f;
-      int n_live = 0;
+      // (base-2 arithmetic: v_c = (x_c - max) * log2(e) in one FMA, e_c = ex2(v_c); the eps correction is taken as C * eps for
+      // every row-sample: a class with p_c << eps contributes ~0 exactly and -eps here, |difference| <= C * eps as well)
+      const float kLog2e = 1.4426950408889634f;
+      const float nmx = -mx * kLog2e;
+      float z = 0.f, ev = 0.f;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (CC > 0 || c < C) {
           sum_l[c] += x[c];
-          const float u = x[c] - mx;
-          x[c] = __expf(u);
-          eu = fmaf(x[c], u, eu);
-          n_live += (u > -16.f) ? 1 : 0;          // p_c >= ~1e-7: the eps correction applies
+          const float v = fmaf(x[c], kLog2e, nmx);
+          x[c] = exp2f(v);
+          ev = fmaf(x[c], v, ev);
         } else {
           x[c] = 0.f;
         }
@@ -109,13 +111,13 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
         if (CC > 0 || c < C) {
           const float pc = x[c] * inv_z;
           if (s == 0) p0[c] = pc;
-          sum_p[c] += pc;
-          const float d = pc - p0[c];
+          const float d = pc - p0[c];          // sum_s p = S * p0 + sum_s d (recovered after the loop)
           sd[c] += d;
           sdd[c] = fmaf(d, d, sdd[c]);
         }
       }
-      sum_h += __logf(z) - eu * inv_z - static_cast<float>(n_live) * eps_entropy;
+      // ln z - (sum e u) / z  with u = v * ln 2
+      sum_h += 0.6931471805599453f * (__log2f(z) - ev * inv_z);
     }
     __syncthreads();   // slab s % MC_STAGES is refilled by the next iteration's issue()
   }
@@ -131,7 +133,7 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     if ((CC > 0 || c < C) && active) {
-      const float mp = sum_p[c] * inv_s;
+      const float mp = fmaf(sd[c], inv_s, p0[c]);
       const float ml = sum_l[c] * inv_s;
       st_p[tid * C + c] = mp;
       st_l[tid * C + c] = ml;
@@ -146,7 +148,7 @@ mc_reduce_kernel(const float* __restrict__ logits, int S, long long B, int Crt, 
   if (mean_logit) for (int i = tid; i < nf; i += MC_ROWS) mean_logit[b0 * C + i] = st_l[i];
   if (!active) return;
   const long long b = b0 + tid;
-  const float al = sum_h * inv_s;
+  const float al = sum_h * inv_s - static_cast<float>(C) * eps_entropy;
   if (argmax_prob) argmax_prob[b] = arg_p;
   if (argmax_logit) argmax_logit[b] = arg_l;
   if (pred_entropy) pred_entropy[b] = hp;
