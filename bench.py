@@ -554,7 +554,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_FULL)
     ap.add_argument("--samples", type=int, default=S_FULL)
-    ap.add_argument("--group", type=int, default=10)
+    ap.add_argument("--group", type=int, default=15, help="MC samples walked together (15: two walks at N=1, one at N>=2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the one-step fp32-class (x3) sub-record")
     ap.add_argument("--no-train-leg", action="store_true", help="skip the cfg3 ELBO training sub-record of the default line")

@@ -257,12 +257,13 @@ kl_kernel(const KlTensor* __restrict__ table, const long long* __restrict__ chun
   }
 }
 
+// (one warp, strided partial sums + a fixed-order shuffle tree: deterministic; a single thread walking the 1 184 block
+// partials took ~40 us, a quarter of the whole forward KL)
 __global__ void kl_final_kernel(const double* __restrict__ block_partial, int n, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) s += block_partial[i];
-    *out = static_cast<float>(s);
-  }
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += block_partial[i];
+  s = warp_sum_d(s);
+  if (threadIdx.x == 0) *out = static_cast<float>(s);
 }
 
 }  // namespace
