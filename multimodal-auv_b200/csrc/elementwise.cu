@@ -349,7 +349,7 @@ constexpr int GQ_N = 64;      // output channels per block (8 warps x 8): 2 broa
 constexpr int GQ_ROWS = 32;   // rows of S staged per step (one per lane)
 __global__ void __launch_bounds__(256)
 gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, const __half* __restrict__ w /*[G][N][K]*/,
-                     int N, int K, double2* __restrict__ out /*[G][1][N] (sum, sum of squares)*/) {
+                     int N, int K, double2* __restrict__ out /*[G][K/32][N] (sum, sum of squares) partials per row tile*/) {
   extern __shared__ __align__(16) float gq_smem[];
   const int pitch = K + 1;                         // lanes read different rows of S at the same column: odd pitch
   float* wt = gq_smem;                             // [K][GQ_N]   this block's weights, transposed: 4 channels = one LDS.128
@@ -364,7 +364,11 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
   const float* Sg = S + static_cast<long long>(g) * K * K;
   double q[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const float* wq = wt + warp * 8;
-  for (int r0 = 0; r0 < K; r0 += GQ_ROWS) {
+  // blockIdx.z = row tile of S: the K/32 tiles of one (sample, channel block) run as separate blocks (8x the parallelism
+  // at K = 256; one block walking all tiles left the SMs at 13 % occupancy) and bn_finalize_kernel adds the partials
+  const int n_rt = gridDim.z;
+  {
+    const int r0 = blockIdx.z * GQ_ROWS;
     __syncthreads();
     for (int i = threadIdx.x; i < GQ_ROWS * K; i += 256) {
       const int r = i / K, c = i - r * K;
@@ -390,9 +394,9 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) q[j] = warp_sum_d(q[j]);
-  // first moment: w_n . s1
+  // first moment: w_n . s1 (row tile 0 only)
   double m[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int c = lane; c < K; c += 32) {
+  for (int c = lane; c < K && blockIdx.z == 0; c += 32) {
     const double sv = s1[static_cast<long long>(g) * K + c];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] += sv * wq[c * GQ_N + j];
@@ -402,7 +406,7 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int n = n0 + warp * 8 + j;
-    if (lane == j && n < N) out[static_cast<long long>(g) * N + n] = make_double2(m[j], q[j]);
+    if (lane == j && n < N) out[(static_cast<long long>(g) * n_rt + blockIdx.z) * N + n] = make_double2(m[j], q[j]);
   }
 }
 
@@ -690,7 +694,7 @@ int mauv_colsum_f16(const void* x, int G, long long M, int C, float* colsum_part
 // workspace of mauv_bn_stats_from_gram: S [G][K*K] + s1 [G][K] floats, then double2 [G][N]
 long long mauv_bn_stats_from_gram_ws_bytes(int G, int N, int K) {
   const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;   // 16-byte aligned
-  return f * 4 + static_cast<long long>(G) * N * sizeof(double2);
+  return f * 4 + static_cast<long long>(G) * ((K + GQ_ROWS - 1) / GQ_ROWS) * N * sizeof(double2);
 }
 
 int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* colsum_partial, int nblk, const void* w,
@@ -716,11 +720,12 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
     MAUV_CUDA(cudaFuncSetAttribute(gram_quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  dim3 g2((N + GQ_N - 1) / GQ_N, G);
+  const int n_rt = (K + GQ_ROWS - 1) / GQ_ROWS;
+  dim3 g2((N + GQ_N - 1) / GQ_N, G, n_rt);
   gram_quadform_kernel<<<g2, 256, smem, st>>>(S, s1, static_cast<const __half*>(w), N, K, sums);
   MAUV_LAUNCH_CHECK("gram_quadform_kernel");
   dim3 fblock(32, G < 16 ? G : 16);
-  bn_finalize_kernel<<<(N + 31) / 32, fblock, 0, st>>>(sums, G, 1, N, count, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<<<(N + 31) / 32, fblock, 0, st>>>(sums, G, n_rt, N, count, gamma, beta, eps, momentum, running_mean,
                                                        running_var, num_batches_tracked,
                                                        reinterpret_cast<float2*>(scale_shift),
                                                        reinterpret_cast<float2*>(batch_stats));
