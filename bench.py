@@ -287,7 +287,7 @@ def run_ours(args):
             fam[b] = (fc + c, ft + t)
         # all launches of the tcgen05 kernels (gemm_f16_tc_kernel and its padded-stream sibling for layer1's 3x3 conv)
         tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16",
-              "mauv_wgrad_f16")     # (inference: the K x K second-moment contractions of the closed-form BN statistics)
+              "mauv_wgrad_f16", "mauv_stem_conv_pool_f16")     # (inference: the K x K second-moment contractions of the closed-form BN statistics)
         conv_calls = sum(fam.get(k, (0, 0.0))[0] for k in tc)
         conv_ms = sum(fam.get(k, (0, 0.0))[1] for k in tc)
         if args.detail:
@@ -301,7 +301,7 @@ def run_ours(args):
                 if all(q in toks for q in "GMNK"):
                     g_, m_, n_, k_ = (int(toks[q]) for q in "GMNK")
                     gf = 2.0 * g_ * m_ * n_ * k_ * c / 1e9
-                    kin = k_ if "x" not in tag or tag.split()[-1].startswith("1x1") else k_ // 9
+                    kin = k_ // 9 if ("3x3" in tag or "stream" in tag) else k_
                     gb = g_ * m_ * (kin + n_) * 2 * c / 1e9
                 elif all(q in toks for q in "GMC"):
                     g_, m_, c_ = (int(toks[q]) for q in "GMC")
@@ -343,7 +343,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * 5 * 4},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_f16_tc_kernel + conv3x3_c64_stream_kernel (tcgen05 implicit-GEMM conv, all 159 convs)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_f16_tc_kernel + conv3x3_c64_stream_kernel + stem_conv_pool_kernel (tcgen05 implicit-GEMM conv, all 159 convs)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_source": peak_src,
                          # mean DRAM read+write bytes per launch of these kernels in one step, from the committed ncu
@@ -351,8 +351,8 @@ def run_ours(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum); null when no capture of this tree exists
                          "traffic": load_traffic(),
                          "note": "algorithmic FLOPs (31.824 GFLOP per triplet-sample, recompute passes not counted) / "
-                                 "summed launch durations; by shape the kernel runs at 0.89-0.94 of the tensor peak "
-                                 "(K >= 2304) and at ~0.87 of the 3.9 TB/s HBM write-only peak on the wide-N 1x1 layers",
+                                 "summed launch durations; the kernel is tensor-bound on the K >= 1152 shapes (0.9 of the "
+                                 "sustained peak at K >= 2304) and HBM-bound on the 1x1 layers of layer1/2 (see per_launch)",
                          "launches_per_step": conv_calls, "avg_launch_ms": conv_ms / max(conv_calls, 1),
                          "share_of_step": conv_ms / total_prof,
                          # the kernel is tensor-bound on some shapes and HBM-bound on others: per launch,
@@ -389,7 +389,10 @@ def tc_launch_model(base: str, tag: str):
     g, m, n, k = (toks[q] for q in "GMNK")
     flops = 2.0 * g * m * n * k
     w_bytes = g * n * k * 2
-    if base == "mauv_conv3x3_c64_f16":
+    if base == "mauv_stem_conv_pool_f16":                      # A shared by all samples; only the pooled (1/4) output is written
+        a_bytes = m * k * 2
+        y_bytes = g * (m // 4) * n * 2
+    elif base == "mauv_conv3x3_c64_f16":
         a_bytes = g * m * 64 * 2
         y_bytes = g * m * n * 2
     elif base == "mauv_conv2d_im2col_f16":

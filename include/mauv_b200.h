@@ -127,6 +127,14 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
                             float* scale_shift, float* batch_stats, void* ws, void* stream);
 int mauv_bn_relu_maxpool_f16(const void* y, const float* scale_shift, int G, int imgs_per_sample, int H,
                              int W, int C, void* out, void* stream);
+/* Inference stem in one kernel: conv1 (7x7/2, im2col matrix a0 [imgs*Ho*128][Kp] shared by all samples, w [G][64][Kp]) + the
+ * bn1 batch statistics (stats_partial [G][imgs*Ho][64][2], same layout as mauv_gemm_f16's) + the 3x3/2 max-pool taken on the RAW
+ * conv output in the epilogue (window max, or window min for channels with gamma < 0: relu(bn(.)) is monotone per channel, so
+ * maxpool(relu(bn1(y))) == relu(bn1(pool(y)))); pooled [G][imgs][Ho/2][64][64] fp16. The full-resolution conv1 output (the
+ * largest tensor of the network) never reaches HBM. Replaces conv1 / maxpool of models/base_models.py:74-76 (torchvision
+ * resnet.py _forward_impl) for 256 x 256 inputs (Wo = 128); follow with mauv_bn_finalize + mauv_bn_act_f16 on `pooled`. */
+int mauv_stem_conv_pool_f16(const void* a0, const void* w, void* pooled, float* stats_partial, const float* gamma, int G,
+                            int imgs, int Ho, int Kp, void* stream);
 int mauv_avgpool_f16(const void* x, long long N, int HW, int C, float* out, void* stream);
 int mauv_nchw_f32_to_nhwc_f16(const float* x, long long N, int C, int HW, int c_pad, void* out, void* stream);
 int mauv_nhwc_f16_to_nchw_f32(const void* x, long long N, int C, int HW, float* out, void* stream);

@@ -16,7 +16,7 @@ CSRC = HERE / "csrc"
 LIB_DIR = HERE / "mauv" / "lib"
 LIB = LIB_DIR / "libmauv_b200.so"
 
-SOURCES = ["runtime.cu", "gemm_tc.cu", "sample_weights.cu", "elementwise.cu", "head.cu", "reduce.cu", "backward.cu", "x3.cu", "train_bwd.cu", "optim.cu", "membench.cu"]
+SOURCES = ["runtime.cu", "gemm_tc.cu", "stem_pool.cu", "sample_weights.cu", "elementwise.cu", "head.cu", "reduce.cu", "backward.cu", "x3.cu", "train_bwd.cu", "optim.cu", "membench.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -38,6 +38,7 @@ SIGNATURES = {
     "mauv_bn_stats_from_gram_ws_bytes": (i64, [i32, i32, i32]),
     "mauv_bn_stats_from_gram": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "mauv_bn_relu_maxpool_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "mauv_stem_conv_pool_f16": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "mauv_avgpool_f16": (i32, [vp, i64, i32, i32, vp, vp]),
     "mauv_nchw_f32_to_nhwc_f16": (i32, [vp, i64, i32, i32, i32, vp, vp]),
     "mauv_nhwc_f16_to_nchw_f32": (i32, [vp, i64, i32, i32, vp, vp]),

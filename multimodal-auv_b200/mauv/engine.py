@@ -124,6 +124,9 @@ class MCEngine:
         # statistics of the recompute scheme in closed form: sum y = w . colsum(a), sum y^2 = w^T (a^T a) w - one K x K
         # second-moment contraction over the pixels instead of the N x K statistics pass (N = 4K)
         self.gram_stats = os.environ.get("MAUV_GRAM_STATS", "1") != "0"
+        # stem: conv1 + bn1 statistics + max-pool of the raw output in one kernel (ops.stem_conv_pool_f16): the full-resolution
+        # conv1 output never reaches HBM. 256 x 256 inputs (Wo = 128) only; other sizes take the three-kernel path.
+        self.stem_pool = os.environ.get("MAUV_STEM_POOL", "1") != "0"
 
     # Philox sample-id cursor, shared by every engine built on the same model (it lives on the model object): each
     # forward_mc / TrainEngine.step / predictor batch that is not given explicit sample ids takes the next S ids, so
@@ -274,14 +277,22 @@ class MCEngine:
         if a0 is None:
             a0 = ops.stem_im2col_f16(x_nchw, st.k, st.k, st.stride, st.pad)      # shared by all samples
         w = self._sample(st, G, s0, eps, seed)
-        y, stats = ops.gemm_f16(a0, w, stats=True, shared_a=True)                # [G, B*Ho*Wo, 64]
-        self.launches += 2
         Ho = (x_nchw.shape[2] + 2 * st.pad - st.k) // st.stride + 1
         Wo = (x_nchw.shape[3] + 2 * st.pad - st.k) // st.stride + 1
-        ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
-        x = ops.bn_relu_maxpool_f16(y.view(G * B, Ho, Wo, st.cout), ss, G)
-        self.launches += 1
-        del y
+        if self.stem_pool and Wo == 128 and Ho % 2 == 0 and st.cout == 64 and a0.shape[1] <= 192:
+            # max-pool of the RAW conv output in the conv's epilogue (window min where gamma < 0), then bn1 + ReLU on the pooled
+            # tensor: relu(bn(.)) is monotone per channel, so this equals maxpool(relu(bn1(conv1(x)))) bit for bit
+            yp, stats = ops.stem_conv_pool_f16(a0, w, B, Ho, gamma=t.stem_bn.weight.detach() if t.stem_bn.weight is not None else None)
+            ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
+            x = ops.bn_act_f16(yp, ss, G, st.cout, relu=True, out=yp)
+            self.launches += 3
+        else:
+            y, stats = ops.gemm_f16(a0, w, stats=True, shared_a=True)            # [G, B*Ho*Wo, 64]
+            self.launches += 2
+            ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
+            x = ops.bn_relu_maxpool_f16(y.view(G * B, Ho, Wo, st.cout), ss, G)
+            self.launches += 1
+            del y
         for blk in t.blocks:
             y1, ss1 = self._conv_bn(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
             c2 = blk.conv2

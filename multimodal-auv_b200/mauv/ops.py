@@ -405,6 +405,20 @@ def bn_relu_maxpool_f16(y: torch.Tensor, ss: torch.Tensor, G: int, out: Optional
     return out
 
 
+def stem_conv_pool_f16(a0: torch.Tensor, w: torch.Tensor, imgs: int, Ho: int, gamma: Optional[torch.Tensor] = None):
+    """Inference stem (256 x 256 inputs: Wo = 128): a0 [imgs*Ho*128, Kp] im2col matrix shared by all samples, w [G, 64, Kp]
+    -> (3x3/2 max-pool of the RAW conv output [G*imgs, Ho/2, 64, 64] fp16 - window min where gamma < 0 -,
+        BN partial statistics [G, imgs*Ho, 64, 2] of the full-resolution output)."""
+    lib = _lib.require_device()
+    G, N, Kp = w.shape
+    assert N == 64 and a0.shape == (imgs * Ho * 128, Kp) and Ho % 2 == 0
+    pooled = torch.empty((G * imgs, Ho // 2, 64, 64), dtype=F16, device=a0.device)
+    stats = torch.empty((G, imgs * Ho, 64, 2), dtype=F32, device=a0.device)
+    _run("mauv_stem_conv_pool_f16", lib.mauv_stem_conv_pool_f16, _ptr(a0, F16), _ptr(w, F16), _ptr(pooled, F16), _ptr(stats, F32),
+         _ptr(gamma, F32), G, imgs, Ho, Kp, _stream(), tag=f"G{G} M{imgs * Ho * 128} N64 K{Kp} pool" if _prof is not None else None)
+    return pooled, stats
+
+
 def avgpool_f16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [N, H, W, C] fp16 -> [N, C] fp32"""
     lib = _lib.require_device()

@@ -225,6 +225,27 @@ def hbmwrite():
     print(f"read-only (sum 4 GiB): {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s", flush=True)
 
 
+def stem(G, B, cin, iters=5):
+    """Inference stem at 256 x 256: conv (stacked samples) + bn_relu_maxpool against the one-kernel stem + bn_act."""
+    x = torch.randn(B, cin, 256, 256, device=dev)
+    a0 = ops.stem_im2col_f16(x, 7, 7, 2, 3)
+    w = (torch.randn(G, 64, a0.shape[1], device=dev) * 0.05).half()
+    gamma, beta = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    y = torch.empty(G, B * 16384, 64, device=dev, dtype=torch.float16)
+    st = torch.empty(G, B * 128, 64, 2, device=dev)
+    ms_c = timeit(lambda: ops.gemm_f16(a0, w, stats=True, shared_a=True, out=y, stats_out=st), iters)
+    ss = ops.bn_finalize(st, B * 16384, gamma, beta)
+    ms_p = timeit(lambda: ops.bn_relu_maxpool_f16(y.view(G * B, 128, 128, 64), ss, G), iters)
+    print(f"stem G={G} B={B} cin={cin}: conv {ms_c:.3f} ms + bn_relu_maxpool {ms_p:.3f} ms = {ms_c + ms_p:.3f} ms", flush=True)
+    del y
+    ms_f = timeit(lambda: ops.stem_conv_pool_f16(a0, w, B, 128, gamma=gamma), iters)
+    yp, st2 = ops.stem_conv_pool_f16(a0, w, B, 128, gamma=gamma)
+    ms_a = timeit(lambda: ops.bn_act_f16(yp, ss, G, 64, relu=True, out=yp), iters)
+    fl = 2.0 * G * B * 16384 * 64 * 49 * cin
+    print(f"   one kernel (conv + statistics + raw max-pool) {ms_f:.3f} ms ({fl / ms_f / 1e9:.0f} TFLOP/s, "
+          f"{(yp.numel() * 2 + a0.numel() * 2) / ms_f / 1e9:.2f} TB/s) + bn_act on the pooled tensor {ms_a:.3f} ms = {ms_f + ms_a:.3f} ms", flush=True)
+
+
 def layers():
     G, B = 4, 256
     for (M, N, K) in [(B * 4096, 256, 64), (B * 4096, 64, 256), (B * 4096, 64, 64), (B * 1024, 512, 128),
@@ -240,4 +261,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "gram": gram, "adam": adam, "wgrad": wgrad, "bnbwd": bnbwd}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "gram": gram, "adam": adam, "wgrad": wgrad, "bnbwd": bnbwd, "stem": stem}[cmd](*a)
