@@ -286,8 +286,7 @@ def run_ours(args):
             fc, ft = fam.get(b, (0, 0.0))
             fam[b] = (fc + c, ft + t)
         # all launches of the tcgen05 kernels (gemm_f16_tc_kernel and its padded-stream sibling for layer1's 3x3 conv)
-        tc = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16",
-              "mauv_wgrad_f16", "mauv_stem_conv_pool_f16")     # (inference: the K x K second-moment contractions of the closed-form BN statistics)
+        tc = ops.TCGEN05_ENTRY_POINTS     # (inference: incl. the K x K second-moment contractions of the closed-form BN statistics)
         conv_calls = sum(fam.get(k, (0, 0.0))[0] for k in tc)
         conv_ms = sum(fam.get(k, (0, 0.0))[1] for k in tc)
         if args.detail:
@@ -378,7 +377,7 @@ def run_ours(args):
 
 def tc_launch_model(base: str, tag: str):
     """Algorithmic (flops, minimum HBM bytes) of ONE launch of gemm_f16_tc_kernel from its profiling tag."""
-    if base == "mauv_wgrad_f16":            # "G10x32 Cout64 K64 px4096": [Cout x px] x [px x K] per (sample, chunk); reads a once
+    if base in ("mauv_wgrad_f16", "mauv_gram_bn_f16"):     # "G10x32 Cout64 K64 px4096": [Cout x px] x [px x K] per (sample, chunk); reads a once
         t = tag.split()
         g, sp = (int(v) for v in t[0][1:].split("x"))
         cout, k, px = int(t[1][4:]), int(t[2][1:]), int(t[3][2:])
@@ -401,7 +400,7 @@ def tc_launch_model(base: str, tag: str):
         taps = int(kk.split("x")[0]) * int(kk.split("x")[1])
         a_bytes = g * m * int(stride) ** 2 * (k // taps) * 2    # the NHWC input is read once
         y_bytes = g * m * n * 2
-    elif base == "mauv_gemm_bn_f16":
+    elif base in ("mauv_gemm_bn_f16", "mauv_gemm_bn_xf_f16"):
         a_bytes = g * m * k * 2
         y_bytes = 0 if tag.startswith("stats") else g * m * n * 2 * (2 if "res1" in tag else 1)
     else:

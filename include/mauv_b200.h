@@ -271,6 +271,23 @@ int mauv_avgpool_bwd_f16(const float* dfeat, long long N, int HW, int C, float t
  * downsample input is made dense with mauv_subsample_f16), w_cat [G][N][K1+K2], scale_shift [G][N][2] = (1, shift). */
 int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
                          int relu, int G, long long M, int N, void* stream);
+
+/* ---- operand-transform variants: BatchNorm + ReLU of the PREVIOUS layer applied to the TMA-loaded operand tiles in shared memory
+ * (4 transform warps between the TMA and the tcgen05 stage), so relu(bn2(conv2(.))) - the bottleneck's a2 - is never written to
+ * or re-read from HBM (the reference materialises it: torchvision Bottleneck.forward `out = self.relu(self.bn2(out))`, reached
+ * from models/base_models.py:74-76). Arithmetic of the transform = mauv_bn_act_f16's (fp32 fma, max, one fp16 rounding), so the
+ * tensor core sees bit-identical operands.
+ *   mauv_gram_bn_f16:        gram_partial [G*splits][K][K] = a^T a per pixel chunk, colsum_partial [G*splits][K] = column sums
+ *                            of a per chunk, a = relu(y * scale + shift), y [G][M][K] raw, scale_shift [G][K][2]; K in {64,128,256},
+ *                            (M / splits) % 64 == 0. Feeds mauv_bn_stats_from_gram (nblk = splits).
+ *   mauv_gemm_bn_xf_f16:     mauv_gemm_bn_f16 mode 2 with A = relu(a_raw * s_a + t_a); K in {64,128,192,256}, N >= 128.
+ *   mauv_gemm_bn_cat_xf_f16: mauv_gemm_bn_cat_f16 with the a1 k-blocks transformed the same way (a2 is read as is). */
+int mauv_gram_bn_f16(const void* y, const float* scale_shift, float* gram_partial, float* colsum_partial, int G, int splits,
+                     long long M, int K, void* stream);
+int mauv_gemm_bn_xf_f16(const void* a_raw, const float* a_scale_shift, const void* w, void* y, const float* scale_shift,
+                        const void* residual, int relu, int G, long long M, int N, int K, void* stream);
+int mauv_gemm_bn_cat_xf_f16(const void* a1_raw, const float* a1_scale_shift, int K1, const void* a2, int K2, const void* w_cat,
+                            void* y, const float* scale_shift, int relu, int G, long long M, int N, void* stream);
 int mauv_sample_weights_scaled_f16(const float* mu, const float* rho, const float* eps, uint64_t seed, uint32_t layer_id,
                                    uint32_t sample0, int G, int cout, int cin, const float* scale_shift, int row_pitch,
                                    int col0, void* w_out, void* stream);

@@ -314,99 +314,122 @@ colsum_kernel(const uint4* __restrict__ x, long long per_sample_vec, int C, floa
 // stage B evaluates the two forms for 32 output channels per block with S staged through shared memory, and writes
 // (sum, sum of squares) in the double2 layout bn_finalize_kernel consumes.
 // ---------------------------------------------------------------------------
-// block = 32 elements x 8 partial lanes: element e < K*K is an entry of S (partials `splits` apart by K*K), element
-// K*K + c is column sum c (partials `nblk` apart by K); every lane sums its partials p = ty, ty+8, .. in double, the 8 lanes
-// are combined in a fixed order (deterministic). Short dependent chains instead of one thread walking 256 partials.
-constexpr int GRAM_REDUCE_REPS = 8;
-__global__ void __launch_bounds__(256)
+// Stage A. Element e < K*K is an entry of S (partials `splits` apart by K*K), element K*K + c is column sum c (partials
+// `nblk` apart by K). block = 32 consecutive elements x LY partial lanes: every lane sums its partials p = ty, ty + LY, .. in
+// double with 8 independent loads in flight, the lanes are combined in a fixed order (deterministic). LY = 1 for short
+// partial lists (K = 256: 16 pixel chunks) - no shared memory, no barrier -, LY = 8 for long ones (K = 64: 256 chunks).
+template <int LY>
+__global__ void __launch_bounds__(32 * LY)
 gram_reduce_kernel(const float* __restrict__ gram, int splits, long long kk /* K*K */, const float* __restrict__ colsum,
                    int nblk, int K, float* __restrict__ S /*[G][K*K]*/, float* __restrict__ s1 /*[G][K]*/) {
-  __shared__ double red[8][33];
+  __shared__ double red[LY][33];
   const int g = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int rep = 0; rep < GRAM_REDUCE_REPS; ++rep) {        // a block covers GRAM_REDUCE_REPS x 32 consecutive elements
-    const long long e = (static_cast<long long>(blockIdx.x) * GRAM_REDUCE_REPS + rep) * 32 + tx;
-    double acc = 0.0;
-    if (e < kk) {
-      const float* src = gram + static_cast<long long>(g) * splits * kk + e;
-      for (int sp = ty; sp < splits; sp += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * kk));
-    } else if (e < kk + K) {
-      const float* src = colsum + static_cast<long long>(g) * nblk * K + (e - kk);
-      for (int b = ty; b < nblk; b += 8) acc += static_cast<double>(__ldcs(src + static_cast<long long>(b) * K));
-    }
-    __syncthreads();
+  const long long e = static_cast<long long>(blockIdx.x) * 32 + tx;
+  const float* src = nullptr;
+  long long pitch = 0;
+  int n = 0;
+  if (e < kk) {
+    src = gram + static_cast<long long>(g) * splits * kk + e; pitch = kk; n = splits;
+  } else if (e < kk + K) {
+    src = colsum + static_cast<long long>(g) * nblk * K + (e - kk); pitch = K; n = nblk;
+  }
+  double acc = 0.0;
+  int sp = ty;
+  for (; sp + 7 * LY < n; sp += 8 * LY) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + static_cast<long long>(sp + u * LY) * pitch);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += static_cast<double>(v[u]);
+  }
+  for (; sp < n; sp += LY) acc += static_cast<double>(__ldcs(src + static_cast<long long>(sp) * pitch));
+  if (LY > 1) {
     red[ty][tx] = acc;
     __syncthreads();
-    if (ty == 0 && e < kk + K) {
+    if (ty == 0) {
 #pragma unroll
-      for (int j = 1; j < 8; ++j) acc += red[j][tx];
-      if (e < kk) S[static_cast<long long>(g) * kk + e] = static_cast<float>(acc);
-      else s1[static_cast<long long>(g) * K + (e - kk)] = static_cast<float>(acc);
+      for (int j = 1; j < LY; ++j) acc += red[j][tx];
     }
+  }
+  if (ty == 0 && e < kk + K) {
+    if (e < kk) S[static_cast<long long>(g) * kk + e] = static_cast<float>(acc);
+    else s1[static_cast<long long>(g) * K + (e - kk)] = static_cast<float>(acc);
   }
 }
 
-constexpr int GQ_N = 64;      // output channels per block (8 warps x 8): 2 broadcast LDS.128 of weights per 8 FMAs
-constexpr int GQ_ROWS = 32;   // rows of S staged per step (one per lane)
+// Stage B. q_n = w_n^T S w_n and m_n = w_n . s1 for a block of GQ_N = 64 output channels and a tile of GQ_ROWS = 64 rows of S:
+// T[row][n] = sum_c S[c][row] w[n][c] (S is symmetric: its rows are read where they lie, no transpose) as a register-tiled fp32
+// contraction - thread (ty, tx) owns rows 4 ty .. 4 ty + 3 x channels 4 tx .. 4 tx + 3, two LDS.128 per 16 FMAs - over
+// 64-column chunks staged in shared memory; then q_n += sum_rows w[n][row] T[row][n] in double, combined over the 16 row
+// groups in a fixed order. The K/64 row tiles of one (sample, channel block) are separate blocks (blockIdx.z) and
+// bn_finalize_kernel adds their partials. (The first version walked one row per lane with three shared-memory reads per
+// 8 FMAs: 236 us for K = 256, N = 1024, G = 15 - more than the second-moment contraction it evaluates.)
+constexpr int GQ_N = 64;
+constexpr int GQ_ROWS = 64;
+constexpr int GQ_WPITCH = 68;   // floats per staged weight row: 16-byte aligned float4 reads, 4-way conflicts on the transposing writes
 __global__ void __launch_bounds__(256)
 gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, const __half* __restrict__ w /*[G][N][K]*/,
-                     int N, int K, double2* __restrict__ out /*[G][K/32][N] (sum, sum of squares) partials per row tile*/) {
-  extern __shared__ __align__(16) float gq_smem[];
-  const int pitch = K + 1;                         // lanes read different rows of S at the same column: odd pitch
-  float* wt = gq_smem;                             // [K][GQ_N]   this block's weights, transposed: 4 channels = one LDS.128
-  float* Ss = gq_smem + GQ_N * K;                  // [GQ_ROWS][pitch]
-  const int g = blockIdx.y, n0 = blockIdx.x * GQ_N;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < GQ_N * K; i += 256) {
-    const int nn = i / K, c = i - nn * K;          // coalesced read of w rows
-    const int n = n0 + nn;
-    wt[c * GQ_N + nn] = n < N ? __half2float(w[(static_cast<long long>(g) * N + n) * K + c]) : 0.f;
-  }
+                     int N, int K, double2* __restrict__ out /*[G][gridDim.z][N] (sum, sum of squares) partials per row tile*/) {
+  __shared__ __align__(16) float wt[64 * GQ_WPITCH];      // [c][channel]  this chunk's weights, transposed
+  __shared__ __align__(16) float St[64 * GQ_ROWS];        // [c][row]      S[c0 + c][r0 + row]
+  __shared__ double red[16][GQ_N];
+  const int g = blockIdx.y, n0 = blockIdx.x * GQ_N, r0 = blockIdx.z * GQ_ROWS;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* Sg = S + static_cast<long long>(g) * K * K;
-  double q[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const float* wq = wt + warp * 8;
-  // blockIdx.z = row tile of S: the K/32 tiles of one (sample, channel block) run as separate blocks (8x the parallelism
-  // at K = 256; one block walking all tiles left the SMs at 13 % occupancy) and bn_finalize_kernel adds the partials
-  const int n_rt = gridDim.z;
-  {
-    const int r0 = blockIdx.z * GQ_ROWS;
-    __syncthreads();
-    for (int i = threadIdx.x; i < GQ_ROWS * K; i += 256) {
-      const int r = i / K, c = i - r * K;
-      Ss[r * pitch + c] = (r0 + r < K) ? Sg[static_cast<long long>(r0 + r) * K + c] : 0.f;
-    }
-    __syncthreads();
-    // lane = row r0 + lane of S: t[j] = S[row][:] . w_j for this warp's 8 channels, then q_j += w_j[row] * t[j]
-    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* srow = Ss + lane * pitch;
-#pragma unroll 4
-    for (int c = 0; c < K; ++c) {
-      const float sv = srow[c];
-      const float4 wa = *reinterpret_cast<const float4*>(wq + c * GQ_N);        // broadcast
-      const float4 wb = *reinterpret_cast<const float4*>(wq + c * GQ_N + 4);
-      t[0] = fmaf(sv, wa.x, t[0]); t[1] = fmaf(sv, wa.y, t[1]); t[2] = fmaf(sv, wa.z, t[2]); t[3] = fmaf(sv, wa.w, t[3]);
-      t[4] = fmaf(sv, wb.x, t[4]); t[5] = fmaf(sv, wb.y, t[5]); t[6] = fmaf(sv, wb.z, t[6]); t[7] = fmaf(sv, wb.w, t[7]);
-    }
-    if (r0 + lane < K) {
-      const float* wr = wq + (r0 + lane) * GQ_N;
+  const __half* wg = w + static_cast<long long>(g) * N * K;
+  float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] += static_cast<double>(wr[j]) * t[j];
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  double m1 = 0.0;                                         // first moment of channel n0 + tid (tid < 64, row tile 0)
+  for (int c0 = 0; c0 < K; c0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int nn = i >> 6, c = i & 63;                   // coalesced along c
+      const int n = n0 + nn;
+      wt[c * GQ_WPITCH + nn] = (n < N && c0 + c < K) ? __half2float(wg[static_cast<long long>(n) * K + c0 + c]) : 0.f;
+    }
+    for (int i = tid; i < 64 * GQ_ROWS; i += 256) {
+      const int c = i >> 6, r = i & 63;                    // coalesced along the row of S
+      St[i] = (c0 + c < K && r0 + r < K) ? Sg[static_cast<long long>(c0 + c) * K + r0 + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float4 sv = *reinterpret_cast<const float4*>(St + c * GQ_ROWS + 4 * ty);
+      const float4 wv = *reinterpret_cast<const float4*>(wt + c * GQ_WPITCH + 4 * tx);
+      const float sr[4] = {sv.x, sv.y, sv.z, sv.w}, wc[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(sr[i], wc[j], acc[i][j]);
+    }
+    if (blockIdx.z == 0 && tid < GQ_N) {
+      for (int c = 0; c < 64 && c0 + c < K; ++c)
+        m1 += static_cast<double>(s1[static_cast<long long>(g) * K + c0 + c]) * static_cast<double>(wt[c * GQ_WPITCH + tid]);
+    }
+  }
+  // q_n partial of this thread: its 4 rows
+  double q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + 4 * tx + j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 4 * ty + i;
+      if (n < N && r < K) q[j] += static_cast<double>(__half2float(wg[static_cast<long long>(n) * K + r])) * static_cast<double>(acc[i][j]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) q[j] = warp_sum_d(q[j]);
-  // first moment: w_n . s1 (row tile 0 only)
-  double m[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int c = lane; c < K && blockIdx.z == 0; c += 32) {
-    const double sv = s1[static_cast<long long>(g) * K + c];
+  for (int j = 0; j < 4; ++j) red[ty][4 * tx + j] = q[j];
+  __syncthreads();
+  if (tid < GQ_N) {
+    double qs = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] += sv * wq[c * GQ_N + j];
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = warp_sum_d(m[j]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = n0 + warp * 8 + j;
-    if (lane == j && n < N) out[(static_cast<long long>(g) * n_rt + blockIdx.z) * N + n] = make_double2(m[j], q[j]);
+    for (int r = 0; r < 16; ++r) qs += red[r][tid];
+    const int n = n0 + tid;
+    if (n < N) out[(static_cast<long long>(g) * gridDim.z + blockIdx.z) * N + n] = make_double2(m1, qs);
   }
 }
 
@@ -711,18 +734,13 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
   const long long f = (static_cast<long long>(G) * K * K + static_cast<long long>(G) * K + 3) / 4 * 4;
   double2* sums = reinterpret_cast<double2*>(static_cast<float*>(ws) + f);
   const long long kk = static_cast<long long>(K) * K;
-  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32 * GRAM_REDUCE_REPS)), G);
-  gram_reduce_kernel<<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
+  dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32)), G);
+  if (splits >= 64) gram_reduce_kernel<8><<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
+  else gram_reduce_kernel<1><<<g1, 32, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
   MAUV_LAUNCH_CHECK("gram_reduce_kernel");
-  const int smem = (GQ_N * K + GQ_ROWS * (K + 1)) * static_cast<int>(sizeof(float));
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    MAUV_CUDA(cudaFuncSetAttribute(gram_quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
   const int n_rt = (K + GQ_ROWS - 1) / GQ_ROWS;
   dim3 g2((N + GQ_N - 1) / GQ_N, G, n_rt);
-  gram_quadform_kernel<<<g2, 256, smem, st>>>(S, s1, static_cast<const __half*>(w), N, K, sums);
+  gram_quadform_kernel<<<g2, 256, 0, st>>>(S, s1, static_cast<const __half*>(w), N, K, sums);
   MAUV_LAUNCH_CHECK("gram_quadform_kernel");
   dim3 fblock(32, G < 16 ? G : 16);
   bn_finalize_kernel<<<(N + 31) / 32, fblock, 0, st>>>(sums, G, n_rt, N, count, gamma, beta, eps, momentum, running_mean,

@@ -75,6 +75,14 @@ struct GemmParams {
                          //     descriptor points at boxes m0/64, m0/64+1 of the B tile (N = K <= BN: one n-tile)
   int cin;               // mn: input channels (column -> (tap, channel block))
   long long chunk;       // mn: pixels per batch entry
+  // XF instances: the activation operand is the RAW output of the previous conv and that layer's BatchNorm + ReLU is applied to
+  // the TMA-loaded tiles in shared memory (4 transform warps between the TMA and the MMA stage), so the activated tensor is
+  // never written to / re-read from HBM. xf_ss [samples][xf_K] (scale, shift); K-major A: the first xf_kb k-blocks are
+  // transformed (all of them, or the a2 part of a K-concatenated tail); gram mode: every box, sample = batch / xf_splits, and
+  // the column sums of the transformed values go to xf_colsum [G][K] (one row per batch entry = (sample, pixel chunk)).
+  const float2* xf_ss;
+  int xf_K, xf_kb, xf_splits;
+  float* xf_colsum;
 };
 
 // Epilogue flavours: 0 = raw fp16 store + BN statistics, 1 = BN statistics only (no output: first pass of the
@@ -110,8 +118,8 @@ struct SmemLayout {
 // PLAIN = 2: the stem's sample-stacked instance (A shared by all samples, 4 samples of 64 channels side by side in one
 // 128 x 256 tile), again with every other flag folded: the stem writes the largest tensor of the network and ran the
 // generic epilogue (2.1 TB/s of output against 4.1 TB/s for the same volume through the PLAIN = 1 instance).
-template <int BN, int EPI, int PLAIN>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, int EPI, int PLAIN, bool XF = false>
+__global__ void __launch_bounds__(XF ? 448 : 384, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const GemmParams p) {
@@ -141,6 +149,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
   auto res_bar = [&](int w, int j) { return bar_base + 8u * (2 * kStages + 6 + w * 3 + j); };   // EPI == 2 only
+  auto xf_ready = [&](int s) { return bar_base + 8u * (2 * kStages + 30 + s); };                // XF only: tile transformed
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + kStages * L::kStageBytes + L::kOutBytes + L::kStatBytes + 8 * (2 * kStages + 4));
 
@@ -164,6 +173,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (EPI == EPI_FUSED_BN)
       for (int w = 0; w < L::kEpiWarps; ++w)
         for (int j = 0; j < 3; ++j) mbar_init(res_bar(w, j), 1);
+    if (XF)
+      for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), 4);       // one arrive per transform warp
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -314,7 +325,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(XF ? xf_ready(stage) : full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t a_addr = tiles_base + stage * L::kStageBytes;
           if (f_mn) {
@@ -340,6 +351,156 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (XF && (warp == 2 || warp == 3 || warp >= 12)) {
+    // ===================== operand transform (XF instances) =====================
+    // The activation operand arrives RAW (the previous conv's output); BatchNorm + ReLU of that layer is applied here, in
+    // place, to every TMA-loaded tile before the MMA warp may read it: a = relu(y * scale + shift), fp32 math and one fp16
+    // rounding - exactly bn_act_kernel's arithmetic, so the MMA sees bit-identical operands. 128 threads: thread t owns the
+    // logical 16-byte chunk lc = t & 7 (8 channels) of rows (t >> 3) + 16 i; the physical chunk is lc ^ (row & 7) (128B
+    // swizzle). Rows past the tensor (TMA zero fill) become relu(shift): K-major tiles never store those rows; gram-mode
+    // chunks are whole multiples of 64 pixels.
+    static_assert(!XF || EPI != EPI_FUSED_BN || BN >= 128, "the (scale, shift) table of the XF fused epilogue lives behind my_ss");
+    const int tw = warp >= 12 ? warp - 10 : warp - 2;                   // 0..3
+    const uint32_t t = static_cast<uint32_t>(tw) * 32u + lane_id();
+    const uint32_t lc = t & 7u, r0 = t >> 3;
+    float* xf_tab = stat_smem + (EPI == EPI_FUSED_BN ? 1024 : 0);     // scale[256] | shift[256], de-interleaved
+    const uint32_t xf_tab_addr = smem_u32(xf_tab);
+    float* xf_scr = reinterpret_cast<float*>(smem_gen + kStages * L::kStageBytes);               // gram: [16][K] (out staging is idle)
+    // 8 consecutive channels' scales / shifts as packed fp32x2 operands (two broadcast LDS.128 each)
+    auto load_ss = [&](uint32_t ch0, unsigned long long (&sc)[4], unsigned long long (&sh)[4]) {
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[0]), "=l"(sc[1]) : "r"(xf_tab_addr + ch0 * 4u));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[2]), "=l"(sc[3]) : "r"(xf_tab_addr + ch0 * 4u + 16u));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[0]), "=l"(sh[1]) : "r"(xf_tab_addr + 1024u + ch0 * 4u));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[2]), "=l"(sh[3]) : "r"(xf_tab_addr + 1024u + ch0 * 4u + 16u));
+    };
+    auto lds128 = [&](uint32_t addr, uint32_t (&wv)[4]) {
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(addr));
+    };
+    auto sts128 = [&](uint32_t addr, const uint32_t (&wv)[4]) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+    };
+    // relu(y * scale + shift) on 8 fp16 values: fp32 fma per element (packed fma.rn.f32x2: the same rounding as fmaf), one fp16
+    // rounding, ReLU on the rounded pair (max(round(x), 0) == round(max(x, 0))) - bit-identical to bn_act_kernel
+    auto xform8 = [&](uint32_t (&wv)[4], const unsigned long long (&sc)[4], const unsigned long long (&sh)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(*reinterpret_cast<__half2*>(&wv[q]));
+        unsigned long long a2, r2;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(f.x), "f"(f.y));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(a2), "l"(sc[q]), "l"(sh[q]));
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r2));
+        const __half2 o = __hmax2(__floats2half2_rn(lo, hi), __float2half2_rn(0.f));
+        wv[q] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+    };
+    int stage = 0, cur_smp = -1;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int g, m_tile, n_tile;
+      decode(tile, g, m_tile, n_tile);
+      const int smp = f_mn ? g / p.xf_splits : g;
+      if (smp != cur_smp) {        // this sample's (scale, shift) table; the 4 warps walk the same tile sequence
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        for (int i = static_cast<int>(t); i < p.xf_K; i += 128) {
+          const float2 v = __ldg(p.xf_ss + static_cast<long long>(smp) * p.xf_K + i);
+          xf_tab[i] = v.x;
+          xf_tab[256 + i] = v.y;
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        cur_smp = smp;
+      }
+      if (EPI == EPI_STORE_STATS && f_mn) {
+        // gram mode: BN/64 boxes of [64 pixels][64 channels] per k-block, channels 64 j + 8 lc .. of box j
+        constexpr int kBoxes = BN / 64;
+        unsigned long long cs[kBoxes][4];                         // packed column sums of channels 64 j + 8 lc + (2q, 2q+1)
+#pragma unroll
+        for (int j = 0; j < kBoxes; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cs[j][q] = 0ull;
+        const int b_boxes = (p.N + 63) / 64;                      // one n-tile holds all K columns (gram)
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          const uint32_t b_dst = tiles_base + stage * L::kStageBytes + L::kABytes;
+#pragma unroll
+          for (int j = 0; j < kBoxes; ++j) {
+            if (j < b_boxes) {
+              unsigned long long sc[4], sh[4];
+              uint32_t wv[4][4];
+              load_ss(64u * j + 8u * lc, sc, sh);
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) {                  // all four loads first: one exposed shared-memory latency
+                const uint32_t row = r0 + 16u * i;
+                lds128(b_dst + j * 8192u + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
+              }
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t row = r0 + 16u * i;
+                xform8(wv[i], sc, sh);
+                sts128(b_dst + j * 8192u + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {        // column sums of the values the tensor core will read
+                  const float2 fo = __half22float2(*reinterpret_cast<__half2*>(&wv[i][q]));
+                  unsigned long long f2;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(fo.x), "f"(fo.y));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(cs[j][q]) : "l"(f2));
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(xf_ready(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (p.xf_colsum && m_tile == 0) {
+          // column sums of the transformed chunk: 16 row groups per channel, combined in a fixed order
+          asm volatile("bar.sync 3, 128;" ::: "memory");        // the previous tile's readers are done with the scratch
+#pragma unroll
+          for (int j = 0; j < kBoxes; ++j)
+            if (j < b_boxes) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float2*>(xf_scr + r0 * p.N + 64 * j + 8 * lc + 2 * q) = *reinterpret_cast<float2*>(&cs[j][q]);
+            }
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+          for (int c = static_cast<int>(t); c < p.N; c += 128) {
+            float a = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) a += xf_scr[r * p.N + c];
+            p.xf_colsum[static_cast<long long>(g) * p.N + c] = a;
+          }
+        }
+      } else {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          if (kb < p.xf_kb) {
+            const uint32_t a_dst = tiles_base + stage * L::kStageBytes;
+            unsigned long long sc[4], sh[4];
+            load_ss(64u * kb + 8u * lc, sc, sh);
+#pragma unroll
+            for (uint32_t half = 0; half < 2; ++half) {           // 4 loads in flight, then 4 transforms + stores
+              uint32_t wv[4][4];
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t row = r0 + 16u * (4u * half + i);
+                lds128(a_dst + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
+              }
+#pragma unroll
+              for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t row = r0 + 16u * (4u * half + i);
+                xform8(wv[i], sc, sh);
+                sts128(a_dst + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
+              }
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(xf_ready(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp >= 4 && warp < 4 + L::kEpiWarps) {
@@ -759,18 +920,18 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, int EPI, int PLAIN>
+template <int BN, int EPI, int PLAIN, bool XF = false>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                   const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN>,
+    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN, EPI, PLAIN><<<static_cast<unsigned>(grid), 384, L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
+  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF><<<static_cast<unsigned>(grid), XF ? 448 : 384, L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
@@ -778,6 +939,19 @@ int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 template <int BN, int EPI>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                 const GemmParams& p, cudaStream_t stream) {
+  // XF instances (BatchNorm + ReLU of the previous layer applied to the operand tiles in shared memory): the fused-BN tails
+  // (plain, or K-concatenated with a downsample branch) and the second-moment contraction
+  if (p.xf_ss) {
+    if constexpr (EPI == EPI_FUSED_BN && BN >= 128) {
+      const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
+                         !p.b_mod && !p.bias && p.a_batch_mul == 1;
+      if (plain) return launch_gemm_t<BN, EPI, 1, true>(tmA, tmB, tmY, tmR, p, stream);
+      return launch_gemm_t<BN, EPI, 0, true>(tmA, tmB, tmY, tmR, p, stream);
+    } else if constexpr (EPI == EPI_STORE_STATS) {
+      if (p.mn && p.gram && p.out_f32) return launch_gemm_t<BN, EPI, 0, true>(tmA, tmB, tmY, tmR, p, stream);
+    }
+    return mauv_set_error(MAUV_ERR_BAD_ARG, "gemm_f16_tc: no operand-transform instance for this mode (BN=%d EPI=%d)", BN, EPI);
+  }
   // the compile-time-specialised instance for the hot inference shapes (store + statistics, fused BatchNorm epilogue)
   if constexpr (EPI == EPI_STORE_STATS || EPI == EPI_FUSED_BN) {
     const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
@@ -1253,8 +1427,8 @@ int mauv_gemm_wmod_f16(const void* a, const void* w, int w_batches, void* y, int
 // ---- weight gradient of the grouped conv, straight from NHWC operands ---------------------------------------------
 // dw[(g, chunk)][co][(r, s, c)] = sum over the chunk's output pixels of dy[pixel][co] * x[pixel shifted by tap (r,s)][c]
 // dw is FP32 ([G*splits][Cout][kh*kw*Cin] floats): the accumulator is stored unrounded.
-int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
-                   int Cout, int kh, int kw, int stride, int pad, void* stream) {
+static int wgrad_impl(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
+                      int Cout, int kh, int kw, int stride, int pad, const float* xf_ss, float* xf_colsum, void* stream) {
   MAUV_CHECK_ARG(dy && x && dw && G >= 1 && splits >= 1, "mauv_wgrad_f16: bad argument");
   MAUV_CHECK_ARG(Cin % 64 == 0 && Cout % 8 == 0, "mauv_wgrad_f16: Cin must be a multiple of 64 and Cout of 8 (Cin=%d Cout=%d)", Cin, Cout);
   MAUV_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -1308,7 +1482,30 @@ int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, i
   p.out_f32 = 1;          // fp32 partial sums: a correlated dy*x sum over thousands of pixels can exceed fp16's 65504
   p.stats = nullptr;
   p.bias = nullptr;
+  if (xf_ss) {
+    MAUV_CHECK_ARG(p.gram, "mauv_gram_bn_f16: shape not eligible for the second-moment mode (K=%d must be 64, 128 or 256)", K);
+    p.xf_ss = reinterpret_cast<const float2*>(xf_ss);
+    p.xf_K = K;
+    p.xf_splits = splits;
+    p.xf_colsum = xf_colsum;
+  }
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+int mauv_wgrad_f16(const void* dy, const void* x, void* dw, int G, int splits, int imgs_per_sample, int H, int W, int Cin,
+                   int Cout, int kh, int kw, int stride, int pad, void* stream) {
+  return wgrad_impl(dy, x, dw, G, splits, imgs_per_sample, H, W, Cin, Cout, kh, kw, stride, pad, nullptr, nullptr, stream);
+}
+
+// Second moments of a = relu(y * scale + shift) WITHOUT materialising a: y [G][M][K] is the raw output of the previous conv,
+// scale_shift [G][K][2] that layer's BatchNorm; the transform runs on the TMA-loaded tiles in shared memory.
+// gram_partial [G*splits][K][K] fp32 (a^T a per pixel chunk), colsum_partial [G*splits][K] fp32 (column sums of a per chunk):
+// the inputs of mauv_bn_stats_from_gram for the 1x1 conv that consumes a. K in {64, 128, 256}, (M / splits) % 64 == 0.
+int mauv_gram_bn_f16(const void* y, const float* scale_shift, float* gram_partial, float* colsum_partial, int G, int splits,
+                     long long M, int K, void* stream) {
+  MAUV_CHECK_ARG(y && scale_shift && gram_partial && colsum_partial, "mauv_gram_bn_f16: null pointer");
+  MAUV_CHECK_ARG(M >= 1 && M < (1LL << 31), "mauv_gram_bn_f16: bad M");
+  return wgrad_impl(y, y, gram_partial, G, splits, 1, static_cast<int>(M), 1, K, K, 1, 1, 1, 0, scale_shift, colsum_partial, stream);
 }
 
 // ---- fp16x3 validation mode -------------------------------------------------------------------------------------
@@ -1373,8 +1570,9 @@ int mauv_conv2d_im2col_x3_f16(const void* x2, const void* w3, void* y2, float* s
 // Recompute scheme for the bottleneck's last 1x1 conv (HBM-write bound): mode 1 = statistics only (y may be NULL),
 // mode 2 = out = relu?(A*W^T * scale + shift [+ residual]) written straight to `y`; the raw conv output never
 // exists in HBM. scale_shift: [G][N][2] from mauv_bn_finalize; residual: [G][M][N] fp16 or NULL. N % 64 == 0.
-int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
-                     const void* residual, int relu, int mode, int G, long long M, int N, int K, void* stream) {
+static int gemm_bn_impl(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
+                        const void* residual, int relu, int mode, int G, long long M, int N, int K, const float* a_scale_shift,
+                        void* stream) {
   MAUV_CHECK_ARG(a && w, "mauv_gemm_bn_f16: null pointer");
   MAUV_CHECK_ARG(mode == EPI_STATS_ONLY || mode == EPI_FUSED_BN, "mauv_gemm_bn_f16: mode must be 1 (stats) or 2 (fused)");
   MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 64 && N % 64 == 0 && K >= 8 && K % 8 == 0, "mauv_gemm_bn_f16: bad shape G=%d M=%lld N=%d K=%d", G, M, N, K);
@@ -1424,18 +1622,36 @@ int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial
   p.ss = reinterpret_cast<const float2*>(scale_shift);
   p.has_res = residual != nullptr;
   p.relu = relu;
-  if (mode == EPI_STATS_ONLY) {
-    // the Y map describes [G][M][N]; with y aliased to A it is never written (EPI 1 issues no store)
+  if (a_scale_shift) {
+    MAUV_CHECK_ARG(mode == EPI_FUSED_BN && K % 64 == 0 && K <= 256 && N >= 128,
+                   "mauv_gemm_bn_xf_f16: needs K in {64, 128, 192, 256} and N >= 128 (K=%d N=%d)", K, N);
+    p.xf_ss = reinterpret_cast<const float2*>(a_scale_shift);
+    p.xf_K = K;
+    p.xf_kb = p.k_blocks;
   }
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream), mode, residual);
+}
+
+int mauv_gemm_bn_f16(const void* a, const void* w, void* y, float* stats_partial, const float* scale_shift,
+                     const void* residual, int relu, int mode, int G, long long M, int N, int K, void* stream) {
+  return gemm_bn_impl(a, w, y, stats_partial, scale_shift, residual, relu, mode, G, M, N, K, nullptr, stream);
+}
+
+// mauv_gemm_bn_f16 mode 2 on the RAW output of the previous conv: out = relu?(relu(a_raw * s_a + t_a) * W^T * scale + shift
+// [+ residual]); a_scale_shift [G][K][2] is the BatchNorm of the layer that produced a_raw, applied (with ReLU) to the A tiles
+// in shared memory. The activated tensor is never written to / re-read from HBM. K in {64, 128, 192, 256}.
+int mauv_gemm_bn_xf_f16(const void* a_raw, const float* a_scale_shift, const void* w, void* y, const float* scale_shift,
+                        const void* residual, int relu, int G, long long M, int N, int K, void* stream) {
+  MAUV_CHECK_ARG(a_scale_shift, "mauv_gemm_bn_xf_f16: null pointer");
+  return gemm_bn_impl(a_raw, w, y, nullptr, scale_shift, residual, relu, EPI_FUSED_BN, G, M, N, K, a_scale_shift, stream);
 }
 
 // Fused tail of a bottleneck WITH a downsample branch: out = relu(bn3(a1 * W3^T) + bnd(a2 * Wd^T)) as ONE contraction over
 // the K-concatenated operands [a1 | a2] * [s3*W3 | sd*Wd]^T + (t3 + td): the BatchNorm scales are folded into the sampled
 // weights (mauv_sample_weights_scaled_f16), the shifts into the epilogue (scale_shift = (1, t3 + td)). Neither raw conv
 // output ever reaches HBM. a1 [G][M][K1], a2 [G][M][K2], w_cat [G][N][K1+K2], K1 % 64 == 0.
-int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
-                         int relu, int G, long long M, int N, void* stream) {
+static int gemm_bn_cat_impl(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
+                            int relu, int G, long long M, int N, const float* a1_scale_shift, void* stream) {
   MAUV_CHECK_ARG(a1 && a2 && w_cat && y && scale_shift, "mauv_gemm_bn_cat_f16: null pointer");
   MAUV_CHECK_ARG(G >= 1 && M >= 1 && N >= 64 && N % 64 == 0 && N % pick_bn(N) == 0, "mauv_gemm_bn_cat_f16: N must be 64, 128 or a multiple of 256 (got %d)", N);
   MAUV_CHECK_ARG(K1 >= 64 && K1 % 64 == 0 && K2 >= 8 && K2 % 8 == 0, "mauv_gemm_bn_cat_f16: K1 must be a multiple of 64, K2 of 8 (K1=%d K2=%d)", K1, K2);
@@ -1458,7 +1674,25 @@ int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const v
   p.ss = reinterpret_cast<const float2*>(scale_shift);
   p.has_res = 0;
   p.relu = relu;
+  if (a1_scale_shift) {
+    MAUV_CHECK_ARG(K1 <= 256 && N >= 128, "mauv_gemm_bn_cat_xf_f16: needs K1 <= 256 and N >= 128 (K1=%d N=%d)", K1, N);
+    p.xf_ss = reinterpret_cast<const float2*>(a1_scale_shift);
+    p.xf_K = K1;
+    p.xf_kb = p.a2_kb;
+  }
   return dispatch(tmA, tmB, p, static_cast<cudaStream_t>(stream), EPI_FUSED_BN, nullptr, &tmA2);
+}
+
+int mauv_gemm_bn_cat_f16(const void* a1, int K1, const void* a2, int K2, const void* w_cat, void* y, const float* scale_shift,
+                         int relu, int G, long long M, int N, void* stream) {
+  return gemm_bn_cat_impl(a1, K1, a2, K2, w_cat, y, scale_shift, relu, G, M, N, nullptr, stream);
+}
+
+// mauv_gemm_bn_cat_f16 with a1 RAW: its BatchNorm + ReLU (a1_scale_shift [G][K1][2]) is applied to the a1 k-blocks in shared memory.
+int mauv_gemm_bn_cat_xf_f16(const void* a1_raw, const float* a1_scale_shift, int K1, const void* a2, int K2, const void* w_cat,
+                            void* y, const float* scale_shift, int relu, int G, long long M, int N, void* stream) {
+  MAUV_CHECK_ARG(a1_scale_shift, "mauv_gemm_bn_cat_xf_f16: null pointer");
+  return gemm_bn_cat_impl(a1_raw, K1, a2, K2, w_cat, y, scale_shift, relu, G, M, N, a1_scale_shift, stream);
 }
 
 int mauv_conv2d_im2col_f16(const void* x, const void* w, void* y, float* stats_partial, int G,

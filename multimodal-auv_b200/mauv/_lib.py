@@ -69,6 +69,9 @@ SIGNATURES = {
     "mauv_maxpool_bwd_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mauv_avgpool_bwd_f16": (i32, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
     "mauv_gemm_bn_cat_f16": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, i32, i64, i32, vp]),
+    "mauv_gram_bn_f16": (i32, [vp, vp, vp, vp, i32, i32, i64, i32, vp]),
+    "mauv_gemm_bn_xf_f16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
+    "mauv_gemm_bn_cat_xf_f16": (i32, [vp, vp, i32, vp, i32, vp, vp, vp, i32, i32, i64, i32, vp]),
     "mauv_sample_weights_scaled_f16": (i32, [vp, vp, vp, u64, u32, u32, i32, i32, i32, vp, i32, i32, vp, vp]),
     "mauv_bn_shift_sum": (i32, [vp, vp, i64, vp, vp]),
     "mauv_subsample_f16": (i32, [vp, i64, i32, i32, i32, i32, vp, vp]),

@@ -127,6 +127,10 @@ class MCEngine:
         # stem: conv1 + bn1 statistics + max-pool of the raw output in one kernel (ops.stem_conv_pool_f16): the full-resolution
         # conv1 output never reaches HBM. 256 x 256 inputs (Wo = 128) only; other sizes take the three-kernel path.
         self.stem_pool = os.environ.get("MAUV_STEM_POOL", "1") != "0"
+        # bn2 + ReLU of the recompute tails' input applied to the operand tiles in shared memory (second-moment contraction and
+        # fused conv3): a2 = relu(bn2(conv2(.))) is never written to / re-read from HBM
+        self.fuse_a2 = os.environ.get("MAUV_FUSE_A2", "1") != "0"
+        self.fuse_a2_max_k = int(os.environ.get("MAUV_FUSE_A2_MAX_K", "128"))     # K = 256 (layer3): the transform costs more than bn_act
 
     # Philox sample-id cursor, shared by every engine built on the same model (it lives on the model object): each
     # forward_mc / TrainEngine.step / predictor batch that is not given explicit sample ids takes the next S ids, so
@@ -200,16 +204,16 @@ class MCEngine:
                              num_batches_tracked=bn.num_batches_tracked if track else None)
         return ss
 
-    def _bn_gram(self, a, colsum, w, count, bn: nn.BatchNorm2d, G):
+    def _bn_gram(self, a, colsum, w, count, bn: nn.BatchNorm2d, G, a_ss=None):
         """BN scale/shift of the 1x1 conv a @ w^T from the input's moments (ops.bn_stats_from_gram); same running-statistics
-        bookkeeping as _bn."""
+        bookkeeping as _bn. a_ss: `a` is raw and relu(a * a_ss) is what the conv reads (transform inside the kernels)."""
         self.launches += 4
         mom = 0.1 if bn.momentum is None else bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
         return ops.bn_stats_from_gram(a, colsum, w, count, bn.weight.detach() if bn.weight is not None else None,
                                       bn.bias.detach() if bn.bias is not None else None, bn.eps, mom,
                                       bn.running_mean if track else None, bn.running_var if track else None,
-                                      bn.num_batches_tracked if track else None)
+                                      bn.num_batches_tracked if track else None, a_ss=a_ss)
 
     def _conv_bn(self, c: _Conv, bn, x, G, B, s0, eps, seed):
         """x: [G*B, H, W, Cin] fp16 -> raw conv output [G*B, Ho, Wo, Cout] fp16 + BN scale/shift [G, Cout, 2]."""
@@ -313,6 +317,22 @@ class MCEngine:
             M2 = y2.shape[0] // G * y2.shape[1] * y2.shape[2]
             gram = fuse_tail and self.gram_stats and ops.gram_splits(M2, G, blk.conv2.cout) > 0
             cs2 = None
+            if (gram and self.fuse_a2 and blk.conv2.cout in (64, 128, 256) and blk.conv2.cout <= self.fuse_a2_max_k
+                    and blk.conv3.cout >= 128):
+                # a2 = relu(bn2(y2)) only ever exists as operand tiles in shared memory: the second-moment contraction (which
+                # then also yields the column sums) and the fused conv3 both read the RAW y2 and transform it on the fly
+                c3 = blk.conv3
+                NB, H, W, Cm = y2.shape
+                if blk.down is not None:
+                    x = self._fused_downsample_tail(blk, y2, x, G, B, s0, eps, seed, None, a_ss=ss2)
+                    continue
+                w3 = self._sample(c3, G, s0, eps, seed)
+                y2v = y2.view(G, B * H * W, Cm)
+                ss3 = self._bn_gram(y2v, None, w3, B * H * W, blk.bn3, G, a_ss=ss2)
+                x = ops.gemm_bn_act_f16(y2v, w3, ss3, residual=x.view(G, B * H * W, c3.cout), relu=True,
+                                        a_ss=ss2).view(NB, H, W, c3.cout)
+                self.launches += 1
+                continue
             if gram:    # the activation pass also emits the column sums of a2 (first moment of conv3's closed-form statistics)
                 a2, cs2 = ops.bn_act_f16(y2, ss2, G, blk.conv2.cout, relu=True, colsum=True)
             else:
@@ -346,7 +366,7 @@ class MCEngine:
         self.launches += 1
         return feat.view(G, B, -1)
 
-    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed, cs2=None):
+    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed, cs2=None, a_ss=None):
         """relu(bn3(conv3(a2)) + bn_d(conv_d(x))) without either raw conv output in HBM: two statistics passes (recompute
         scheme), then ONE contraction over K-concatenated operands [a2 | x'] * [s3*W3 | sd*Wd]^T + (t3 + td) - the BN scales
         folded into freshly sampled weights, the shifts into the epilogue. x' = x for stride 1, else x subsampled."""
@@ -359,7 +379,9 @@ class MCEngine:
         xv = xs.view(G, M, cd.cin)
         w3 = self._sample(c3, G, s0, eps, seed)
         wd = self._sample(cd, G, s0, eps, seed)
-        if cs2 is not None:
+        if a_ss is not None:         # a2 is the raw conv2 output, bn2 + ReLU happen on the operand tiles (see _run_trunk)
+            ss3 = self._bn_gram(a2v, None, w3, M, blk.bn3, G, a_ss=a_ss)
+        elif cs2 is not None:
             ss3 = self._bn_gram(a2v, cs2, w3, M, blk.bn3, G)
         else:
             ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), M, blk.bn3, G)
@@ -372,7 +394,7 @@ class MCEngine:
                                       eps=self._eps_w(eps, c3.name, s0, G), seed=seed, layer_id=c3.layer_id, sample0=s0)
         ops.sample_weights_scaled_f16(cd.layer.mu_kernel.detach(), cd.layer.rho_kernel.detach(), G, ssd, wcat, Cm,
                                       eps=self._eps_w(eps, cd.name, s0, G), seed=seed, layer_id=cd.layer_id, sample0=s0)
-        out = ops.gemm_bn_cat_f16(a2v, xv, wcat, ops.bn_shift_sum(ss3, ssd), relu=True)
+        out = ops.gemm_bn_cat_f16(a2v, xv, wcat, ops.bn_shift_sum(ss3, ssd), relu=True, a1_ss=a_ss)
         self.launches += 9 + (cd.stride != 1)
         return out.view(NB, H, W, c3.cout)
 

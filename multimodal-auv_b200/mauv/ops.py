@@ -203,13 +203,19 @@ def gemm_stats_f16(a: torch.Tensor, w: torch.Tensor, stats_out: Optional[torch.T
 
 
 def gemm_bn_act_f16(a: torch.Tensor, w: torch.Tensor, ss: torch.Tensor, *, residual: Optional[torch.Tensor] = None,
-                    relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Second pass: out = relu?((A W^T) * scale + shift [+ residual]) -> [G, M, N] fp16."""
+                    relu: bool = True, out: Optional[torch.Tensor] = None, a_ss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Second pass: out = relu?((A W^T) * scale + shift [+ residual]) -> [G, M, N] fp16. a_ss [G, K, 2]: `a` is the RAW output
+    of the previous conv and A = relu(a * a_ss.scale + a_ss.shift) is formed on the operand tiles in shared memory."""
     lib = _lib.require_device()
     G, N, K = w.shape
     M = a.shape[1]
     if out is None:
         out = torch.empty((G, M, N), dtype=F16, device=a.device)
+    if a_ss is not None:
+        _run("mauv_gemm_bn_xf_f16", lib.mauv_gemm_bn_xf_f16, _ptr(a, F16), _ptr(a_ss, F32), _ptr(w, F16), _ptr(out, F16), _ptr(ss, F32),
+             _ptr(residual, F16), int(relu), G, M, N, K, _stream(),
+             tag=f"fused G{G} M{M} N{N} K{K} res{int(residual is not None)} xf" if _prof is not None else None)
+        return out
     _run("mauv_gemm_bn_f16", lib.mauv_gemm_bn_f16, _ptr(a, F16), _ptr(w, F16), _ptr(out, F16), None, _ptr(ss, F32),
          _ptr(residual, F16), int(relu), 2, G, M, N, K, _stream(),
          tag=f"fused G{G} M{M} N{N} K{K} res{int(residual is not None)}" if _prof is not None else None)
@@ -266,19 +272,31 @@ def subsample_f16(x: torch.Tensor, stride: int) -> torch.Tensor:
     return out
 
 
-def gemm_bn_cat_f16(a1: torch.Tensor, a2: torch.Tensor, w_cat: torch.Tensor, shift: torch.Tensor, *, relu: bool = True) -> torch.Tensor:
-    """relu?([a1 | a2] * w_cat^T + shift): a1 [G, M, K1], a2 [G, M, K2], w_cat [G, N, K1+K2], shift [G, N, 2] -> [G, M, N]"""
+def gemm_bn_cat_f16(a1: torch.Tensor, a2: torch.Tensor, w_cat: torch.Tensor, shift: torch.Tensor, *, relu: bool = True,
+                    a1_ss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu?([a1 | a2] * w_cat^T + shift): a1 [G, M, K1], a2 [G, M, K2], w_cat [G, N, K1+K2], shift [G, N, 2] -> [G, M, N].
+    a1_ss [G, K1, 2]: a1 is raw and relu(a1 * scale + shift) is formed on its operand tiles in shared memory."""
     lib = _lib.require_device()
     G, M, K1 = a1.shape
     K2 = a2.shape[2]
     N = w_cat.shape[1]
     assert w_cat.shape[2] == K1 + K2 and a2.shape[:2] == a1.shape[:2]
     out = torch.empty((G, M, N), dtype=F16, device=a1.device)
+    if a1_ss is not None:
+        _run("mauv_gemm_bn_cat_xf_f16", lib.mauv_gemm_bn_cat_xf_f16, _ptr(a1, F16), _ptr(a1_ss, F32), K1, _ptr(a2, F16), K2,
+             _ptr(w_cat, F16), _ptr(out), _ptr(shift, F32), int(relu), G, M, N, _stream(),
+             tag=f"fused G{G} M{M} N{N} K{K1 + K2} cat xf" if _prof is not None else None)
+        return out
     _run("mauv_gemm_bn_cat_f16", lib.mauv_gemm_bn_cat_f16, _ptr(a1, F16), K1, _ptr(a2, F16), K2, _ptr(w_cat, F16), _ptr(out),
          _ptr(shift, F32), int(relu), G, M, N, _stream(),
          tag=f"fused G{G} M{M} N{N} K{K1 + K2} cat" if _prof is not None else None)
     return out
 
+
+# C-ABI entry points whose kernel is a tcgen05 contraction (bench.py's roofline family: every launch of these is counted)
+TCGEN05_ENTRY_POINTS = ("mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_conv3x3_c64_f16", "mauv_gemm_bn_cat_f16",
+                        "mauv_wgrad_f16", "mauv_stem_conv_pool_f16", "mauv_gemm_bn_xf_f16", "mauv_gemm_bn_cat_xf_f16",
+                        "mauv_gram_bn_f16", "mauv_gemm_wmod_f16", "mauv_gemm_x3_f16", "mauv_conv2d_im2col_x3_f16")
 
 STREAM_CONV = __import__("os").environ.get("MAUV_STREAM_CONV", "1") != "0"
 
@@ -372,20 +390,28 @@ def gram_splits(M: int, G: int, K: int) -> int:
     return s
 
 
-def bn_stats_from_gram(a: torch.Tensor, colsum: torch.Tensor, w: torch.Tensor, count: int, gamma, beta, eps: float,
+def bn_stats_from_gram(a: torch.Tensor, colsum: Optional[torch.Tensor], w: torch.Tensor, count: int, gamma, beta, eps: float,
                        momentum: float, running_mean=None, running_var=None, num_batches_tracked=None,
-                       want_batch_stats: bool = False, splits: Optional[int] = None):
+                       want_batch_stats: bool = False, splits: Optional[int] = None, a_ss: Optional[torch.Tensor] = None):
     """BatchNorm(train) scale/shift [G, N, 2] of y = a w^T without computing y: a [G, M, K] fp16 (contiguous), colsum
-    [G, nblk, K] (bn_act_f16(colsum=True) / colsum_f16), w [G, N, K] fp16."""
+    [G, nblk, K] (bn_act_f16(colsum=True) / colsum_f16), w [G, N, K] fp16. With a_ss [G, K, 2] `a` is the RAW output of the
+    previous conv: its BatchNorm + ReLU is applied inside the second-moment kernel, which then also produces the column sums."""
     lib = _lib.require_device()
     G, M, K = a.shape
     N = w.shape[1]
-    assert w.shape[0] == G and w.shape[2] == K and colsum.shape[0] == G and colsum.shape[2] == K
+    assert w.shape[0] == G and w.shape[2] == K
     splits = splits or gram_splits(M, G, K)
     if splits == 0:
         raise _lib.MauvError(f"bn_stats_from_gram: shape M={M} K={K} is not eligible")
-    x4 = a.view(G, M, 1, K)                     # NHWC view [G*B', H, W, C] with B'=1, H=M, W=1
-    gram = wgrad_f16(x4, x4, G, splits, 1, 1, 1, 0)            # [G*splits, K, K] fp32
+    if a_ss is not None:
+        gram = torch.empty((G * splits, K, K), dtype=F32, device=a.device)
+        colsum = torch.empty((G, splits, K), dtype=F32, device=a.device)
+        _run("mauv_gram_bn_f16", lib.mauv_gram_bn_f16, _ptr(a, F16), _ptr(a_ss, F32), _ptr(gram), _ptr(colsum), G, splits, M, K, _stream(),
+             tag=f"G{G}x{splits} Cout{K} K{K} px{M // splits} xf" if _prof is not None else None)
+    else:
+        assert colsum.shape[0] == G and colsum.shape[2] == K
+        x4 = a.view(G, M, 1, K)                     # NHWC view [G*B', H, W, C] with B'=1, H=M, W=1
+        gram = wgrad_f16(x4, x4, G, splits, 1, 1, 1, 0)            # [G*splits, K, K] fp32
     out = torch.empty((G, N, 2), dtype=F32, device=a.device)
     bs = torch.empty((G, N, 2), dtype=F32, device=a.device) if want_batch_stats else None
     ws = torch.empty(lib.mauv_bn_stats_from_gram_ws_bytes(G, N, K), dtype=torch.uint8, device=a.device)

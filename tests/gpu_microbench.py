@@ -246,6 +246,27 @@ def stem(G, B, cin, iters=5):
           f"{(yp.numel() * 2 + a0.numel() * 2) / ms_f / 1e9:.2f} TB/s) + bn_act on the pooled tensor {ms_a:.3f} ms = {ms_f + ms_a:.3f} ms", flush=True)
 
 
+def tail(G, M, N, K, iters=5):
+    """Bottleneck tail from the raw conv2 output: bn_act(+colsum) -> second moments + evaluation -> fused conv3, against the
+    operand-transform chain (no a2 in HBM)."""
+    y = torch.randn(G, M, K, device=dev).half()
+    ss = torch.stack([torch.rand(G, K, device=dev) + 0.5, torch.randn(G, K, device=dev) * 0.2], dim=-1).contiguous()
+    w = (torch.randn(G, N, K, device=dev) * 0.05).half()
+    r = torch.randn(G, M, N, device=dev).half()
+    out = torch.empty(G, M, N, device=dev, dtype=torch.float16)
+    gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+    a = torch.empty_like(y)
+    t1 = timeit(lambda: ops.bn_act_f16(y, ss, G, K, relu=True, colsum=True, out=a), iters)
+    a, cs = ops.bn_act_f16(y, ss, G, K, relu=True, colsum=True, out=a)
+    t2 = timeit(lambda: ops.bn_stats_from_gram(a, cs, w, M, gamma, beta, 1e-5, 0.1), iters)
+    ss3 = ops.bn_stats_from_gram(a, cs, w, M, gamma, beta, 1e-5, 0.1)
+    t3 = timeit(lambda: ops.gemm_bn_act_f16(a, w, ss3, residual=r, relu=True, out=out), iters)
+    print(f"tail G={G} M={M} N={N} K={K}: bn_act {t1:.3f} + moments/eval {t2:.3f} + fused conv3 {t3:.3f} = {t1 + t2 + t3:.3f} ms", flush=True)
+    u2 = timeit(lambda: ops.bn_stats_from_gram(y, None, w, M, gamma, beta, 1e-5, 0.1, a_ss=ss), iters)
+    u3 = timeit(lambda: ops.gemm_bn_act_f16(y, w, ss3, residual=r, relu=True, out=out, a_ss=ss), iters)
+    print(f"   operand transform: moments/eval {u2:.3f} + fused conv3 {u3:.3f} = {u2 + u3:.3f} ms", flush=True)
+
+
 def layers():
     G, B = 4, 256
     for (M, N, K) in [(B * 4096, 256, 64), (B * 4096, 64, 256), (B * 4096, 64, 64), (B * 1024, 512, 128),
@@ -261,4 +282,4 @@ def layers():
 if __name__ == "__main__":
     cmd = sys.argv[1]
     a = [int(x) for x in sys.argv[2:]]
-    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "gram": gram, "adam": adam, "wgrad": wgrad, "bnbwd": bnbwd, "stem": stem}[cmd](*a)
+    {"gemm": gemm, "gemm_bn": gemm_bn, "conv": conv, "bnact": bnact, "mcreduce": mcreduce, "kl": kl, "sample": sample, "layers": layers, "hbm": hbm, "hbmwrite": hbmwrite, "gram": gram, "adam": adam, "wgrad": wgrad, "bnbwd": bnbwd, "stem": stem, "tail": tail}[cmd](*a)

@@ -83,3 +83,90 @@ def test_engine_with_the_fused_stem_gives_bit_identical_logits(bu, kind):
     assert torch.equal(rm_fused, stem_bn.running_mean)
     eng.stem_pool = True
     assert torch.equal(eng.forward_mc(xs, 6, seed=77, group=4, sample0=0), plain)
+
+
+def _raw_and_bn(G, M, K, seed):
+    torch.manual_seed(seed)
+    y = torch.randn(G, M, K, device="cuda").half()
+    ss = torch.stack([torch.randn(G, K, device="cuda") * 0.7, torch.randn(G, K, device="cuda") * 0.3], dim=-1).contiguous()
+    return y, ss
+
+
+@pytest.mark.parametrize("G,M,K", [(2, 8192, 64), (3, 4096 * 3, 128), (2, 4096, 256), (1, 64 * 5, 64)])
+def test_second_moments_of_bn_relu_of_a_raw_tensor_without_materialising_it(bu, G, M, K):
+    """mauv_gram_bn_f16 (BatchNorm + ReLU applied to the operand tiles in shared memory) against bn_act -> second moments of
+    the materialised tensor: the a^T a partials must be bit-identical (same fp16 operands, same chunking), the column sums
+    equal to fp32 summation-order noise, and the BatchNorm scale/shift that follow within 1e-6."""
+    from mauv import _lib, ops
+    lib = _lib.require_device()
+    y, ss = _raw_and_bn(G, M, K, 11 + K)
+    a, cs = ops.bn_act_f16(y, ss, G, K, relu=True, colsum=True)
+    splits = ops.gram_splits(M, G, K)
+    assert splits > 0
+    a4 = a.view(G, M, 1, K)
+    ref = ops.wgrad_f16(a4, a4, G, splits, 1, 1, 1, 0)
+    gram = torch.empty_like(ref)
+    colsum = torch.empty(G, splits, K, device="cuda")
+    _lib.check(lib.mauv_gram_bn_f16(y.data_ptr(), ss.data_ptr(), gram.data_ptr(), colsum.data_ptr(), G, splits, M, K,
+                                    torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(gram, ref)
+    cs_ref = a.float().view(G, splits, M // splits, K).sum(2)
+    assert torch.allclose(colsum, cs_ref, rtol=2e-6, atol=1e-3)
+    assert torch.allclose(colsum.sum(1), cs.sum(1), rtol=1e-5, atol=1e-2)
+    w = (torch.randn(G, 4 * K, K, device="cuda") * 0.05).half()
+    gamma, beta = torch.rand(4 * K, device="cuda") + 0.5, torch.randn(4 * K, device="cuda") * 0.1
+    s_ref = ops.bn_stats_from_gram(a, cs, w, M, gamma, beta, 1e-5, 0.1)
+    s_xf = ops.bn_stats_from_gram(y, None, w, M, gamma, beta, 1e-5, 0.1, a_ss=ss)
+    assert torch.allclose(s_xf, s_ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("G,M,N,K,res", [(2, 4096, 256, 64, True), (3, 1000, 512, 128, True), (2, 2048, 1024, 256, True),
+                                         (2, 777, 256, 64, False)])
+def test_fused_tail_on_the_raw_conv2_output_is_bit_identical_to_bn_act_then_fused_tail(bu, G, M, N, K, res):
+    """mauv_gemm_bn_xf_f16 == mauv_bn_act_f16 -> mauv_gemm_bn_f16 (mode 2), torch.equal: the transform warps produce exactly
+    bn_act's fp16 values, so the tensor core sees the same operands (ragged M: the zero-filled rows are never stored)."""
+    from mauv import ops
+    y, ss = _raw_and_bn(G, M, K, 5 + N)
+    w = (torch.randn(G, N, K, device="cuda") * 0.05).half()
+    ss3 = torch.stack([torch.rand(G, N, device="cuda") + 0.5, torch.randn(G, N, device="cuda") * 0.2], dim=-1).contiguous()
+    r = torch.randn(G, M, N, device="cuda").half() if res else None
+    a = ops.bn_act_f16(y, ss, G, K, relu=True)
+    ref = ops.gemm_bn_act_f16(a, w, ss3, residual=r, relu=True)
+    got = ops.gemm_bn_act_f16(y, w, ss3, residual=r, relu=True, a_ss=ss)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("G,M,N,K1,K2", [(2, 4096, 256, 64, 64), (2, 1500, 512, 128, 256), (1, 2048, 1024, 256, 512)])
+def test_k_concatenated_tail_with_a_raw_first_operand(bu, G, M, N, K1, K2):
+    """mauv_gemm_bn_cat_xf_f16: only the a2 k-blocks are transformed, the downsample branch's input is read as is."""
+    from mauv import ops
+    y, ss = _raw_and_bn(G, M, K1, 3 + N)
+    x = torch.randn(G, M, K2, device="cuda").half()
+    wcat = (torch.randn(G, N, K1 + K2, device="cuda") * 0.05).half()
+    shift = torch.stack([torch.ones(G, N, device="cuda"), torch.randn(G, N, device="cuda") * 0.2], dim=-1).contiguous()
+    a = ops.bn_act_f16(y, ss, G, K1, relu=True)
+    ref = ops.gemm_bn_cat_f16(a, x, wcat, shift, relu=True)
+    got = ops.gemm_bn_cat_f16(y, x, wcat, shift, relu=True, a1_ss=ss)
+    assert torch.equal(got, ref)
+
+
+def test_engine_without_a2_in_hbm_agrees_with_the_materialising_plan(bu):
+    """MCEngine.fuse_a2 on / off on the multimodal net at 256 x 256: the only arithmetic difference is the summation order
+    of conv3's first-moment column sums (fp32), i.e. BatchNorm statistics equal to ~1e-7 relative; logits must agree far
+    inside the fp16-operand tolerance of DESIGN 4.3 (1.5e-3 of scale against the fp32 oracle)."""
+    import bnn_oracle as O
+    from mauv.engine import MCEngine
+    _, model = bu.build_pair("multimodal")
+    img, bathy, sss, _ = O.synthetic_batch(3, size=256)
+    xs = [t.cuda() for t in (img, bathy, sss)]
+    eng = MCEngine(model)
+    assert eng.fuse_a2
+    a = eng.forward_mc(xs, 4, seed=5, group=4, sample0=0)
+    assert torch.equal(a, eng.forward_mc(xs, 4, seed=5, group=3, sample0=0))
+    eng.fuse_a2 = False
+    b = eng.forward_mc(xs, 4, seed=5, group=4, sample0=0)
+    scale = b.abs().max().item()
+    err = (a - b).abs().max().item() / scale
+    print(f"fuse_a2 on/off: max |dlogit| / scale = {err:.2e}")
+    assert err < 1.5e-3, err
+    assert torch.equal(a.mean(0).argmax(-1), b.mean(0).argmax(-1))

@@ -51,7 +51,7 @@ print(f"one step = {len(step)} launches, {tot:.2f} ms of serialised kernel time,
 print("| kernel | launches | total ms | share | DRAM read GB | DRAM write GB | GB/s |\n|---|---|---|---|---|---|---|")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{k}` | {a[0]} | {a[1]:.2f} | {100 * a[1] / tot:.1f}% | {a[2] / 1e9:.2f} | {a[3] / 1e9:.2f} | {(a[2] + a[3]) / max(a[1], 1e-9) / 1e6:.0f} |")
-tc = [a for k, a in agg.items() if "gemm_f16_tc_kernel" in k or "conv3x3_c64_stream" in k]
+tc = [a for k, a in agg.items() if "gemm_f16_tc_kernel" in k or "conv3x3_c64_stream" in k or "stem_conv_pool" in k]
 n_tc = sum(a[0] for a in tc)
 traffic = sum(a[2] + a[3] for a in tc) / max(n_tc, 1)
 share = sum(a[1] for a in tc) / tot
