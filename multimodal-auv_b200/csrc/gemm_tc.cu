@@ -41,6 +41,7 @@ struct GemmParams {
   int k_blocks;     // ceil(K / 64)
   int G;            // samples in this launch
   int m_tiles, n_tiles;
+  int stat_tiles;   // leading dimension of the statistics buffer (128-row tiles per sample); == m_tiles except for M-stacked tiles
   long long total_tiles;
   int a_mode;       // 0 = tiled [K, M, G] ; 1 = im2col (C, W, H, N)
   int a_batch_mul;  // 0 when A is shared by all samples (stem), else 1
@@ -118,6 +119,10 @@ struct SmemLayout {
 // PLAIN = 2: the stem's sample-stacked instance (A shared by all samples, 4 samples of 64 channels side by side in one
 // 128 x 256 tile), again with every other flag folded: the stem writes the largest tensor of the network and ran the
 // generic epilogue (2.1 TB/s of output against 4.1 TB/s for the same volume through the PLAIN = 1 instance).
+// PLAIN = 3 (BN = 256, N <= 128, im2col A): TWO 128-row A tiles per CTA tile share one B tile - accumulator columns 0..127 hold
+// rows m0 .. m0+127, columns 128..255 rows m0+128 .. m0+255. The N = 128 3x3 convs (K = 1152) were bound by the operand
+// stream into shared memory (16 KB A + 16 KB B per 128 x 128 x 64 block = one 128-byte TMA row per MMA clock); sharing B
+// moves 25 % fewer bytes and rows per flop.
 template <int BN, int EPI, int PLAIN, bool XF = false>
 __global__ void __launch_bounds__(XF ? 448 : 384, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -130,6 +135,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int f_a_wrap_kb = PLAIN ? 0 : p.a_wrap_kb, f_a_cwrap = PLAIN ? 0 : p.a_cwrap, f_b_mod = PLAIN ? 0 : p.b_mod;
   const int f_batch_mul = PLAIN == 2 ? 0 : (PLAIN ? 1 : p.a_batch_mul);
   const int f_N = PLAIN == 2 ? 64 : p.N;            // channels per sample (only read by the stacked-mode index math)
+  constexpr bool MSTACK = (PLAIN == 3);             // two M tiles per CTA tile (p.m_tiles counts 256-row pairs in the tile index)
+  static_assert(!MSTACK || (BN == 256 && EPI == EPI_STORE_STATS), "M-stacked tiles: BN = 256 accumulator columns, store + statistics");
   const float* const f_bias = PLAIN ? nullptr : p.bias;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
 
@@ -231,9 +238,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int g, m_tile, n_tile;
         decode(tile, g, m_tile, n_tile);
-        const int m0 = m_tile * BM;
-        // im2col start pixel of this tile
-        int iq = 0, ip = 0, in_ = 0;
+        const int m0 = m_tile * (MSTACK ? 2 * BM : BM);
+        // im2col start pixel of this tile (M-stacked: of its two 128-row halves)
+        int iq = 0, ip = 0, in_ = 0, iq1 = 0, ip1 = 0, in1 = 0;
         if (p.a_mode == 1) {
           const int hw = p.Ho * p.Wo;
           const int b = m0 / hw;
@@ -241,6 +248,13 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ip = r2 / p.Wo;
           iq = r2 - ip * p.Wo;
           in_ = g * p.imgs_per_sample + b;
+          if (MSTACK) {
+            const int b1 = (m0 + BM) / hw;
+            const int r3 = (m0 + BM) - b1 * hw;
+            ip1 = r3 / p.Wo;
+            iq1 = r3 - ip1 * p.Wo;
+            in1 = g * p.imgs_per_sample + b1;
+          }
         }
         if (f_mn) {
           // weight-gradient mode: 64-pixel k-blocks; A = 2 boxes of 64 output channels, B = BN/64 boxes of 64 columns
@@ -298,8 +312,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), cb * BK, iq * p.stride - p.pad,
                                ip * p.stride - p.pad, in_, static_cast<uint16_t>(s),
                                static_cast<uint16_t>(r));
+            if (MSTACK)      // second 128-row half; stage layout: A0 16 KB | A1 16 KB | B 16 KB
+              tma_load_im2col_4d(a_dst + L::kABytes, &tmA, full_bar(stage), cb * BK, iq1 * p.stride - p.pad,
+                                 ip1 * p.stride - p.pad, in1, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
           }
-          if (f_stack > 1) tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, g * f_N, 0);   // flattened [G*N][K]
+          if (MSTACK) tma_load_3d(a_dst + 2 * L::kABytes, &tmB, full_bar(stage), kb * BK, 0, g);
+          else if (f_stack > 1) tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, g * f_N, 0);   // flattened [G*N][K]
           else tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, f_b_mod ? g % f_b_mod : g);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -338,6 +356,16 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_f16_ss(d_tmem, a_desc + 128u * k, b_desc + 128u * k, idesc_mn, (kb | k) != 0 ? 1u : 0u);
+          } else if (MSTACK) {
+            constexpr uint32_t idesc_half = umma_idesc_f16(BM, 128);
+            const uint64_t a0_desc = umma_smem_desc_sw128(a_addr);
+            const uint64_t a1_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
+            const uint64_t b_desc = umma_smem_desc_sw128(a_addr + 2 * L::kABytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_f16_ss(d_tmem, a0_desc + 2u * k, b_desc + 2u * k, idesc_half, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_ss(d_tmem + 128u, a1_desc + 2u * k, b_desc + 2u * k, idesc_half, (kb | k) != 0 ? 1u : 0u);
+            }
           } else {
             const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
             const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
@@ -728,10 +756,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int g, m_tile, n_tile;
       decode(tile, g, m_tile, n_tile);
       const uint32_t acc = it & 1u;
-      const int row0 = m_tile * BM + ew * 32;
+      // M-stacked tiles: column blocks 0,1 belong to rows m0 .., blocks 2,3 to rows m0 + 128 ..
+      const int row0 = MSTACK ? m_tile * (2 * BM) + (cb >> 1) * BM + ew * 32 : m_tile * BM + ew * 32;
       int rmax = p.M - row0;            // valid rows of this warp's 32-row slab
       rmax = rmax < 0 ? 0 : (rmax > 32 ? 32 : rmax);
-      const int n0 = n_tile * BN;
+      const int n0 = MSTACK ? 0 : n_tile * BN;
       const float* bias = f_bias ? f_bias + static_cast<long long>(g) * p.N + n0 : nullptr;
       float* stat_buf = stat_smem + (it & 1u) * (4 * BN * 2);
       // next work item of this warp
@@ -744,7 +773,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int col0 = cb * 64;
       // stacked mode: this 64-column block belongs to sample gb at channel offset nb
       const int gb = (f_stack > 1) ? g + col0 / f_N : g;
-      const int nb = (f_stack > 1) ? col0 % f_N : n0 + col0;
+      const int nb = MSTACK ? (cb & 1) * 64 : ((f_stack > 1) ? col0 % f_N : n0 + col0);
       const bool cols_ok = (f_stack > 1) ? (gb < p.G) : (nb < p.N);     // warp uniform
 
       tmem_ld_wait();                   // ra / rb of this item are in registers
@@ -890,8 +919,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int jj = es; jj < 64 * ((kBlocks - cset + kColSets - 1) / kColSets); jj += kSetThreads) {
           const int j = (cset + (jj >> 6) * kColSets) * 64 + (jj & 63);        // this set's column blocks
           const int gj = (f_stack > 1) ? g + j / f_N : g;
-          const int nj = (f_stack > 1) ? j % f_N : n0 + j;
-          if (nj < p.N && gj < p.G) {
+          const int nj = MSTACK ? (j & 127) : ((f_stack > 1) ? j % f_N : n0 + j);
+          const int tj = MSTACK ? 2 * m_tile + (j >> 7) : m_tile;            // 128-row statistics tile
+          if (nj < p.N && gj < p.G && tj < p.stat_tiles) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -899,7 +929,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               b += stat_buf[(w * BN + j) * 2 + 1];
             }
             float2* dst = reinterpret_cast<float2*>(p.stats) +
-                          (static_cast<long long>(gj) * p.m_tiles + m_tile) * p.N + nj;
+                          (static_cast<long long>(gj) * p.stat_tiles + tj) * p.N + nj;
             *dst = make_float2(a, b);
           }
         }
@@ -980,8 +1010,19 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
   const int n_out = (p.split || p.out_f32) ? 2 * p.N : p.N;      // out_f32: the (unused) map spans the same bytes
   if (int rc = make_tiled_map(&tmY, p.y, n_out, p.M, p.G, static_cast<int64_t>(p.M) * n_out, 32)) return rc;
   p.m_tiles = static_cast<int>(ceil_div_i64(p.M, BM));
+  p.stat_tiles = p.m_tiles;
   p.n_tiles = static_cast<int>(ceil_div_i64(p.N, bn));
   p.total_tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.G;
+  // M-stacked tiles (PLAIN = 3): the N = 128 im2col convs (3x3, K = 1152) are bound by the operand stream into shared memory
+  static const bool mstack_on = [] { const char* e = getenv("MAUV_MSTACK"); return !(e && e[0] == '0'); }();
+  const bool mstack = mstack_on && epi == EPI_STORE_STATS && bn == 128 && p.a_mode == 1 && p.M >= 2 * BM && p.stack <= 1 && !p.split &&
+                      !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap && !p.b_mod && !p.bias &&
+                      p.a_batch_mul == 1 && !p.xf_ss && p.k_blocks >= 8;
+  if (mstack) {
+    p.m_tiles = static_cast<int>(ceil_div_i64(p.M, 2 * BM));       // 256-row pairs
+    p.n_tiles = 1;
+    p.total_tiles = static_cast<long long>(p.m_tiles) * p.G;
+  }
   if (p.stack > 1) {
     p.n_tiles = 1;
     p.g_blocks = static_cast<int>(ceil_div_i64(p.G, p.stack));
@@ -1009,6 +1050,7 @@ int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cuda
       default: return launch_gemm<256, 2>(tmA, tmB, tmY, tmR, p, stream);
     }
   }
+  if (mstack) return launch_gemm_t<256, 0, 3>(tmA, tmB, tmY, tmR, p, stream);
   switch (bn) {
     case 64: return launch_gemm<64, 0>(tmA, tmB, tmY, tmR, p, stream);
     case 128: return launch_gemm<128, 0>(tmA, tmB, tmY, tmR, p, stream);

@@ -170,3 +170,34 @@ def test_engine_without_a2_in_hbm_agrees_with_the_materialising_plan(bu):
     print(f"fuse_a2 on/off: max |dlogit| / scale = {err:.2e}")
     assert err < 1.5e-3, err
     assert torch.equal(a.mean(0).argmax(-1), b.mean(0).argmax(-1))
+
+
+@pytest.mark.parametrize("G,B,H,Cin,Cout,k,stride", [(2, 3, 12, 128, 128, 3, 1), (3, 4, 32, 128, 128, 3, 1), (2, 2, 32, 128, 128, 3, 2),
+                                                      (2, 5, 16, 256, 128, 1, 2), (1, 3, 20, 128, 96, 3, 1)])
+def test_m_stacked_tiles_of_the_n128_im2col_convs(bu, G, B, H, Cin, Cout, k, stride):
+    """gemm_f16_tc_kernel<256, 0, 3> (two 128-row A tiles share one B tile; taken by im2col convs with 64 < N <= 128 and
+    K >= 512) against F.conv2d on the same fp16 operands: outputs within the fp16 rounding of the result, per-channel
+    statistics equal to the sums of the STORED values; ragged M (second half tile partial or empty), strides, N < 128."""
+    import torch.nn.functional as F
+    from mauv import ops
+    torch.manual_seed(G * 7 + B)
+    x = (torch.randn(G * B, H, H, Cin, device="cuda") * 0.5).half()
+    w = (torch.randn(G, Cout, k, k, Cin, device="cuda") * 0.1).half()
+    pad = k // 2
+    y, st = ops.conv2d_im2col_f16(x, w.view(G, Cout, -1), G, k, k, stride, pad, stats=True)
+    refs = []
+    for g in range(G):
+        xg = x[g * B:(g + 1) * B].float().permute(0, 3, 1, 2)
+        refs.append(F.conv2d(xg, w[g].float().permute(0, 3, 1, 2), None, stride, pad).permute(0, 2, 3, 1))
+    ref = torch.cat(refs)
+    assert y.shape == ref.shape
+    assert (y.float() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-3
+    yv = y.float().view(G, -1, Cout)
+    M = yv.shape[1]
+    assert st.shape == (G, (M + 127) // 128, Cout, 2)
+    s = st.double().sum(1)
+    assert torch.allclose(s[..., 0], yv.double().sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(s[..., 1], (yv.double() ** 2).sum(1), rtol=1e-5, atol=1e-2)
+    # per-tile partials: tile t covers rows 128 t .. 128 t + 127
+    t_last = (M + 127) // 128 - 1
+    assert torch.allclose(st[:, t_last, :, 0].double(), yv[:, 128 * t_last:].double().sum(1), rtol=1e-5, atol=1e-2)
