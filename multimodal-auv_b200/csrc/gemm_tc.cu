@@ -123,8 +123,14 @@ struct SmemLayout {
 // rows m0 .. m0+127, columns 128..255 rows m0+128 .. m0+255. The N = 128 3x3 convs (K = 1152) were bound by the operand
 // stream into shared memory (16 KB A + 16 KB B per 128 x 128 x 64 block = one 128-byte TMA row per MMA clock); sharing B
 // moves 25 % fewer bytes and rows per flop.
+// XF instances: the fused-BN epilogue needs its ~166 registers (a 448-thread block is capped at 128: it spilled), so there the
+// transform runs on the two otherwise idle warps 2 and 3; the second-moment (gram) instance has a light epilogue and takes four
+// transform warps (2, 3, 12, 13) in a 448-thread block.
+template <int EPI> constexpr int xf_warps() { return EPI == 2 ? 2 : 4; }
+template <int EPI, bool XF> constexpr int gemm_threads() { return (XF && xf_warps<EPI>() == 4) ? 448 : 384; }
+
 template <int BN, int EPI, int PLAIN, bool XF = false>
-__global__ void __launch_bounds__(XF ? 448 : 384, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI, XF>(), 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const GemmParams p) {
@@ -181,7 +187,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int w = 0; w < L::kEpiWarps; ++w)
         for (int j = 0; j < 3; ++j) mbar_init(res_bar(w, j), 1);
     if (XF)
-      for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), 4);       // one arrive per transform warp
+      for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), xf_warps<EPI>());       // one arrive per transform warp
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -382,11 +388,13 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (XF && (warp == 2 || warp == 3 || warp >= 12)) {
+    constexpr int kXfThreads = 32 * xf_warps<EPI>();      // 64 or 128
+    constexpr uint32_t kXfRowStep = kXfThreads / 8;       // rows between two chunks of one thread
     // ===================== operand transform (XF instances) =====================
     // The activation operand arrives RAW (the previous conv's output); BatchNorm + ReLU of that layer is applied here, in
     // place, to every TMA-loaded tile before the MMA warp may read it: a = relu(y * scale + shift), fp32 math and one fp16
-    // rounding - exactly bn_act_kernel's arithmetic, so the MMA sees bit-identical operands. 128 threads: thread t owns the
-    // logical 16-byte chunk lc = t & 7 (8 channels) of rows (t >> 3) + 16 i; the physical chunk is lc ^ (row & 7) (128B
+    // rounding - exactly bn_act_kernel's arithmetic, so the MMA sees bit-identical operands. kXfThreads threads: thread t owns the
+    // logical 16-byte chunk lc = t & 7 (8 channels) of rows (t >> 3) + kXfRowStep i; the physical chunk is lc ^ (row & 7) (128B
     // swizzle). Rows past the tensor (TMA zero fill) become relu(shift): K-major tiles never store those rows; gram-mode
     // chunks are whole multiples of 64 pixels.
     static_assert(!XF || EPI != EPI_FUSED_BN || BN >= 128, "the (scale, shift) table of the XF fused epilogue lives behind my_ss");
@@ -431,13 +439,13 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       decode(tile, g, m_tile, n_tile);
       const int smp = f_mn ? g / p.xf_splits : g;
       if (smp != cur_smp) {        // this sample's (scale, shift) table; the 4 warps walk the same tile sequence
-        asm volatile("bar.sync 3, 128;" ::: "memory");
-        for (int i = static_cast<int>(t); i < p.xf_K; i += 128) {
+        asm volatile("bar.sync 3, %0;" ::"n"(kXfThreads) : "memory");
+        for (int i = static_cast<int>(t); i < p.xf_K; i += kXfThreads) {
           const float2 v = __ldg(p.xf_ss + static_cast<long long>(smp) * p.xf_K + i);
           xf_tab[i] = v.x;
           xf_tab[256 + i] = v.y;
         }
-        asm volatile("bar.sync 3, 128;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kXfThreads) : "memory");
         cur_smp = smp;
       }
       if (EPI == EPI_STORE_STATS && f_mn) {
@@ -509,16 +517,16 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             unsigned long long sc[4], sh[4];
             load_ss(64u * kb + 8u * lc, sc, sh);
 #pragma unroll
-            for (uint32_t half = 0; half < 2; ++half) {           // 4 loads in flight, then 4 transforms + stores
+            for (uint32_t grp = 0; grp < 128u / kXfRowStep / 4u; ++grp) {      // 4 loads in flight, then 4 transforms + stores
               uint32_t wv[4][4];
 #pragma unroll
               for (uint32_t i = 0; i < 4; ++i) {
-                const uint32_t row = r0 + 16u * (4u * half + i);
+                const uint32_t row = r0 + kXfRowStep * (4u * grp + i);
                 lds128(a_dst + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
               }
 #pragma unroll
               for (uint32_t i = 0; i < 4; ++i) {
-                const uint32_t row = r0 + 16u * (4u * half + i);
+                const uint32_t row = r0 + kXfRowStep * (4u * grp + i);
                 xform8(wv[i], sc, sh);
                 sts128(a_dst + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
               }
@@ -674,44 +682,58 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           ss_g = gb; ss_n = nb;
         }
+        // One half = 4 chunks of 8 channels of this lane's row. The shared-memory reads are batched - all four residual chunks
+        // first, then (scale, shift) for two chunks at a time - and the two chunks' arithmetic is interleaved: the ncu source view
+        // of the chunk-at-a-time version had the epilogue warps (2 per scheduler) 32 % in `wait` and 19 % in `short_scoreboard`
+        // stalls on eight serial LDS -> FFMA2 -> FADD2 -> F2FP -> HMNMX2 -> STS chains per block.
         auto transform_half = [&](const uint32_t (&r)[32], int half) {
+          uint32_t rr[4][4];
+          if (p.has_res) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int q = half * 4 + q4;                 // 16-byte chunk of the 128-byte row = channels 8q .. 8q+7
-            const uint32_t* src = &r[q4 * 8];
-            const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4);
-            unsigned long long sc[4], sh[4], v[4];
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[0]), "=l"(sc[1]) : "r"(my_ss_addr + q * 32u));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[2]), "=l"(sc[3]) : "r"(my_ss_addr + q * 32u + 16u));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[0]), "=l"(sh[1]) : "r"(my_ss_addr + 256u + q * 32u));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[2]), "=l"(sh[3]) : "r"(my_ss_addr + 256u + q * 32u + 16u));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              unsigned long long a2;
-              asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(src[2 * j]), "r"(src[2 * j + 1]));
-              asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v[j]) : "l"(a2), "l"(sc[j]), "l"(sh[j]));
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(half * 4 + q4) ^ (lane & 7u)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[q4][0]), "=r"(rr[q4][1]), "=r"(rr[q4][2]), "=r"(rr[q4][3]) : "r"(addr));
             }
-            if (p.has_res) {
-              uint32_t rr[4];
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(addr));
+          }
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            unsigned long long sc[2][4], sh[2][4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t q = static_cast<uint32_t>(half * 4 + pr * 2 + c);
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[c][0]), "=l"(sc[c][1]) : "r"(my_ss_addr + q * 32u));
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sc[c][2]), "=l"(sc[c][3]) : "r"(my_ss_addr + q * 32u + 16u));
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[c][0]), "=l"(sh[c][1]) : "r"(my_ss_addr + 256u + q * 32u));
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sh[c][2]), "=l"(sh[c][3]) : "r"(my_ss_addr + 256u + q * 32u + 16u));
+            }
+            uint32_t h[2][4];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int q4 = pr * 2 + c;
+              const uint32_t* src = &r[q4 * 8];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[j]));
-                unsigned long long f2;
-                asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(f.x), "f"(f.y));
-                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v[j]) : "l"(f2));
+                unsigned long long a2, v;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(src[2 * j]), "r"(src[2 * j + 1]));
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(a2), "l"(sc[c][j]), "l"(sh[c][j]));
+                if (p.has_res) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[q4][j]));
+                  unsigned long long f2;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(f.x), "f"(f.y));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(f2));
+                }
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+                __half2 hh = __floats2half2_rn(lo, hi);
+                if (p.relu) hh = __hmax2(hh, __float2half2_rn(0.f));      // ReLU after rounding == rounding after ReLU
+                h[c][j] = *reinterpret_cast<uint32_t*>(&hh);
               }
             }
-            uint32_t h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float lo, hi;
-              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[j]));
-              __half2 hh = __floats2half2_rn(lo, hi);
-              if (p.relu) hh = __hmax2(hh, __float2half2_rn(0.f));      // ReLU after rounding == rounding after ReLU
-              h[j] = *reinterpret_cast<uint32_t*>(&hh);
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(half * 4 + pr * 2 + c) ^ (lane & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[c][0]), "r"(h[c][1]), "r"(h[c][2]), "r"(h[c][3]) : "memory");
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
           }
         };
         transform_half(ra, 0);
@@ -961,7 +983,7 @@ int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF><<<static_cast<unsigned>(grid), XF ? 448 : 384, L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
+  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF><<<static_cast<unsigned>(grid), gemm_threads<EPI, XF>(), L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
