@@ -93,22 +93,26 @@ enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2, EPI_STATS_T = 
 // is a channel, so every epilogue thread sums its own channel over the tile's pixels in registers - no shuffles, no
 // shared memory, no output. Pixels past M are zero-filled by TMA and contribute nothing.
 
-template <int BN, int EPI = 0>
+template <int BN, int EPI = 0, bool GRAMX = false>
 struct SmemLayout {
   // the fused epilogue needs 3 staging buffers per warp (residual prefetch / transform / store in flight) and is
-  // only used for short-K (HBM-bound) layers, so it trades pipeline depth for staging space
-  static constexpr int kStages = (EPI == 2) ? ((BN == 256) ? 2 : 3) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
+  // only used for short-K (HBM-bound) layers, so it trades pipeline depth for staging space.
+  // GRAMX (second moments with the operand transform): only the B boxes are loaded (the A descriptor aliases them), so a stage
+  // is BN x 128 bytes and the ring is 2x deeper - every stage is also held for the ~700 clocks of its in-place transform, and
+  // 6 x 8 KB in flight per SM did not cover the HBM latency
+  static constexpr int kStages = GRAMX ? ((BN == 256) ? 4 : (BN == 128 ? 8 : 12))
+                                       : ((EPI == 2) ? ((BN == 256) ? 2 : 3) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
   static constexpr int kOutBufs = (EPI == 2) ? 3 : 2;
   // epilogue warps: one set of 4 (TMEM lane quarters) per 64-column block in flight; two sets when BN >= 128
   static constexpr int kEpiWarps = (BN >= 128) ? 8 : 4;
-  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kABytes = GRAMX ? 0 : BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging for the TMA store: per epilogue warp 2 buffers of 32 rows x 64 fp16 (128B-swizzled rows)
   static constexpr int kOutBufBytes = 32 * 64 * 2;
   static constexpr int kOutBytes = kEpiWarps * kOutBufs * kOutBufBytes;
   static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
-  static constexpr int kBarBytes = 512;   // pipeline + TMEM barriers, TMEM pointer, 3 residual barriers per epilogue warp
+  static constexpr int kBarBytes = 1024;  // pipeline + TMEM barriers, TMEM pointer, 3 residual barriers per epilogue warp, transform barriers
   static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes;
 };
 
@@ -127,6 +131,9 @@ struct SmemLayout {
 // transform runs on the two otherwise idle warps 2 and 3; the second-moment (gram) instance has a light epilogue and takes four
 // transform warps (2, 3, 12, 13) in a 448-thread block.
 template <int EPI> constexpr int xf_warps() { return EPI == 2 ? 2 : 4; }
+// second-moment instance: k-blocks in transform at the same time (one group of 4 / split warps each), bounded by the ring depth
+template <int BN> constexpr int xf_gram_split() { return BN == 256 ? 2 : 4; }
+template <int BN, int EPI> constexpr int xf_arrivals() { return EPI == 2 ? 2 : 4 / xf_gram_split<BN>(); }
 template <int EPI, bool XF> constexpr int gemm_threads() { return (XF && xf_warps<EPI>() == 4) ? 448 : 384; }
 
 template <int BN, int EPI, int PLAIN, bool XF = false>
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, XF>(), 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const GemmParams p) {
-  using L = SmemLayout<BN, EPI>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS>;
   constexpr int kStages = L::kStages;
   const int f_stack = PLAIN == 2 ? 4 : (PLAIN ? 1 : p.stack), f_split = PLAIN ? 0 : p.split, f_out_f32 = PLAIN ? 0 : p.out_f32;
   const int f_mn = PLAIN ? 0 : p.mn, f_gram = PLAIN ? 0 : p.gram, f_a2_kb = PLAIN ? 0 : p.a2_kb;
@@ -187,7 +194,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int w = 0; w < L::kEpiWarps; ++w)
         for (int j = 0; j < 3; ++j) mbar_init(res_bar(w, j), 1);
     if (XF)
-      for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), xf_warps<EPI>());       // one arrive per transform warp
+      for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), xf_arrivals<BN, EPI>());   // one arrive per warp that transforms the stage
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -433,7 +440,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     };
     int stage = 0, cur_smp = -1;
-    uint32_t phase = 0;
+    uint32_t phase = 0, kbc = 0;           // kbc: k-blocks seen so far (all tiles)
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int g, m_tile, n_tile;
       decode(tile, g, m_tile, n_tile);
@@ -449,57 +456,72 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         cur_smp = smp;
       }
       if (EPI == EPI_STORE_STATS && f_mn) {
-        // gram mode: BN/64 boxes of [64 pixels][64 channels] per k-block, channels 64 j + 8 lc .. of box j
+        // gram mode: BN/64 boxes of [64 pixels][64 channels] per k-block, channels 64 j + 8 glc .. of box j. A k-block is only
+        // 8 KB per box and every hand-over costs a fixed ~400 clocks (mbarrier wait, fence.proxy.async, arrive), so the four
+        // warps do NOT share one k-block: they form kSplit groups that take every kSplit-th k-block (ring depth permitting),
+        // i.e. kSplit k-blocks are being transformed at any time.
         constexpr int kBoxes = BN / 64;
-        unsigned long long cs[kBoxes][4];                         // packed column sums of channels 64 j + 8 lc + (2q, 2q+1)
+        constexpr int kGw = 4 / xf_gram_split<BN>();              // warps per group
+        constexpr uint32_t kGRowStep = 4u * kGw;                  // rows between two chunks of one thread
+        constexpr uint32_t kGChunks = 64u / kGRowStep;            // chunks per box per thread: 16, 8 or 4
+        const int grp = tw / kGw;
+        const uint32_t tg = static_cast<uint32_t>(tw % kGw) * 32u + lane_id();
+        const uint32_t glc = tg & 7u, gr0 = tg >> 3;
+        unsigned long long cs[kBoxes][4];                         // packed column sums of channels 64 j + 8 glc + (2q, 2q+1)
 #pragma unroll
         for (int j = 0; j < kBoxes; ++j)
 #pragma unroll
           for (int q = 0; q < 4; ++q) cs[j][q] = 0ull;
         const int b_boxes = (p.N + 63) / 64;                      // one n-tile holds all K columns (gram)
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          const uint32_t b_dst = tiles_base + stage * L::kStageBytes + L::kABytes;
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++kbc) {
+          if (static_cast<int>(kbc % xf_gram_split<BN>()) == grp) {
+            mbar_wait(full_bar(stage), phase);
+            const uint32_t b_dst = tiles_base + stage * L::kStageBytes + L::kABytes;
 #pragma unroll
-          for (int j = 0; j < kBoxes; ++j) {
-            if (j < b_boxes) {
-              unsigned long long sc[4], sh[4];
-              uint32_t wv[4][4];
-              load_ss(64u * j + 8u * lc, sc, sh);
+            for (int j = 0; j < kBoxes; ++j) {
+              if (j < b_boxes) {
+                unsigned long long sc[4], sh[4];
+                load_ss(64u * j + 8u * glc, sc, sh);
 #pragma unroll
-              for (uint32_t i = 0; i < 4; ++i) {                  // all four loads first: one exposed shared-memory latency
-                const uint32_t row = r0 + 16u * i;
-                lds128(b_dst + j * 8192u + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
-              }
+                for (uint32_t c4 = 0; c4 < kGChunks / 4u; ++c4) {
+                  uint32_t wv[4][4];
 #pragma unroll
-              for (uint32_t i = 0; i < 4; ++i) {
-                const uint32_t row = r0 + 16u * i;
-                xform8(wv[i], sc, sh);
-                sts128(b_dst + j * 8192u + row * 128u + ((lc ^ (row & 7u)) << 4), wv[i]);
+                  for (uint32_t i = 0; i < 4; ++i) {                // four loads first: one exposed shared-memory latency
+                    const uint32_t row = gr0 + kGRowStep * (4u * c4 + i);
+                    lds128(b_dst + j * 8192u + row * 128u + ((glc ^ (row & 7u)) << 4), wv[i]);
+                  }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {        // column sums of the values the tensor core will read
-                  const float2 fo = __half22float2(*reinterpret_cast<__half2*>(&wv[i][q]));
-                  unsigned long long f2;
-                  asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(fo.x), "f"(fo.y));
-                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(cs[j][q]) : "l"(f2));
+                  for (uint32_t i = 0; i < 4; ++i) {
+                    const uint32_t row = gr0 + kGRowStep * (4u * c4 + i);
+                    xform8(wv[i], sc, sh);
+                    sts128(b_dst + j * 8192u + row * 128u + ((glc ^ (row & 7u)) << 4), wv[i]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {        // column sums of the values the tensor core will read
+                      const float2 fo = __half22float2(*reinterpret_cast<__half2*>(&wv[i][q]));
+                      unsigned long long f2;
+                      asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(fo.x), "f"(fo.y));
+                      asm("add.rn.f32x2 %0, %0, %1;" : "+l"(cs[j][q]) : "l"(f2));
+                    }
+                  }
                 }
               }
             }
+            fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(xf_ready(stage));
           }
-          fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane_id() == 0) mbar_arrive(xf_ready(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (p.xf_colsum && m_tile == 0) {
-          // column sums of the transformed chunk: 16 row groups per channel, combined in a fixed order
+          // column sums of the transformed chunk: 16 partial rows per channel (group x row lane), combined in a fixed order
           asm volatile("bar.sync 3, 128;" ::: "memory");        // the previous tile's readers are done with the scratch
 #pragma unroll
           for (int j = 0; j < kBoxes; ++j)
             if (j < b_boxes) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float2*>(xf_scr + r0 * p.N + 64 * j + 8 * lc + 2 * q) = *reinterpret_cast<float2*>(&cs[j][q]);
+                *reinterpret_cast<float2*>(xf_scr + (grp * kGRowStep + gr0) * p.N + 64 * j + 8 * glc + 2 * q) =
+                    *reinterpret_cast<float2*>(&cs[j][q]);
             }
           asm volatile("bar.sync 3, 128;" ::: "memory");
           for (int c = static_cast<int>(t); c < p.N; c += 128) {
@@ -509,7 +531,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             p.xf_colsum[static_cast<long long>(g) * p.N + c] = a;
           }
         }
-      } else {
+      } else if (EPI == EPI_FUSED_BN) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (kb < p.xf_kb) {
@@ -975,7 +997,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 template <int BN, int EPI, int PLAIN, bool XF = false>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                   const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, EPI>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS>;
   static bool attr_set = false;
   if (!attr_set) {
     MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF>,
