@@ -229,6 +229,8 @@ def stem(G, B, cin, iters=5):
     """Inference stem at 256 x 256: conv (stacked samples) + bn_relu_maxpool against the one-kernel stem + bn_act."""
     x = torch.randn(B, cin, 256, 256, device=dev)
     a0 = ops.stem_im2col_f16(x, 7, 7, 2, 3)
+    ms_i = timeit(lambda: ops.stem_im2col_f16(x, 7, 7, 2, 3, out=a0), iters)
+    print(f"stem im2col B={B} cin={cin}: {ms_i:.3f} ms  {(a0.numel() * 2 + x.numel() * 4) / ms_i / 1e9:.2f} TB/s", flush=True)
     w = (torch.randn(G, 64, a0.shape[1], device=dev) * 0.05).half()
     gamma, beta = torch.ones(64, device=dev), torch.zeros(64, device=dev)
     y = torch.empty(G, B * 16384, 64, device=dev, dtype=torch.float16)

@@ -201,3 +201,20 @@ def test_m_stacked_tiles_of_the_n128_im2col_convs(bu, G, B, H, Cin, Cout, k, str
     # per-tile partials: tile t covers rows 128 t .. 128 t + 127
     t_last = (M + 127) // 128 - 1
     assert torch.allclose(st[:, t_last, :, 0].double(), yv[:, 128 * t_last:].double().sum(1), rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,C,size", [(2, 3, 256), (3, 1, 256), (2, 3, 64), (1, 1, 40)])
+def test_row_tiled_stem_im2col_matches_unfold(bu, B, C, size):
+    """stem_im2col_rows_kernel (7x7 / 2 / pad 3 stems: input rows staged in shared memory) against F.unfold in the (r, s, c)
+    K order of the NHWC implicit GEMM; the K padding columns are zero."""
+    import torch.nn.functional as F
+    from mauv import ops
+    torch.manual_seed(C * 10 + B)
+    x = torch.randn(B, C, size, size, device="cuda")
+    a = ops.stem_im2col_f16(x, 7, 7, 2, 3)
+    cols = F.unfold(x, 7, padding=3, stride=2)                # [B, C*49, L] in (c, r, s) order
+    L = cols.shape[2]
+    ref = cols.view(B, C, 49, L).permute(0, 3, 2, 1).reshape(B * L, 49 * C).half()
+    assert a.shape == (B * L, (49 * C + 7) // 8 * 8)
+    assert torch.equal(a[:, :49 * C], ref)
+    assert (a[:, 49 * C:] == 0).all()
