@@ -250,18 +250,22 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               // order as gemm_f16_tc_kernel's store + statistics epilogue (two chains over even / odd rows)
               unsigned long long sa = 0ull, sb = 0ull, qa = 0ull, qb = 0ull;
 #pragma unroll
-              for (int rr = 0; rr < 32; rr += 2) {
-                uint32_t w0, w1;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(buf + sw_off[rr & 7] + rr * 128u));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(buf + sw_off[(rr + 1) & 7] + (rr + 1) * 128u));
-                const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&w0));
-                const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&w1));
-                const unsigned long long p0 = *reinterpret_cast<const unsigned long long*>(&f0);
-                const unsigned long long p1 = *reinterpret_cast<const unsigned long long*>(&f1);
-                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(p0));
-                asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qa) : "l"(p0));
-                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sb) : "l"(p1));
-                asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qb) : "l"(p1));
+              for (int r8 = 0; r8 < 32; r8 += 8) {          // 8 reads in flight, then their 4 x 2 accumulation steps (same order)
+                uint32_t wv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv[u]) : "r"(buf + sw_off[(r8 + u) & 7] + (r8 + u) * 128u));
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                  const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&wv[u]));
+                  const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&wv[u + 1]));
+                  const unsigned long long p0 = *reinterpret_cast<const unsigned long long*>(&f0);
+                  const unsigned long long p1 = *reinterpret_cast<const unsigned long long*>(&f1);
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(p0));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qa) : "l"(p0));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sb) : "l"(p1));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(qb) : "l"(p1));
+                }
               }
               asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sa) : "l"(sb));
               asm("add.rn.f32x2 %0, %0, %1;" : "+l"(qa) : "l"(qb));
@@ -288,17 +292,26 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             // horizontal 3-max (stride 2, pad 1) from the staged rows, then the vertical combine
             const long long out_row = ((static_cast<long long>(gb * 4 + slot) * p.imgs + b) * Hp + (r >> 1)) * 64;
+            // all 12 window reads first (one exposed shared-memory latency instead of twelve: the ncu source view had these
+            // warps 20 % in short_scoreboard stalls on the LDS -> XOR chains)
+            uint4 vc[4], vr[4], vl[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t q_local = ql + 4u * j;                    // pooled pixel 16*ew + q_local
               const uint32_t rc = 2u * q_local;                        // staged row of the window centre (0..30)
-              uint4 h = xor_u4(lds_u4(buf + rc * 128u + ((ch ^ (rc & 7u)) << 4)), sgn);
-              h = hmax2_u4(h, xor_u4(lds_u4(buf + (rc + 1u) * 128u + ((ch ^ ((rc + 1u) & 7u)) << 4)), sgn));
-              if (rc > 0u) {
-                h = hmax2_u4(h, xor_u4(lds_u4(buf + (rc - 1u) * 128u + ((ch ^ ((rc - 1u) & 7u)) << 4)), sgn));
-              } else if (ew > 0) {                                     // pixel 32*ew - 1: row 31 of the left neighbour's slab
-                h = hmax2_u4(h, xor_u4(lds_u4(left_out + bsel + 31u * 128u + ((ch ^ 7u) << 4)), sgn));
-              }
+              const uint32_t a_c = buf + rc * 128u + ((ch ^ (rc & 7u)) << 4);
+              // left neighbour: row rc - 1, or (rc == 0) pixel 32*ew - 1 = row 31 of the left lane quarter's slab, or (image
+              // border) the centre again - max(x, x) = x
+              const uint32_t a_l = rc > 0u ? buf + (rc - 1u) * 128u + ((ch ^ ((rc - 1u) & 7u)) << 4)
+                                           : (ew > 0 ? left_out + bsel + 31u * 128u + ((ch ^ 7u) << 4) : a_c);
+              vc[j] = lds_u4(a_c);
+              vr[j] = lds_u4(buf + (rc + 1u) * 128u + ((ch ^ ((rc + 1u) & 7u)) << 4));
+              vl[j] = lds_u4(a_l);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t q_local = ql + 4u * j;
+              const uint4 h = hmax2_u4(hmax2_u4(xor_u4(vc[j], sgn), xor_u4(vr[j], sgn)), xor_u4(vl[j], sgn));
               if (r == r_begin) {
                 state[i][j] = h;
               } else if ((r & 1) == 0) {
