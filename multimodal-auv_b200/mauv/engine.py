@@ -127,6 +127,7 @@ class MCEngine:
         # stem: conv1 + bn1 statistics + max-pool of the raw output in one kernel (ops.stem_conv_pool_f16): the full-resolution
         # conv1 output never reaches HBM. 256 x 256 inputs (Wo = 128) only; other sizes take the three-kernel path.
         self.stem_pool = os.environ.get("MAUV_STEM_POOL", "1") != "0"
+        self.stem_colsum = True      # the fused stem's bn_act pass also emits the column sums layer1.0's downsample statistics need
         # bn2 + ReLU of the recompute tails' input applied to the operand tiles in shared memory (second-moment contraction and
         # fused conv3): a2 = relu(bn2(conv2(.))) is never written to / re-read from HBM
         self.fuse_a2 = os.environ.get("MAUV_FUSE_A2", "1") != "0"
@@ -278,6 +279,7 @@ class MCEngine:
             return self._run_trunk_x3(t, x_nchw, G, s0, eps, seed)
         B = x_nchw.shape[0]
         st = t.stem
+        x_colsum = None          # column sums of the current block input, when its producer emitted them
         if a0 is None:
             a0 = ops.stem_im2col_f16(x_nchw, st.k, st.k, st.stride, st.pad)      # shared by all samples
         w = self._sample(st, G, s0, eps, seed)
@@ -288,7 +290,12 @@ class MCEngine:
             # tensor: relu(bn(.)) is monotone per channel, so this equals maxpool(relu(bn1(conv1(x)))) bit for bit
             yp, stats = ops.stem_conv_pool_f16(a0, w, B, Ho, gamma=t.stem_bn.weight.detach() if t.stem_bn.weight is not None else None)
             ss = self._bn(stats, B * Ho * Wo, t.stem_bn, G)
-            x = ops.bn_act_f16(yp, ss, G, st.cout, relu=True, out=yp)
+            # (the column sums of the activated tensor come for free with this pass: first moment of the closed-form
+            # statistics of layer1.0's downsample conv, which reads x as is)
+            if self.stem_colsum:
+                x, x_colsum = ops.bn_act_f16(yp, ss, G, st.cout, relu=True, out=yp, colsum=True)
+            else:
+                x = ops.bn_act_f16(yp, ss, G, st.cout, relu=True, out=yp)
             self.launches += 3
         else:
             y, stats = ops.gemm_f16(a0, w, stats=True, shared_a=True)            # [G, B*Ho*Wo, 64]
@@ -297,7 +304,8 @@ class MCEngine:
             x = ops.bn_relu_maxpool_f16(y.view(G * B, Ho, Wo, st.cout), ss, G)
             self.launches += 1
             del y
-        for blk in t.blocks:
+        for bi, blk in enumerate(t.blocks):
+            xcs = x_colsum if bi == 0 else None
             y1, ss1 = self._conv_bn(blk.conv1, blk.bn1, x, G, B, s0, eps, seed)
             c2 = blk.conv2
             if (self.fuse_input_bn and ops.STREAM_CONV and c2.cin == 64 and c2.cout == 64 and c2.k == 3 and c2.stride == 1
@@ -324,7 +332,7 @@ class MCEngine:
                 c3 = blk.conv3
                 NB, H, W, Cm = y2.shape
                 if blk.down is not None:
-                    x = self._fused_downsample_tail(blk, y2, x, G, B, s0, eps, seed, None, a_ss=ss2)
+                    x = self._fused_downsample_tail(blk, y2, x, G, B, s0, eps, seed, None, a_ss=ss2, x_colsum=xcs)
                     continue
                 w3 = self._sample(c3, G, s0, eps, seed)
                 y2v = y2.view(G, B * H * W, Cm)
@@ -353,7 +361,7 @@ class MCEngine:
                 self.launches += 2
                 continue
             if blk.down is not None and fuse_tail:
-                x = self._fused_downsample_tail(blk, a2, x, G, B, s0, eps, seed, cs2)
+                x = self._fused_downsample_tail(blk, a2, x, G, B, s0, eps, seed, cs2, x_colsum=xcs)
                 continue
             y3, ss3 = self._conv_bn(blk.conv3, blk.bn3, a2, G, B, s0, eps, seed)
             if blk.down is not None:
@@ -366,7 +374,7 @@ class MCEngine:
         self.launches += 1
         return feat.view(G, B, -1)
 
-    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed, cs2=None, a_ss=None):
+    def _fused_downsample_tail(self, blk: _Block, a2, x, G, B, s0, eps, seed, cs2=None, a_ss=None, x_colsum=None):
         """relu(bn3(conv3(a2)) + bn_d(conv_d(x))) without either raw conv output in HBM: two statistics passes (recompute
         scheme), then ONE contraction over K-concatenated operands [a2 | x'] * [s3*W3 | sd*Wd]^T + (t3 + td) - the BN scales
         folded into freshly sampled weights, the shifts into the epilogue. x' = x for stride 1, else x subsampled."""
@@ -386,7 +394,8 @@ class MCEngine:
         else:
             ss3 = self._bn(ops.gemm_stats_f16(a2v, w3), M, blk.bn3, G)
         if self.gram_stats and ops.gram_splits(M, G, cd.cin) > 0:
-            ssd = self._bn_gram(xv, ops.colsum_f16(xv, G, cd.cin), wd, M, blk.down_bn, G)
+            csx = x_colsum if (x_colsum is not None and cd.stride == 1) else ops.colsum_f16(xv, G, cd.cin)
+            ssd = self._bn_gram(xv, csx, wd, M, blk.down_bn, G)
         else:
             ssd = self._bn(ops.gemm_stats_f16(xv, wd), M, blk.down_bn, G)
         wcat = torch.empty((G, c3.cout, Cm + cd.cin), dtype=F16, device=self.device)

