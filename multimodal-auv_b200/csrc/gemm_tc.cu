@@ -93,7 +93,10 @@ enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2, EPI_STATS_T = 
 // is a channel, so every epilogue thread sums its own channel over the tile's pixels in registers - no shuffles, no
 // shared memory, no output. Pixels past M are zero-filled by TMA and contribute nothing.
 
-template <int BN, int EPI = 0, bool GRAMX = false>
+// NR (fused-BN epilogue without a residual operand - the K-concatenated downsample tails): no residual prefetch, so two staging
+// buffers per warp suffice and the 32 KB they free buy a third pipeline stage at BN = 256 (a tile is 2-6 k-blocks there and two
+// stages gave the producer less than one tile of look-ahead: 7 000 clocks per tile against 4 200 of HBM time).
+template <int BN, int EPI = 0, bool GRAMX = false, bool NR = false>
 struct SmemLayout {
   // the fused epilogue needs 3 staging buffers per warp (residual prefetch / transform / store in flight) and is
   // only used for short-K (HBM-bound) layers, so it trades pipeline depth for staging space.
@@ -101,8 +104,8 @@ struct SmemLayout {
   // is BN x 128 bytes and the ring is 2x deeper - every stage is also held for the ~700 clocks of its in-place transform, and
   // 6 x 8 KB in flight per SM did not cover the HBM latency
   static constexpr int kStages = GRAMX ? ((BN == 256) ? 4 : (BN == 128 ? 8 : 12))
-                                       : ((EPI == 2) ? ((BN == 256) ? 2 : 3) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
-  static constexpr int kOutBufs = (EPI == 2) ? 3 : 2;
+                                       : ((EPI == 2) ? ((BN == 256) ? (NR ? 3 : 2) : (NR ? 4 : 3)) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
+  static constexpr int kOutBufs = (EPI == 2 && !NR) ? 3 : 2;
   // epilogue warps: one set of 4 (TMEM lane quarters) per 64-column block in flight; two sets when BN >= 128
   static constexpr int kEpiWarps = (BN >= 128) ? 8 : 4;
   static constexpr int kABytes = GRAMX ? 0 : BM * BK * 2;
@@ -136,12 +139,13 @@ template <int BN> constexpr int xf_gram_split() { return BN == 256 ? 2 : 4; }
 template <int BN, int EPI> constexpr int xf_arrivals() { return EPI == 2 ? 2 : 4 / xf_gram_split<BN>(); }
 template <int EPI, bool XF> constexpr int gemm_threads() { return (XF && xf_warps<EPI>() == 4) ? 448 : 384; }
 
-template <int BN, int EPI, int PLAIN, bool XF = false>
+template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false>
 __global__ void __launch_bounds__(gemm_threads<EPI, XF>(), 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const GemmParams p) {
-  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR>;
+  static_assert(!NR || EPI == EPI_FUSED_BN, "NR: fused-BN epilogue without residual");
   constexpr int kStages = L::kStages;
   const int f_stack = PLAIN == 2 ? 4 : (PLAIN ? 1 : p.stack), f_split = PLAIN ? 0 : p.split, f_out_f32 = PLAIN ? 0 : p.out_f32;
   const int f_mn = PLAIN ? 0 : p.mn, f_gram = PLAIN ? 0 : p.gram, f_a2_kb = PLAIN ? 0 : p.a2_kb;
@@ -636,12 +640,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       auto issue_residual = [&](uint32_t b, long long tile, int cb) {   // lane 0 only
         int gb, nb, row0, rmax;
         block_coords(tile, cb, gb, nb, row0, rmax);
-        if (p.has_res) {
+        if (!NR && p.has_res) {
           // issued for EVERY block so that buffer b%3's barrier completes exactly once per use (parity = (b/3)&1);
           // a slab entirely past M loads rows 0.. instead (never stored), N % BN == 0 keeps the columns in range
           const uint32_t bar = res_bar(wq, b % 3u);
           mbar_expect_tx(bar, L::kOutBufBytes);
-          tma_load_3d(my_out + (b % 3u) * L::kOutBufBytes, &tmR, bar, nb, rmax > 0 ? row0 : 0, gb);
+          tma_load_3d(my_out + (b % static_cast<uint32_t>(L::kOutBufs)) * L::kOutBufBytes, &tmR, bar, nb, rmax > 0 ? row0 : 0, gb);
         }
       };
       // flat loop over this warp's work items (tile, 64-column block) with a one-item look-ahead on the TMEM side: the
@@ -691,8 +695,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           tmem_ld_32x32b_x32(acc_addr(nit, ncb) + 32 * half, dst);
         };
-        const uint32_t buf = my_out + (b % 3u) * L::kOutBufBytes;
-        if (p.has_res) mbar_wait(res_bar(wq, b % 3u), (b / 3u) & 1u);
+        const uint32_t buf = my_out + (b % static_cast<uint32_t>(L::kOutBufs)) * L::kOutBufBytes;
+        if (!NR && p.has_res) mbar_wait(res_bar(wq, b % 3u), (b / 3u) & 1u);
         // (scale, shift) of this block's 64 channels, de-interleaved into this warp's private shared-memory slice (scale[64] |
         // shift[64]) and re-read with broadcast 16-byte loads: 32 LDS.128 per block instead of 64 LDG.64, and the pairs come
         // out as packed fp32x2 operands. Reloaded only when the (sample, channel block) changes - with N = BN once per sample.
@@ -710,7 +714,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // stalls on eight serial LDS -> FFMA2 -> FADD2 -> F2FP -> HMNMX2 -> STS chains per block.
         auto transform_half = [&](const uint32_t (&r)[32], int half) {
           uint32_t rr[4][4];
-          if (p.has_res) {
+          if (!NR && p.has_res) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const uint32_t addr = buf + lane * 128u + ((static_cast<uint32_t>(half * 4 + q4) ^ (lane & 7u)) << 4);
@@ -738,7 +742,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 unsigned long long a2, v;
                 asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(src[2 * j]), "r"(src[2 * j + 1]));
                 asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(a2), "l"(sc[c][j]), "l"(sh[c][j]));
-                if (p.has_res) {
+                if (!NR && p.has_res) {
                   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[q4][j]));
                   unsigned long long f2;
                   asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(f.x), "f"(f.y));
@@ -994,18 +998,18 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, int EPI, int PLAIN, bool XF = false>
+template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                   const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR>;
   static bool attr_set = false;
   if (!attr_set) {
-    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF>,
+    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF><<<static_cast<unsigned>(grid), gemm_threads<EPI, XF>(), L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
+  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR><<<static_cast<unsigned>(grid), gemm_threads<EPI, XF>(), L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
@@ -1020,6 +1024,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
       const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
                          !p.b_mod && !p.bias && p.a_batch_mul == 1;
       if (plain) return launch_gemm_t<BN, EPI, 1, true>(tmA, tmB, tmY, tmR, p, stream);
+      if (!p.has_res) return launch_gemm_t<BN, EPI, 0, true, true>(tmA, tmB, tmY, tmR, p, stream);
       return launch_gemm_t<BN, EPI, 0, true>(tmA, tmB, tmY, tmR, p, stream);
     } else if constexpr (EPI == EPI_STORE_STATS) {
       if (p.mn && p.gram && p.out_f32) return launch_gemm_t<BN, EPI, 0, true>(tmA, tmB, tmY, tmR, p, stream);
@@ -1031,6 +1036,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
                        !p.b_mod && !p.bias && p.a_batch_mul == 1;
     if (plain) return launch_gemm_t<BN, EPI, 1>(tmA, tmB, tmY, tmR, p, stream);
+    if constexpr (EPI == EPI_FUSED_BN && BN >= 128) {
+      if (!p.has_res && p.a2_kb) return launch_gemm_t<BN, EPI, 0, false, true>(tmA, tmB, tmY, tmR, p, stream);
+    }
     if constexpr (BN == 256 && EPI == EPI_STORE_STATS) {
       const bool stacked = p.stack == 4 && p.N == 64 && p.a_batch_mul == 0 && p.a_mode == 0 && !p.split && !p.out_f32 && !p.mn &&
                            !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap && !p.b_mod && !p.bias;
