@@ -12,3 +12,6 @@ KREGEX=gemm_f16_tc SKIP=3 P conv_3x3_N128_K1152_mstack conv 10 256 32 32 128 128
 KREGEX=gemm_f16_tc SKIP=8 P tail_fused_K64 tail 15 1048576 256 64 3
 KREGEX=gemm_f16_tc SKIP=13 P tail_gram_xf_K64 tail 15 1048576 256 64 3
 KREGEX=gemm_f16_tc SKIP=18 P tail_fused_xf_K64 tail 15 1048576 256 64 3
+# launch list of the default bench command (one whole step = the launches between two mc_reduce_kernel launches; a step is ~860
+# launches at the default group of 30 samples)
+python bench.py --no-cpu-baseline --no-x3 --no-train-leg --steps 1 --warmup 3 > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 3500 -c 2000 --csv --log-file gpurun_out/r3_launches_bench.csv python bench.py --no-cpu-baseline --no-x3 --no-train-leg --steps 1 --warmup 3 > gpurun_out/ncu_bench.log 2>&1; echo "launchlist exit $?"
