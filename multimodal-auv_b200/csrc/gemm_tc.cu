@@ -96,27 +96,32 @@ enum { EPI_STORE_STATS = 0, EPI_STATS_ONLY = 1, EPI_FUSED_BN = 2, EPI_STATS_T = 
 // NR (fused-BN epilogue without a residual operand - the K-concatenated downsample tails): no residual prefetch, so two staging
 // buffers per warp suffice and the 32 KB they free buy a third pipeline stage at BN = 256 (a tile is 2-6 k-blocks there and two
 // stages gave the producer less than one tile of look-ahead: 7 000 clocks per tile against 4 200 of HBM time).
-template <int BN, int EPI = 0, bool GRAMX = false, bool NR = false>
+// BR (fused-BN tails whose weight tile is at most 64 KB: K <= 128 at BN = 256): with the n-tile fastest tile order and a grid
+// that is a multiple of the n-tile count, a CTA meets ONE n-tile per sample, so its B tile ([BN][K] fp16) is loaded once per
+// sample into a resident region and only the 16 KB A k-blocks stream: 3 A stages (5 without residual staging) = 1.5-5 tiles of
+// look-ahead instead of 1-2, and no per-tile re-fetch of 32-64 KB of weights from L2.
+template <int BN, int EPI = 0, bool GRAMX = false, bool NR = false, bool BR = false>
 struct SmemLayout {
   // the fused epilogue needs 3 staging buffers per warp (residual prefetch / transform / store in flight) and is
   // only used for short-K (HBM-bound) layers, so it trades pipeline depth for staging space.
   // GRAMX (second moments with the operand transform): only the B boxes are loaded (the A descriptor aliases them), so a stage
   // is BN x 128 bytes and the ring is 2x deeper - every stage is also held for the ~700 clocks of its in-place transform, and
   // 6 x 8 KB in flight per SM did not cover the HBM latency
-  static constexpr int kStages = GRAMX ? ((BN == 256) ? 4 : (BN == 128 ? 8 : 12))
+  static constexpr int kStages = BR ? (NR ? 5 : 3) : GRAMX ? ((BN == 256) ? 4 : (BN == 128 ? 8 : 12))
                                        : ((EPI == 2) ? ((BN == 256) ? (NR ? 3 : 2) : (NR ? 4 : 3)) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
+  static constexpr int kBResBytes = BR ? 65536 : 0;       // resident B tile (after the barrier block)
   static constexpr int kOutBufs = (EPI == 2 && !NR) ? 3 : 2;
   // epilogue warps: one set of 4 (TMEM lane quarters) per 64-column block in flight; two sets when BN >= 128
   static constexpr int kEpiWarps = (BN >= 128) ? 8 : 4;
   static constexpr int kABytes = GRAMX ? 0 : BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = BR ? 0 : BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue staging for the TMA store: per epilogue warp 2 buffers of 32 rows x 64 fp16 (128B-swizzled rows)
   static constexpr int kOutBufBytes = 32 * 64 * 2;
   static constexpr int kOutBytes = kEpiWarps * kOutBufs * kOutBufBytes;
   static constexpr int kStatBytes = 2 /*buffers*/ * 4 /*warps*/ * BN * 2 * 4;
   static constexpr int kBarBytes = 1024;  // pipeline + TMEM barriers, TMEM pointer, 3 residual barriers per epilogue warp, transform barriers
-  static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes;
+  static constexpr int kTotal = 1024 /*alignment slack*/ + kStages * kStageBytes + kOutBytes + kStatBytes + kBarBytes + kBResBytes;
 };
 
 // PLAIN = true: the common case (one sample per tile column block, fp16 output, no bias, K-major tiled / im2col A, no
@@ -139,13 +144,14 @@ template <int BN> constexpr int xf_gram_split() { return BN == 256 ? 2 : 4; }
 template <int BN, int EPI> constexpr int xf_arrivals() { return EPI == 2 ? 2 : 4 / xf_gram_split<BN>(); }
 template <int EPI, bool XF> constexpr int gemm_threads() { return (XF && xf_warps<EPI>() == 4) ? 448 : 384; }
 
-template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false>
+template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false, bool BR = false>
 __global__ void __launch_bounds__(gemm_threads<EPI, XF>(), 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                    const GemmParams p) {
-  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR, BR>;
   static_assert(!NR || EPI == EPI_FUSED_BN, "NR: fused-BN epilogue without residual");
+  static_assert(!BR || (EPI == EPI_FUSED_BN && BN == 256), "BR: resident weight tile of the fused-BN tails");
   constexpr int kStages = L::kStages;
   const int f_stack = PLAIN == 2 ? 4 : (PLAIN ? 1 : p.stack), f_split = PLAIN ? 0 : p.split, f_out_f32 = PLAIN ? 0 : p.out_f32;
   const int f_mn = PLAIN ? 0 : p.mn, f_gram = PLAIN ? 0 : p.gram, f_a2_kb = PLAIN ? 0 : p.a2_kb;
@@ -174,6 +180,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
   auto res_bar = [&](int w, int j) { return bar_base + 8u * (2 * kStages + 6 + w * 3 + j); };   // EPI == 2 only
   auto xf_ready = [&](int s) { return bar_base + 8u * (2 * kStages + 30 + s); };                // XF only: tile transformed
+  const uint32_t b_full = bar_base + 8u * 120, b_empty = bar_base + 8u * 121;                   // BR only: resident B tile
+  const uint32_t bres_base = bar_base + L::kBarBytes;                                           // BR only (1024-aligned)
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + kStages * L::kStageBytes + L::kOutBytes + L::kStatBytes + 8 * (2 * kStages + 4));
 
@@ -199,6 +207,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int j = 0; j < 3; ++j) mbar_init(res_bar(w, j), 1);
     if (XF)
       for (int s = 0; s < kStages; ++s) mbar_init(xf_ready(s), xf_arrivals<BN, EPI>());   // one arrive per warp that transforms the stage
+    if (BR) {
+      mbar_init(b_full, 1);
+      mbar_init(b_empty, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -252,9 +264,18 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int br_g = -1;
+      uint32_t br_loads = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int g, m_tile, n_tile;
         decode(tile, g, m_tile, n_tile);
+        if (BR && g != br_g) {      // new sample: its weight tile replaces the resident one once the MMAs reading it have retired
+          if (br_loads > 0) mbar_wait(b_empty, (br_loads - 1) & 1u);
+          mbar_expect_tx(b_full, static_cast<uint32_t>(p.k_blocks) * (BN * BK * 2));
+          for (int kb = 0; kb < p.k_blocks; ++kb) tma_load_3d(bres_base + kb * (BN * BK * 2), &tmB, b_full, kb * BK, n_tile * BN, g);
+          ++br_loads;
+          br_g = g;
+        }
         const int m0 = m_tile * (MSTACK ? 2 * BM : BM);
         // im2col start pixel of this tile (M-stacked: of its two 128-row halves)
         int iq = 0, ip = 0, in_ = 0, iq1 = 0, ip1 = 0, in1 = 0;
@@ -333,7 +354,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               tma_load_im2col_4d(a_dst + L::kABytes, &tmA, full_bar(stage), cb * BK, iq1 * p.stride - p.pad,
                                  ip1 * p.stride - p.pad, in1, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
           }
-          if (MSTACK) tma_load_3d(a_dst + 2 * L::kABytes, &tmB, full_bar(stage), kb * BK, 0, g);
+          if (BR) { /* B is resident */ }
+          else if (MSTACK) tma_load_3d(a_dst + 2 * L::kABytes, &tmB, full_bar(stage), kb * BK, 0, g);
           else if (f_stack > 1) tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, g * f_N, 0);   // flattened [G*N][K]
           else tma_load_3d(b_dst, &tmB, full_bar(stage), kb * BK, n_tile * BN, f_b_mod ? g % f_b_mod : g);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -344,8 +366,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, br_g = -1;
+      uint32_t phase = 0, br_uses = 0;
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
@@ -355,6 +377,17 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           int g_, m_tile_, n_tile_;
           decode(tile, g_, m_tile_, n_tile_);
           tile_m0 = m_tile_ * BM;
+        }
+        if (BR) {
+          int g_, m_tile_, n_tile_;
+          decode(tile, g_, m_tile_, n_tile_);
+          if (g_ != br_g) {
+            if (br_g >= 0) umma_commit(b_empty);      // arrives when every MMA issued so far (old weights) has completed
+            mbar_wait(b_full, br_uses & 1u);
+            tcgen05_fence_after();
+            ++br_uses;
+            br_g = g_;
+          }
         }
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -385,7 +418,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           } else {
             const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
-            const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::kABytes);
+            const uint64_t b_desc = umma_smem_desc_sw128(BR ? bres_base + static_cast<uint32_t>(kb) * (BN * BK * 2) : a_addr + L::kABytes);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
@@ -998,18 +1031,19 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false>
+template <int BN, int EPI, int PLAIN, bool XF = false, bool NR = false, bool BR = false>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                   const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR>;
+  using L = SmemLayout<BN, EPI, XF && EPI == EPI_STORE_STATS, NR, BR>;
   static bool attr_set = false;
   if (!attr_set) {
-    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR>,
+    MAUV_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR, BR>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
-  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR><<<static_cast<unsigned>(grid), gemm_threads<EPI, XF>(), L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
+  long long grid = p.total_tiles < mauv_num_sms() ? p.total_tiles : mauv_num_sms();
+  if (BR) grid -= grid % p.n_tiles;       // a CTA must meet one n-tile only (tile index step = grid, n-tile = tile % n_tiles)
+  gemm_f16_tc_kernel<BN, EPI, PLAIN, XF, NR, BR><<<static_cast<unsigned>(grid), gemm_threads<EPI, XF>(), L::kTotal, stream>>>(tmA, tmB, tmY, tmR, p);
   MAUV_LAUNCH_CHECK("gemm_f16_tc_kernel");
   return MAUV_OK;
 }
@@ -1019,10 +1053,22 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                 const GemmParams& p, cudaStream_t stream) {
   // XF instances (BatchNorm + ReLU of the previous layer applied to the operand tiles in shared memory): the fused-BN tails
   // (plain, or K-concatenated with a downsample branch) and the second-moment contraction
+  // resident weight tile (BR): fused-BN tails at BN = 256 whose [BN][K] tile fits 64 KB and whose n-tile count divides the grid
+  static const bool br_on = [] { const char* e = getenv("MAUV_BRES"); return !(e && e[0] == '0'); }();
+  bool br = false;
+  if constexpr (EPI == EPI_FUSED_BN && BN == 256) {
+    br = br_on && p.a_mode == 0 && p.k_blocks * (BN * BK * 2) <= 65536 && p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram &&
+         !p.a_wrap_kb && !p.a_cwrap && !p.b_mod && !p.bias && p.a_batch_mul == 1 && (p.n_tiles == 1 || p.n_tiles == 2 || p.n_tiles == 4) &&
+         p.total_tiles >= mauv_num_sms();
+  }
   if (p.xf_ss) {
     if constexpr (EPI == EPI_FUSED_BN && BN >= 128) {
       const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
                          !p.b_mod && !p.bias && p.a_batch_mul == 1;
+      if constexpr (BN == 256) {
+        if (br && plain) return launch_gemm_t<BN, EPI, 1, true, false, true>(tmA, tmB, tmY, tmR, p, stream);
+        if (br && !p.has_res) return launch_gemm_t<BN, EPI, 0, true, true, true>(tmA, tmB, tmY, tmR, p, stream);
+      }
       if (plain) return launch_gemm_t<BN, EPI, 1, true>(tmA, tmB, tmY, tmR, p, stream);
       if (!p.has_res) return launch_gemm_t<BN, EPI, 0, true, true>(tmA, tmB, tmY, tmR, p, stream);
       return launch_gemm_t<BN, EPI, 0, true>(tmA, tmB, tmY, tmR, p, stream);
@@ -1035,6 +1081,10 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   if constexpr (EPI == EPI_STORE_STATS || EPI == EPI_FUSED_BN) {
     const bool plain = p.stack <= 1 && !p.split && !p.out_f32 && !p.mn && !p.gram && !p.a2_kb && !p.a_wrap_kb && !p.a_cwrap &&
                        !p.b_mod && !p.bias && p.a_batch_mul == 1;
+    if constexpr (EPI == EPI_FUSED_BN && BN == 256) {
+      if (br && plain) return launch_gemm_t<BN, EPI, 1, false, false, true>(tmA, tmB, tmY, tmR, p, stream);
+      if (br && !p.has_res && p.a2_kb) return launch_gemm_t<BN, EPI, 0, false, true, true>(tmA, tmB, tmY, tmR, p, stream);
+    }
     if (plain) return launch_gemm_t<BN, EPI, 1>(tmA, tmB, tmY, tmR, p, stream);
     if constexpr (EPI == EPI_FUSED_BN && BN >= 128) {
       if (!p.has_res && p.a2_kb) return launch_gemm_t<BN, EPI, 0, false, true>(tmA, tmB, tmY, tmR, p, stream);
