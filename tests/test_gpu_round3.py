@@ -222,3 +222,34 @@ def test_row_tiled_stem_im2col_matches_unfold(bu, B, C, size):
     assert a.shape == (B * L, (49 * C + 7) // 8 * 8)
     assert torch.equal(a[:, :49 * C], ref)
     assert (a[:, 49 * C:] == 0).all()
+
+
+@pytest.mark.parametrize("G,M,N,K,res,xf", [(3, 8192, 512, 128, True, False), (4, 8192, 256, 64, True, True), (3, 12800, 512, 128, True, True),
+                                            (5, 4096 + 64, 1024, 128, False, False)])
+def test_resident_weight_tile_tails_against_a_torch_reference(bu, G, M, N, K, res, xf):
+    """Fused-BN tails large enough (>= 148 tiles) to take the resident-weight layout (one B load per sample and CTA, the tile is
+    replaced when the CTA's tile sequence crosses into the next sample): out = relu((A W^T) * scale + shift + residual) against
+    fp32 torch on the same fp16 operands, with and without the operand transform; ragged last m-tile; N = 1024 (4 n-tiles)."""
+    from mauv import ops
+    y, ss = _raw_and_bn(G, M, K, 17 + N)
+    w = (torch.randn(G, N, K, device="cuda") * 0.05).half()
+    ss3 = torch.stack([torch.rand(G, N, device="cuda") + 0.5, torch.randn(G, N, device="cuda") * 0.2], dim=-1).contiguous()
+    r = torch.randn(G, M, N, device="cuda").half() if res else None
+    if xf:
+        a = ops.bn_act_f16(y, ss, G, K, relu=True)
+        got = ops.gemm_bn_act_f16(y, w, ss3, residual=r, relu=True, a_ss=ss)
+    else:
+        a = y
+        got = ops.gemm_bn_act_f16(a, w, ss3, residual=r, relu=True)
+    ref = torch.bmm(a.float(), w.float().transpose(1, 2)) * ss3[:, None, :, 0] + ss3[:, None, :, 1]
+    if res:
+        ref = ref + r.float()
+    ref = torch.relu(ref)
+    err = (got.float() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    # every sample used ITS weights: permuting the samples permutes the outputs
+    perm = torch.arange(G - 1, -1, -1, device="cuda")
+    got_p = ops.gemm_bn_act_f16(a[perm].contiguous() if not xf else y[perm].contiguous(), w[perm].contiguous(), ss3[perm].contiguous(),
+                                residual=None if r is None else r[perm].contiguous(), relu=True,
+                                a_ss=ss[perm].contiguous() if xf else None)
+    assert torch.equal(got_p, got[perm])
