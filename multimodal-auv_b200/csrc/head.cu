@@ -9,8 +9,10 @@
 namespace {
 
 constexpr int TO = 32;        // outputs per CTA
-constexpr int TB = 32;        // batch rows per CTA (every row tile re-samples its weight tile: Philox is cheap, latency is not)
 constexpr int TK = 32;        // k chunk
+// batch rows per CTA (template parameter TBR): every row tile re-samples its weight tile - 4 exact softplus + one Philox block +
+// two Box-Muller pairs per thread and k-step, ~80 % of the kernel's instructions at 32 rows - so large batches take 128-row
+// tiles (4x fewer samplings per weight, 8 x 2 outputs per thread); small ones (training: 8 rows) keep 32.
 constexpr int PITCH = TK + 4; // 16-byte aligned rows, float4 reads in the inner product
 
 struct LinearParams {
@@ -26,8 +28,11 @@ struct LinearParams {
 // 256 threads = 16 x 16; each thread owns a 2 x 2 block of the 32 x 32 output tile (rows ty, ty+16; outputs tx, tx+16) and
 // walks k four at a time with 16-byte shared-memory reads (4 FMAs per LDS.128). Per k-step the CTA stages a 32 x 32
 // activation tile (one float4 per thread) and SAMPLES its 32 x 32 weight tile in place (one Philox4x32 block per thread).
+template <int TBR>
 __global__ void __launch_bounds__(256)
 sampled_linear_kernel(const LinearParams p) {
+  constexpr int TB = TBR;
+  constexpr int RT = TBR / 16;     // rows per thread
   const uint32_t sample0 = p.sample0 + (p.sample_base ? *p.sample_base : 0u);
   __shared__ __align__(16) float xs[TB][PITCH];
   __shared__ __align__(16) float ws[TO][PITCH];
@@ -37,14 +42,17 @@ sampled_linear_kernel(const LinearParams p) {
   const int tx = threadIdx.x & 15;
   const int ty = threadIdx.x >> 4;  // 0..15
   const float* xg = p.x + static_cast<long long>(g) * p.x_gs;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float acc[RT][2];
+#pragma unroll
+  for (int jb = 0; jb < RT; ++jb) acc[jb][0] = acc[jb][1] = 0.f;
   const bool quads = (p.in % 4 == 0);     // 4 consecutive k share one Philox4x32 block / one 16-byte load
   const bool x_vec = quads && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) && (p.ldx % 4 == 0);
   const int sr = threadIdx.x >> 3, sc = (threadIdx.x & 7) * 4;      // staging role: row sr, columns sc .. sc+3
 
   for (int k0 = 0; k0 < p.in; k0 += TK) {
-    {   // activations
-      const int b = b0 + sr, kk = k0 + sc;
+#pragma unroll
+    for (int rb = 0; rb < TB / 32; ++rb) {   // activations: 32 rows per pass
+      const int b = b0 + 32 * rb + sr, kk = k0 + sc;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b < p.B) {
         const float* src = xg + static_cast<long long>(b) * p.ldx + kk;
@@ -56,7 +64,7 @@ sampled_linear_kernel(const LinearParams p) {
           if (kk + 3 < p.in) v.w = src[3];
         }
       }
-      *reinterpret_cast<float4*>(&xs[sr][sc]) = v;
+      *reinterpret_cast<float4*>(&xs[32 * rb + sr][sc]) = v;
     }
     {   // weights: sample the tile in place
       const int o = o0 + sr, kk = k0 + sc;
@@ -90,13 +98,13 @@ sampled_linear_kernel(const LinearParams p) {
     for (int k4 = 0; k4 < TK; k4 += 4) {
       const float4 wa = *reinterpret_cast<const float4*>(&ws[tx][k4]);
       const float4 wb = *reinterpret_cast<const float4*>(&ws[tx + 16][k4]);
-      const float4 xa = *reinterpret_cast<const float4*>(&xs[ty][k4]);
-      const float4 xb = *reinterpret_cast<const float4*>(&xs[ty + 16][k4]);
-      // k order inside the chunk is fixed (x, y, z, w): deterministic accumulation
-      acc[0][0] = fmaf(xa.w, wa.w, fmaf(xa.z, wa.z, fmaf(xa.y, wa.y, fmaf(xa.x, wa.x, acc[0][0]))));
-      acc[0][1] = fmaf(xa.w, wb.w, fmaf(xa.z, wb.z, fmaf(xa.y, wb.y, fmaf(xa.x, wb.x, acc[0][1]))));
-      acc[1][0] = fmaf(xb.w, wa.w, fmaf(xb.z, wa.z, fmaf(xb.y, wa.y, fmaf(xb.x, wa.x, acc[1][0]))));
-      acc[1][1] = fmaf(xb.w, wb.w, fmaf(xb.z, wb.z, fmaf(xb.y, wb.y, fmaf(xb.x, wb.x, acc[1][1]))));
+#pragma unroll
+      for (int jb = 0; jb < RT; ++jb) {
+        const float4 xa = *reinterpret_cast<const float4*>(&xs[ty + 16 * jb][k4]);
+        // k order inside the chunk is fixed (x, y, z, w): deterministic accumulation
+        acc[jb][0] = fmaf(xa.w, wa.w, fmaf(xa.z, wa.z, fmaf(xa.y, wa.y, fmaf(xa.x, wa.x, acc[jb][0]))));
+        acc[jb][1] = fmaf(xa.w, wb.w, fmaf(xa.z, wb.z, fmaf(xa.y, wb.y, fmaf(xa.x, wb.x, acc[jb][1]))));
+      }
     }
     __syncthreads();
   }
@@ -113,7 +121,7 @@ sampled_linear_kernel(const LinearParams p) {
       bias = fmaf(softplus_ref(p.rho_b[o]), z, p.mu_b[o]);
     }
 #pragma unroll
-    for (int jb = 0; jb < 2; ++jb) {
+    for (int jb = 0; jb < RT; ++jb) {
       const int b = b0 + ty + 16 * jb;
       if (b < p.B) yg[static_cast<long long>(b) * p.ldy + o] = acc[jb][jo] + bias;
     }
@@ -166,8 +174,13 @@ int mauv_sampled_linear_f32(const float* x, long long x_sample_stride, int ldx, 
   p.sample_base = mauv_sample_base();
   p.G = G; p.B = B; p.in = in_features; p.out = out_features;
   p.y = y; p.y_gs = y_sample_stride; p.ldy = ldy;
-  dim3 grid((out_features + TO - 1) / TO, (B + TB - 1) / TB, G);
-  sampled_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (B >= 128) {
+    dim3 grid((out_features + TO - 1) / TO, (B + 127) / 128, G);
+    sampled_linear_kernel<128><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    dim3 grid((out_features + TO - 1) / TO, (B + 31) / 32, G);
+    sampled_linear_kernel<32><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   MAUV_LAUNCH_CHECK("sampled_linear_kernel");
   return MAUV_OK;
 }

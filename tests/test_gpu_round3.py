@@ -253,3 +253,25 @@ def test_resident_weight_tile_tails_against_a_torch_reference(bu, G, M, N, K, re
                                 residual=None if r is None else r[perm].contiguous(), relu=True,
                                 a_ss=ss[perm].contiguous() if xf else None)
     assert torch.equal(got_p, got[perm])
+
+
+@pytest.mark.parametrize("B,fin,fout,bias", [(130, 2048, 128, True), (256, 384, 1263, True), (128, 96, 7, False)])
+def test_head_linear_128_row_tiles_equal_the_32_row_tiles(bu, B, fin, fout, bias):
+    """sampled_linear_kernel<128> (batches >= 128 rows: the sampled weight tile is reused by 128 rows) against the 32-row
+    instance run on row slices < 128 - same Philox ids, same accumulation order: torch.equal - and against fp64."""
+    from mauv import ops
+    torch.manual_seed(fin + B)
+    G = 3
+    x = torch.randn(G, B, fin, device="cuda")
+    mu, rho = torch.randn(fout, fin, device="cuda") * 0.05, torch.full((fout, fin), -3.0, device="cuda") + torch.randn(fout, fin, device="cuda") * 0.1
+    mu_b = torch.randn(fout, device="cuda") * 0.1 if bias else None
+    rho_b = torch.full((fout,), -3.0, device="cuda") if bias else None
+    kw = dict(seed=99, layer_id=5, sample0=11)
+    big = ops.sampled_linear_f32(x, mu, rho, mu_b, rho_b, **kw)
+    parts = [ops.sampled_linear_f32(x[:, lo:lo + 100].contiguous(), mu, rho, mu_b, rho_b, **kw) for lo in range(0, B, 100)]
+    assert torch.equal(big, torch.cat(parts, dim=1))
+    eps = torch.randn(G, fout, fin, device="cuda")
+    got = ops.sampled_linear_f32(x, mu, rho, None, None, eps_w=eps)
+    w = mu.double() + torch.log1p(torch.exp(rho.double())) * eps.double()
+    ref = torch.einsum("gbi,goi->gbo", x.double(), w)
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-5
