@@ -174,7 +174,9 @@ int mauv_sampled_linear_f32(const float* x, long long x_sample_stride, int ldx, 
   p.sample_base = mauv_sample_base();
   p.G = G; p.B = B; p.in = in_features; p.out = out_features;
   p.y = y; p.y_gs = y_sample_stride; p.ldy = ldy;
-  if (B >= 128) {
+  // 128-row tiles only when they still fill the GPU (at 8 GPUs a rank walks 3-4 samples: 32 CTAs for a 128-wide projection)
+  const long long ctas128 = static_cast<long long>((out_features + TO - 1) / TO) * ((B + 127) / 128) * G;
+  if (B >= 128 && ctas128 >= mauv_num_sms()) {
     dim3 grid((out_features + TO - 1) / TO, (B + 127) / 128, G);
     sampled_linear_kernel<128><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   } else {
