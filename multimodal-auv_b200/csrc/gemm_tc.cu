@@ -28,7 +28,14 @@
 //   * mn = 1: weight gradient dW = dY^T X with BOTH operands MN-major, read where they lie ([64 px][64 ch] TMA boxes of
 //     the row-major dY and of the NHWC activations; im2col-mode TMA on the B side for 3x3 / strided layers);
 //   * split / a_wrap_kb / a_cwrap: the fp16x3 validation arithmetic (K-concatenated hi/lo operands).
-// conv3x3_c64_stream_kernel (below) is the padded-stream sibling for layer1's 3x3 64->64 convs.
+// Compile-time instances (template parameters):
+//   * PLAIN 1 / 2 / 3: every mode flag folded (hot inference shapes) / the stem's sample-stacked tiles / M-stacked tiles (two
+//     128-row A tiles share one B tile: the N = 128 im2col convs);
+//   * XF: BatchNorm + ReLU of the PREVIOUS layer applied to the TMA-loaded operand tiles in shared memory by transform warps
+//     between the TMA and the MMA stage (fused tails and second moments read the raw conv2 output);
+//   * NR / BR: fused-BN tails without a residual operand (third pipeline stage) / with a resident weight tile (one B load per
+//     sample and CTA, only the A k-blocks stream).
+// conv3x3_c64_stream_kernel (below) is the padded-stream sibling for layer1's 3x3 64->64 convs; stem_pool.cu holds the stem.
 #include <cstdlib>
 #include "common.cuh"
 #include "tmap.cuh"
