@@ -345,13 +345,13 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (f_a2_kb && kb >= f_a2_kb) {
               tma_load_3d(a_dst, &tmR, full_bar(stage), (kb - f_a2_kb) * BK, m0, g);
             } else {
-              const int akb = f_a_wrap_kb ? kb % f_a_wrap_kb : kb;
+              const int akb = f_a_wrap_kb ? kb % (f_a_wrap_kb ? f_a_wrap_kb : 1) : kb;
               tma_load_3d(a_dst, &tmA, full_bar(stage), akb * BK, m0, g * f_batch_mul);
             }
           } else {
             const int tap = kb / p.c_blocks;
             int cb = kb - tap * p.c_blocks;
-            if (f_a_cwrap) cb %= f_a_cwrap;
+            if (f_a_cwrap) cb %= (f_a_cwrap ? f_a_cwrap : 1);     // (the ternary only silences the constant-folded '% 0' warning)
             const int r = tap / p.kw;
             const int s = tap - r * p.kw;
             tma_load_im2col_4d(a_dst, &tmA, full_bar(stage), cb * BK, iq * p.stride - p.pad,
