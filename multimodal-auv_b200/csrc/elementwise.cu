@@ -425,7 +425,7 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  double m1 = 0.0;                                         // first moment of channel n0 + tid (tid < 64, row tile 0)
+  double m1 = 0.0;                                         // partial first moment of channel n0 + (tid & 63) (row tile 0)
   for (int c0 = 0; c0 < K; c0 += 64) {
     __syncthreads();
     for (int i = tid; i < 64 * 64; i += 256) {
@@ -448,9 +448,11 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(sr[i], wc[j], acc[i][j]);
     }
-    if (blockIdx.z == 0 && tid < GQ_N) {
-      for (int c = 0; c < 64 && c0 + c < K; ++c)
-        m1 += static_cast<double>(s1[static_cast<long long>(g) * K + c0 + c]) * static_cast<double>(wt[c * GQ_WPITCH + tid]);
+    if (blockIdx.z == 0) {       // first moment: every thread takes 16 of the chunk's 64 columns for channel tid & 63
+      const int nn = tid & 63, part = tid >> 6;
+#pragma unroll 4
+      for (int c = part * 16; c < part * 16 + 16; ++c)
+        if (c0 + c < K) m1 += static_cast<double>(s1[static_cast<long long>(g) * K + c0 + c]) * static_cast<double>(wt[c * GQ_WPITCH + nn]);
     }
   }
   // q_n partial of this thread: its 4 rows
@@ -464,15 +466,18 @@ gram_quadform_kernel(const float* __restrict__ S, const float* __restrict__ s1, 
       if (n < N && r < K) q[j] += static_cast<double>(__half2float(wg[static_cast<long long>(n) * K + r])) * static_cast<double>(acc[i][j]);
     }
   }
+  __shared__ double red1[4][GQ_N];
 #pragma unroll
   for (int j = 0; j < 4; ++j) red[ty][4 * tx + j] = q[j];
+  red1[tid >> 6][tid & 63] = m1;
   __syncthreads();
   if (tid < GQ_N) {
     double qs = 0.0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) qs += red[r][tid];
+    const double ms = (red1[0][tid] + red1[1][tid]) + (red1[2][tid] + red1[3][tid]);
     const int n = n0 + tid;
-    if (n < N) out[(static_cast<long long>(g) * gridDim.z + blockIdx.z) * N + n] = make_double2(m1, qs);
+    if (n < N) out[(static_cast<long long>(g) * gridDim.z + blockIdx.z) * N + n] = make_double2(ms, qs);
   }
 }
 
@@ -787,7 +792,7 @@ int mauv_bn_stats_from_gram(const float* gram_partial, int splits, const float* 
   const long long kk = static_cast<long long>(K) * K;
   dim3 g1(static_cast<unsigned>(ceil_div_i64(kk + K, 32)), G);
   if (splits >= 64) gram_reduce_kernel<8><<<g1, 256, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
-  else gram_reduce_kernel<1><<<g1, 32, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);
+  else gram_reduce_kernel<1><<<g1, 32, 0, st>>>(gram_partial, splits, kk, colsum_partial, nblk, K, S, s1);   // (256-thread blocks of 8 independent warps: 34 -> 83 us)
   MAUV_LAUNCH_CHECK("gram_reduce_kernel");
   const int n_rt = (K + GQ_ROWS - 1) / GQ_ROWS;
   dim3 g2((N + GQ_N - 1) / GQ_N, G, n_rt);
