@@ -183,6 +183,31 @@ def test_bench_roofline_launch_model():
     f, b = bench.tc_launch_model("mauv_conv3x3_c64_f16", "G10 M1048576 N64 K576 stream")
     assert b == 10 * 1048576 * 64 * 2 * 2 + 10 * 64 * 576 * 2
     assert bench.tc_launch_model("mauv_bn_act_f16", "G10 M100 C64 res0 dual0") is None
+    # round 3: the stem kernel (A shared, only the pooled quarter is written), the operand-transform tails, the second moments
+    f, b = bench.tc_launch_model("mauv_stem_conv_pool_f16", "G15 M4194304 N64 K152 pool")
+    assert f == 2.0 * 15 * 4194304 * 64 * 152
+    assert b == 4194304 * 152 * 2 + 15 * 64 * 152 * 2 + 15 * (4194304 // 4) * 64 * 2
+    f, b = bench.tc_launch_model("mauv_gemm_bn_xf_f16", "fused G30 M1048576 N256 K64 res1 xf")
+    assert b == 30 * 1048576 * 64 * 2 + 30 * 256 * 64 * 2 + 2 * 30 * 1048576 * 256 * 2
+    f, b = bench.tc_launch_model("mauv_gram_bn_f16", "G30x256 Cout64 K64 px4096 xf")
+    assert f == 2.0 * 30 * 256 * 64 * 64 * 4096 and b == 30 * 256 * 4096 * 64 * 2 + 30 * 256 * 64 * 64 * 4
+    f, b = bench.tc_launch_model("mauv_gemm_bn_cat_xf_f16", "fused G30 M262144 N512 K384 cat xf")
+    assert f == 2.0 * 30 * 262144 * 512 * 384
+
+
+def test_every_tcgen05_entry_point_is_bound_and_counted_by_the_bench():
+    """bench.py's roofline family is ops.TCGEN05_ENTRY_POINTS: every name must be a bound C-ABI symbol (a kernel left out of
+    the family would inflate the reported fraction: its FLOPs counted, its time not)."""
+    from pathlib import Path
+    from mauv import _lib, ops
+    for name in ops.TCGEN05_ENTRY_POINTS:
+        assert name in _lib.SIGNATURES, name
+    src = (Path(__file__).resolve().parent.parent / "multimodal-auv_b200" / "mauv" / "ops.py").read_text()
+    hot = {"mauv_gemm_f16", "mauv_conv2d_im2col_f16", "mauv_gemm_bn_f16", "mauv_gemm_bn_xf_f16", "mauv_gemm_bn_cat_f16",
+           "mauv_gemm_bn_cat_xf_f16", "mauv_conv3x3_c64_f16", "mauv_wgrad_f16", "mauv_gram_bn_f16", "mauv_stem_conv_pool_f16"}
+    assert hot <= set(ops.TCGEN05_ENTRY_POINTS)
+    for name in hot:
+        assert f'"{name}"' in src
 
 
 # ------------------------------------------------------------------ a10: the product's own dnn_to_bnn + MOPED vs the oracle
