@@ -86,12 +86,15 @@ class _Trunk:
 class MCEngine:
     """Execution plan for a (Bayesian) MultiModalModel or ResNet50Custom living on a CUDA device."""
 
-    def __init__(self, model: nn.Module, max_group: int = 8, precision: Optional[str] = None):
+    def __init__(self, model: nn.Module, max_group: Optional[int] = None, precision: Optional[str] = None):
         _lib.require_device()
         if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
             model = model.module
         self.model = model
+        # samples walked together. None: as many as fit in half of the free device memory (auto_group) - every grouping gives
+        # bit-identical logits, larger groups mean fewer, larger launches (cfg2: 461 / 470 / 475 triplets/s at 10 / 15 / 30)
         self.max_group = max_group
+        self._auto_groups: Dict[tuple, int] = {}
         self.layer_ids: Dict[str, int] = {n: i for i, (n, _) in enumerate(bayesian_layers(model))}
         self._by_module = {id(l): n for n, l in bayesian_layers(model)}
         if hasattr(model, "image_model_feat"):
@@ -144,6 +147,21 @@ class MCEngine:
     @_sample_cursor.setter
     def _sample_cursor(self, v: int) -> None:
         self.model.__dict__["_mauv_sample_cursor"] = int(v) & 0xFFFFFFFF
+
+    def auto_group(self, inputs: Sequence[torch.Tensor], S: int) -> int:
+        """Largest sample group whose live activations fit in half of the free device memory (measured: ~9.8 MB per
+        (sample, triplet) at 256 x 256 in the fp16 plan - one trunk is live at a time -, 2.2x that in the x3 plan); cached per
+        input geometry so that consecutive batches take the same plan."""
+        B, _, H, W = inputs[0].shape
+        key = (B, H, W, S, self.precision)
+        g = self._auto_groups.get(key)
+        if g is None:
+            free, _total = torch.cuda.mem_get_info(self.device)
+            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)   # the allocator's cache
+            per = 9.8e6 * (H * W / 65536.0) * (2.2 if self.precision == "x3" else 1.0)
+            g = max(1, min(S, int(0.5 * free / (B * per))))
+            self._auto_groups[key] = g
+        return g
 
     def take_samples(self, S: int) -> int:
         """-> first id of a fresh block of S sample ids (advances the model's cursor)"""
@@ -461,7 +479,7 @@ class MCEngine:
                    seed: Optional[int] = None, group: Optional[int] = None) -> torch.Tensor:
         """logits [S, B, C] for MC samples sample0 .. sample0+S-1. sample0=None: a fresh block of ids from the model's
         cursor (production); with injected eps (validation) the ids index the eps tensors and default to 0."""
-        G = min(group or self.max_group, S)
+        G = min(group or self.max_group or self.auto_group(inputs, S), S)
         if eps is None:
             eps = DEBUG_EPS
         if sample0 is None:

@@ -46,9 +46,9 @@ def gather_sample_blocks(local: Optional[torch.Tensor], S: int, B: int, C: int, 
 class MCPredictor:
     """H2D -> S-batched MC forward -> MC statistics -> one D2H, for one batch."""
 
-    def __init__(self, model: nn.Module, num_mc_samples: int, group: int = 8, eps_entropy: float = 1e-7,
+    def __init__(self, model: nn.Module, num_mc_samples: int, group: Optional[int] = None, eps_entropy: float = 1e-7,
                  use_graph="auto"):
-        self.engine = MCEngine(model, max_group=group)
+        self.engine = MCEngine(model, max_group=group)      # group None: as many samples per walk as memory allows
         # CUDA graph of this rank's S-pass forward (all sample groups): one replay instead of ~2.4 k Python-driven
         # launches per sample group. Python enqueues ~57 us per launch (414 ms per cfg2 step), which is hidden behind
         # the GPU at B=256 / G=10 (93 us of GPU work per launch) but bounds small batches (cfg1) and the 8-GPU
@@ -112,7 +112,7 @@ class MCPredictor:
 
     def _want_graph(self, B: int, S_local: int) -> bool:
         if self.use_graph == "auto":
-            G = min(self.engine.max_group, S_local)
+            G = min(self.engine.max_group or S_local, S_local)
             return 0.036 * G * B < 60.0          # measured: 93 us GPU time per launch at G=10, B=256; 57 us to enqueue
         return bool(self.use_graph)
 
