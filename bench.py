@@ -557,7 +557,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_FULL)
     ap.add_argument("--samples", type=int, default=S_FULL)
     ap.add_argument("--group", type=int, default=30, help="MC samples walked together (30: one walk of the network per batch; "
-                                                            "~75 GB of live activations at B=256; measured 461 / 470 / 475 triplets/s at 10 / 15 / 30)")
+                                                            "53 GB peak at B=256; measured 461 / 470 / 475 triplets/s at 10 / 15 / 30)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the one-step fp32-class (x3) sub-record")
     ap.add_argument("--no-train-leg", action="store_true", help="skip the cfg3 ELBO training sub-record of the default line")
