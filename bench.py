@@ -229,9 +229,11 @@ def run_ours(args):
 
     # per-kernel breakdown: one extra instrumented step, run eagerly (CUDA events around every C-ABI launch)
     pred.use_graph = False            # profile eagerly: the event pairs cannot be recorded inside a graph replay
+    pred.engine.trunk_streams = False  # ... and one trunk at a time: per-launch times of overlapping streams would count waits
     ops.start_profile()
     step_dev()
     prof = ops.stop_profile()
+    pred.engine.trunk_streams = None
 
     # per-rank view of the instrumented step (strong scaling: which terms shrink with N and which do not)
     fam_local = {}

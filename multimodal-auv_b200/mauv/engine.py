@@ -130,6 +130,7 @@ class MCEngine:
         # stem: conv1 + bn1 statistics + max-pool of the raw output in one kernel (ops.stem_conv_pool_f16): the full-resolution
         # conv1 output never reaches HBM. 256 x 256 inputs (Wo = 128) only; other sizes take the three-kernel path.
         self.stem_pool = os.environ.get("MAUV_STEM_POOL", "1") != "0"
+        self.trunk_streams = None    # None: automatic (see _trunks_in_parallel); True / False force it
         self.stem_colsum = True      # the fused stem's bn_act pass also emits the column sums layer1.0's downsample statistics need
         # bn2 + ReLU of the recompute tails' input applied to the operand tiles in shared memory (second-moment contraction and
         # fused conv3): a2 = relu(bn2(conv2(.))) is never written to / re-read from HBM
@@ -162,6 +163,32 @@ class MCEngine:
             g = max(1, min(S, int(0.5 * free / (B * per))))
             self._auto_groups[key] = g
         return g
+
+    def _trunk_stream(self, i: int) -> torch.cuda.Stream:
+        if not hasattr(self, "_trunk_streams"):
+            self._trunk_streams = [torch.cuda.Stream(self.device) for _ in range(3)]
+        return self._trunk_streams[i]
+
+    def _trunks_in_parallel(self, xs, G: int) -> bool:
+        """Run the three trunks on three streams? MAUV_TRUNK_STREAMS=0|1 forces it; by default when three trunks' live
+        activations (3 x the sequential footprint, see auto_group) fit in half of the free memory AND the group is small
+        enough for the latency-bound launches to matter (G <= 8)."""
+        if self.trunk_streams is not None:
+            return bool(self.trunk_streams)
+        mode = os.environ.get("MAUV_TRUNK_STREAMS", "auto")
+        if mode in ("0", "1"):
+            return mode == "1"
+        if self.precision != "fp16" or G > 8:
+            return False
+        B, _, H, W = xs[0].shape
+        key = ("par", B, H, W, G)
+        ok = self._auto_groups.get(key)
+        if ok is None:
+            free, _total = torch.cuda.mem_get_info(self.device)
+            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            ok = int(3 * B * G * 9.8e6 * (H * W / 65536.0) <= 0.5 * free)
+            self._auto_groups[key] = ok
+        return bool(ok)
 
     def take_samples(self, S: int) -> int:
         """-> first id of a fresh block of S sample ids (advances the model's cursor)"""
@@ -466,10 +493,33 @@ class MCEngine:
             return self._linear(fc, name, feat, G, sample0, eps, seed)
         m = self.model
         concat = torch.empty((G, B, 384), dtype=F32, device=self.device)
-        for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn,
-                                                  ("attention_image", "attention_bathy", "attention_sss"))):
-            feat = self._run_trunk(t, x, G, sample0, eps, seed, None if stems is None else stems[i])
-            self._attention(attn, pre, feat, G, sample0, eps, seed, concat, 128 * i)
+        names = ("attention_image", "attention_bathy", "attention_sss")
+        if self._trunks_in_parallel(xs, G):
+            # The three trunks are independent until the fusion head: each runs on its own stream (forked from / joined to the
+            # caller's stream with events, also inside a CUDA-graph capture), so the ~300 latency-bound launches per trunk (BN
+            # finalize, closed-form evaluation, sampling, head projections) and the tails of under-filled kernels overlap with
+            # another trunk's work. Same kernels, same order per trunk: bit-identical results. Needs three trunks' activations
+            # live at once, so it is taken for small sample groups (the 4- and 8-GPU shards) only.
+            main = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            joins = []
+            for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn, names)):
+                side = self._trunk_stream(i)
+                side.wait_event(fork)
+                with torch.cuda.stream(side), ops.on_current_stream():
+                    feat = self._run_trunk(t, x, G, sample0, eps, seed, None if stems is None else stems[i])
+                    self._attention(attn, pre, feat, G, sample0, eps, seed, concat, 128 * i)
+                    del feat
+                    done = torch.cuda.Event()
+                    done.record(side)
+                joins.append(done)
+            for done in joins:
+                main.wait_event(done)
+        else:
+            for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn, names)):
+                feat = self._run_trunk(t, x, G, sample0, eps, seed, None if stems is None else stems[i])
+                self._attention(attn, pre, feat, G, sample0, eps, seed, concat, 128 * i)
         h = self._linear(m.fc, "fc", concat, G, sample0, eps, seed)
         h = self._linear(m.fc1, "fc1", h, G, sample0, eps, seed)
         return self._linear(m.fc2, "fc2", h, G, sample0, eps, seed)

@@ -274,3 +274,30 @@ def test_head_linear_128_row_tiles_equal_the_32_row_tiles(bu, G, B, fin, fout, b
     w = mu.double() + torch.log1p(torch.exp(rho.double())) * eps.double()
     ref = torch.einsum("gbi,goi->gbo", x.double(), w)
     assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-5
+
+
+def test_three_trunks_on_three_streams_give_bit_identical_logits(bu):
+    """MCEngine with the trunks forked onto three streams (the plan of the small sample groups at 4 / 8 GPUs) against the
+    sequential walk, eagerly and inside a CUDA-graph replay of the predictor: torch.equal."""
+    import bnn_oracle as O
+    from mauv.engine import MCEngine
+    from mauv.inference.predictors import MCPredictor
+    _, model = bu.build_pair("multimodal")
+    img, bathy, sss, _ = O.synthetic_batch(3, size=256)
+    xs = [t.cuda() for t in (img, bathy, sss)]
+    eng = MCEngine(model)
+    eng.trunk_streams = False
+    seq = eng.forward_mc(xs, 4, seed=21, group=4, sample0=0)
+    eng.trunk_streams = True
+    par = eng.forward_mc(xs, 4, seed=21, group=4, sample0=0)
+    torch.cuda.synchronize()
+    assert torch.equal(par, seq)
+    assert torch.equal(eng.forward_mc(xs, 4, seed=21, group=2, sample0=0), seq)
+    pred = MCPredictor(model, 4, use_graph=True)
+    pred.engine.trunk_streams = True
+    from mauv.bayesian import manual_seed
+    manual_seed(21)
+    a = pred.mc_logits(xs, sample0=0)            # records the graph (after an eager warm-up), then replays
+    b = pred.mc_logits(xs, sample0=0)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, seq)
