@@ -161,6 +161,13 @@ class TrainEngine(MCEngine):
         rec.HW = x.shape[1] * x.shape[2]
         return rec, ops.avgpool_f16(x).view(G, B, -1)
 
+    def _train_trunks_parallel(self) -> bool:
+        if self.kind != "multimodal":
+            return False
+        if self.trunk_streams is not None:
+            return bool(self.trunk_streams)
+        return os.environ.get("MAUV_TRUNK_STREAMS", "1") != "0"
+
     def _lin(self, layer, name, x, G, s0, eps, seed, out=None, out_col=0):
         return self._linear(layer, name, x, G, s0, eps, seed, out=out, out_col=out_col)
 
@@ -175,18 +182,39 @@ class TrainEngine(MCEngine):
         m = self.model
         concat = torch.empty((G, B, 384), dtype=F32, device=self.device)
         tape = {"trunks": [], "feat": [], "attn": [], "concat": concat}
+        # The three trunks are independent until the fusion head: each runs on its own stream (forked from / joined to the
+        # caller's stream; also inside the CUDA-graph capture of the step). A training step is ~2 300 launches over only
+        # B x S = 240 images - most of them latency-bound or under-filled - so another trunk's kernels fill the gaps; the tape
+        # holds all three trunks' activations anyway, so this costs no memory. Same kernels in the same order per trunk:
+        # bit-identical losses and gradients.
+        par = self._train_trunks_parallel()
+        main = torch.cuda.current_stream(self.device)
+        if par:
+            fork = torch.cuda.Event()
+            fork.record(main)
+        joins = []
         for i, (t, x, attn, pre) in enumerate(zip(self.trunks, xs, self.attn,
                                                   ("attention_image", "attention_bathy", "attention_sss"))):
-            rec, feat = self._trunk_forward(t, x, G, s0, eps, seed)
-            k = self._lin(attn.key_projection, pre + ".key_projection", feat, G, s0, eps, seed)
-            v = self._lin(attn.value_projection, pre + ".value_projection", feat, G, s0, eps, seed)
-            q = self._lin(attn.query_projection, pre + ".query_projection", feat, G, s0, eps, seed)
-            th = ops.tanh_add_f32(q, k)
-            sc = self._lin(attn.attention_mechanism, pre + ".attention_mechanism", th, G, s0, eps, seed)
-            ops.softmax_gate_f32(sc, v, concat, 128 * i)
+            side = self._trunk_stream(i) if par else main
+            if par:
+                side.wait_event(fork)
+            with torch.cuda.stream(side), ops.on_current_stream():
+                rec, feat = self._trunk_forward(t, x, G, s0, eps, seed)
+                k = self._lin(attn.key_projection, pre + ".key_projection", feat, G, s0, eps, seed)
+                v = self._lin(attn.value_projection, pre + ".value_projection", feat, G, s0, eps, seed)
+                q = self._lin(attn.query_projection, pre + ".query_projection", feat, G, s0, eps, seed)
+                th = ops.tanh_add_f32(q, k)
+                sc = self._lin(attn.attention_mechanism, pre + ".attention_mechanism", th, G, s0, eps, seed)
+                ops.softmax_gate_f32(sc, v, concat, 128 * i)
+                if par:
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    joins.append(done)
             tape["trunks"].append(rec)
             tape["feat"].append(feat)
             tape["attn"].append((th, sc, v))
+        for done in joins:
+            main.wait_event(done)
         h1 = self._lin(m.fc, "fc", concat, G, s0, eps, seed)
         h2 = self._lin(m.fc1, "fc1", h1, G, s0, eps, seed)
         tape["h1"], tape["h2"] = h1, h2
@@ -308,19 +336,36 @@ class TrainEngine(MCEngine):
         dh2 = self._lin_bwd(m.fc2, "fc2", tape["h2"], dlogits, G, s0, eps, seed, stale)
         dh1 = self._lin_bwd(m.fc1, "fc1", tape["h1"], dh2, G, s0, eps, seed, stale)
         dcat = self._lin_bwd(m.fc, "fc", tape["concat"], dh1, G, s0, eps, seed, stale)
+        par = self._train_trunks_parallel()       # each trunk's backward on the stream its forward ran on (see _forward_group)
+        main = torch.cuda.current_stream(self.device)
+        if par:
+            fork = torch.cuda.Event()
+            fork.record(main)
+        joins = []
         for i, (attn, pre) in enumerate(zip(self.attn, ("attention_image", "attention_bathy", "attention_sss"))):
-            th, sc, v = tape["attn"][i]
-            feat = tape["feat"][i]
-            dsc, dv = ops.softmax_gate_bwd_f32(sc, v, dcat[:, :, 128 * i:128 * (i + 1)])
-            dt = self._lin_bwd(attn.attention_mechanism, pre + ".attention_mechanism", th, dsc, G, s0, eps, seed, stale)
-            dqk = ops.tanh_bwd_f32(th, dt)
-            dfeat = self._lin_bwd(attn.key_projection, pre + ".key_projection", feat, dqk, G, s0, eps, seed, stale)
-            self._lin_bwd(attn.query_projection, pre + ".query_projection", feat, dqk, G, s0, eps, seed, stale,
-                          gx=dfeat, accumulate=True)
-            self._lin_bwd(attn.value_projection, pre + ".value_projection", feat, dv, G, s0, eps, seed, stale,
-                          gx=dfeat, accumulate=True)
-            self._trunk_backward(tape["trunks"][i], dfeat.view(G * B, -1), G, s0, eps, seed, stale, gs)
-            tape["trunks"][i] = None          # free this trunk's activations
+            side = self._trunk_stream(i) if par else main
+            if par:
+                side.wait_event(fork)
+            with torch.cuda.stream(side), ops.on_current_stream():
+                th, sc, v = tape["attn"][i]
+                feat = tape["feat"][i]
+                dsc, dv = ops.softmax_gate_bwd_f32(sc, v, dcat[:, :, 128 * i:128 * (i + 1)])
+                dt = self._lin_bwd(attn.attention_mechanism, pre + ".attention_mechanism", th, dsc, G, s0, eps, seed, stale)
+                dqk = ops.tanh_bwd_f32(th, dt)
+                dfeat = self._lin_bwd(attn.key_projection, pre + ".key_projection", feat, dqk, G, s0, eps, seed, stale)
+                self._lin_bwd(attn.query_projection, pre + ".query_projection", feat, dqk, G, s0, eps, seed, stale,
+                              gx=dfeat, accumulate=True)
+                self._lin_bwd(attn.value_projection, pre + ".value_projection", feat, dv, G, s0, eps, seed, stale,
+                              gx=dfeat, accumulate=True)
+                self._trunk_backward(tape["trunks"][i], dfeat.view(G * B, -1), G, s0, eps, seed, stale, gs)
+                tape["trunks"][i] = None          # free this trunk's activations
+                del th, sc, v, feat, dsc, dv, dt, dqk, dfeat
+                if par:
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    joins.append(done)
+        for done in joins:
+            main.wait_event(done)
 
     # ------------------------------------------------------------------ public
     def flatten_grads(self) -> torch.Tensor:

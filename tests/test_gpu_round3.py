@@ -301,3 +301,48 @@ def test_three_trunks_on_three_streams_give_bit_identical_logits(bu):
     b = pred.mc_logits(xs, sample0=0)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, seq)
+
+
+def test_train_step_with_trunks_on_three_streams_is_bit_identical(bu):
+    """TrainEngine.step of the multimodal net with the three trunks (forward AND backward) on three streams against the
+    sequential walk: loss, every gradient and the BN running statistics torch.equal - eagerly and as a recorded CUDA graph."""
+    import bnn_oracle as O
+    from mauv.bayesian import manual_seed
+    from mauv.train_engine import TrainEngine
+    _, model = bu.build_pair("multimodal")
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    batches = [O.synthetic_batch(2, seed=70 + i, size=64) for i in range(3)]
+    manual_seed(13)
+
+    def run(eng, i, sample0):
+        model.load_state_dict(state0)
+        for p in model.parameters():
+            if p.grad is not None:
+                p.grad.zero_()
+        img, bathy, sss, labels = batches[i]
+        res = eng.step([img.cuda(), bathy.cuda(), sss.cuda()], labels, 3, 1e-4, sample0=sample0)
+        torch.cuda.synchronize()
+        return ({n: p.grad.clone() for n, p in model.named_parameters()}, res["loss"].item(),
+                {k: v.clone() for k, v in model.state_dict().items() if "running" in k})
+
+    seq = TrainEngine(model)
+    seq.use_graph = False
+    seq.trunk_streams = False
+    ref = run(seq, 2, 7)
+    par = TrainEngine(model)
+    par.use_graph = False
+    par.trunk_streams = True
+    got = run(par, 2, 7)
+    assert got[1] == ref[1]
+    for n in ref[0]:
+        assert torch.equal(got[0][n], ref[0][n]), n
+    for k in ref[2]:
+        assert torch.equal(got[2][k], ref[2][k]), k
+    gr = TrainEngine(model)              # default: trunk streams on, graph replay from the third call
+    assert gr.use_graph and gr._train_trunks_parallel()
+    run(gr, 0, 3)
+    run(gr, 1, 5)
+    got = run(gr, 2, 7)
+    assert got[1] == ref[1]
+    for n in ref[0]:
+        assert torch.equal(got[0][n], ref[0][n]), n
